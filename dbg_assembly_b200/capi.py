@@ -1,0 +1,162 @@
+"""ctypes binding of libdbgb200.so (include/dbg_b200.h).  Plumbing only: every compute call goes to the
+CUDA library; there is no Python/NumPy fallback.  Importing this module without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libdbgb200.so")
+
+DBG_OK = 0
+DBG_ERR_INVALID, DBG_ERR_CUDA, DBG_ERR_NOMEM, DBG_ERR_TABLE_FULL, DBG_ERR_STATE, DBG_ERR_BUFFER = -1, -2, -3, -4, -5, -6
+
+
+class DbgError(RuntimeError):
+    def __init__(self, code, where, detail=""):
+        self.code = code
+        super().__init__(f"{where}: {_strerror(code)} ({code}) {detail}".strip())
+
+
+class dbg_params(C.Structure):
+    _fields_ = [("K", C.c_int32), ("max_read_len", C.c_int32), ("init_slots", C.c_uint64),
+                ("load_factor", C.c_float), ("device", C.c_int32), ("track_order", C.c_int32),
+                ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("force_wide", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+class dbg_stats(C.Structure):
+    _fields_ = [("array_size", C.c_uint64), ("max_cutoff", C.c_uint64), ("count", C.c_uint64),
+                ("conflict", C.c_uint64), ("reads", C.c_uint64), ("kmers_logged", C.c_uint64),
+                ("occurrences", C.c_uint64), ("polyA_l", C.c_uint64), ("polyA_r", C.c_uint64),
+                ("shard_lo", C.c_uint64), ("shard_hi", C.c_uint64), ("load_factor", C.c_float), ("wide", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class dbg_synth_params(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32), ("insert", C.c_uint32),
+                ("err_per_2p24", C.c_uint32), ("n_per_2p24", C.c_uint32)]
+
+
+class kfreq_params(C.Structure):
+    _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("block_rank", C.c_int32), ("block_count", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+# every symbol include/dbg_b200.h declares; tests check that the library exports all of them
+SYMBOLS = [
+    "dbg_find_next_prime", "dbg_hash_code", "dbg_hash_code_wide", "dbg_strerror", "dbg_last_error",
+    "dbg_device_count", "dbg_host_alloc", "dbg_host_free", "dbg_create", "dbg_destroy", "dbg_submit_reads",
+    "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
+    "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
+    "dbg_export_links", "dbg_dump_compact", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
+    "dbg_reset", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
+]
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """Load libdbgb200.so (building it in-tree with nvcc if it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m dbg_assembly_b200.csrc.build`")
+        from .csrc import build as _b
+        _b.build()
+    L = C.CDLL(LIB_PATH)
+    u64, i32, vp = C.c_uint64, C.c_int32, C.c_void_p
+    sig = {
+        "dbg_find_next_prime": (u64, [u64]),
+        "dbg_hash_code": (u64, [u64]),
+        "dbg_hash_code_wide": (u64, [u64, u64]),
+        "dbg_strerror": (C.c_char_p, [C.c_int]),
+        "dbg_last_error": (C.c_char_p, []),
+        "dbg_device_count": (C.c_int, []),
+        "dbg_host_alloc": (C.c_int, [C.POINTER(vp), u64]),
+        "dbg_host_free": (C.c_int, [vp]),
+        "dbg_create": (C.c_int, [C.POINTER(vp), C.POINTER(dbg_params)]),
+        "dbg_destroy": (None, [vp]),
+        "dbg_submit_reads": (C.c_int, [vp, vp, vp, u64]),
+        "dbg_submit_reads_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, vp]),
+        "dbg_extract_tuples_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, i32, vp, u64, vp, vp]),
+        "dbg_insert_tuples_device": (C.c_int, [vp, vp, u64, vp]),
+        "dbg_tuple_bytes": (C.c_int, [vp]),
+        "dbg_get_polyA_counts": (C.c_int, [vp, vp]),
+        "dbg_set_polyA_counts": (C.c_int, [vp, vp]),
+        "dbg_finalize": (C.c_int, [vp, C.POINTER(dbg_stats)]),
+        "dbg_get_stats": (C.c_int, [vp, C.POINTER(dbg_stats)]),
+        "dbg_export_kmerset": (C.c_int, [vp, vp, vp]),
+        "dbg_export_links": (C.c_int, [vp, i32, vp, vp, vp, vp, C.POINTER(u64), vp, C.POINTER(u64), vp]),
+        "dbg_dump_compact": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, C.POINTER(u64)]),
+        "dbg_device_image": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "dbg_get_timings": (C.c_int, [vp, vp]),
+        "dbg_launch_count": (u64, [vp]),
+        "dbg_reset": (C.c_int, [vp]),
+        "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),
+        "dbg_synth_reads_device": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp, i32, vp]),
+        "dbg_measure_random_rmw": (C.c_int, [i32, u64, u64, i32, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _strerror(code):
+    try:
+        return load().dbg_strerror(code).decode()
+    except Exception:
+        return "error"
+
+
+def check(code, where):
+    if code != DBG_OK:
+        raise DbgError(code, where, load().dbg_last_error().decode())
+
+
+def device_count() -> int:
+    return int(load().dbg_device_count())
+
+
+def find_next_prime(n: int) -> int:
+    return int(load().dbg_find_next_prime(int(n)))
+
+
+def hash_code(k: int) -> int:
+    return int(load().dbg_hash_code(int(k)))
+
+
+def hash_code_wide(lo: int, hi: int) -> int:
+    return int(load().dbg_hash_code_wide(int(lo), int(hi)))
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'ed bytes exposed as a numpy array (front ends decode reads straight into it)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(load().dbg_host_alloc(C.byref(self.ptr), int(nbytes)), "dbg_host_alloc")
+        self.nbytes = int(nbytes)
+        self.array = np.frombuffer((C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr.value), dtype=np.uint8,
+                                   count=self.nbytes)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            load().dbg_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,753 @@
+// dbg_build.cu -- host side of libdbgb200.so: context, streams, staging and the extern "C" entry
+// points declared in include/dbg_b200.h.  The kernels live in dbg_kernels.cuh.
+//
+// There is no CPU fallback in this file: every entry point that computes launches sm_100a kernels, and
+// dbg_create fails with DBG_ERR_CUDA when no device is available.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dbg_b200.h"
+#include "dbg_kernels.cuh"
+
+using namespace dbg;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? DBG_ERR_NOMEM : DBG_ERR_CUDA;          \
+            return set_err(code_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                         \
+    } while (0)
+
+extern "C" const char *dbg_strerror(int code)
+{
+    switch (code) {
+    case DBG_OK: return "ok";
+    case DBG_ERR_INVALID: return "invalid argument";
+    case DBG_ERR_CUDA: return "CUDA error";
+    case DBG_ERR_NOMEM: return "out of memory";
+    case DBG_ERR_TABLE_FULL: return "k-mer table full (the reference would enlarge; raise -i)";
+    case DBG_ERR_STATE: return "call order violated";
+    case DBG_ERR_BUFFER: return "output buffer too small";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *dbg_last_error(void) { return g_err; }
+
+extern "C" int dbg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scalar helpers, bit-identical to the reference
+// ---------------------------------------------------------------------------------------------------
+// kmerSet.cpp:72-82: trial division up to (uint64)sqrt((float)num), EXCLUSIVE -- float rounding and the
+// `<` make some composites pass; table sizes must match the reference, so the quirk is kept.
+static int ref_is_prime(uint64_t num)
+{
+    if (num < 4) return 1;
+    if (num % 2 == 0) return 0;
+    uint64_t max = (uint64_t)sqrtf((float)num);
+    for (uint64_t i = 3; i < max; i += 2)
+        if (num % i == 0) return 0;
+    return 1;
+}
+
+extern "C" uint64_t dbg_find_next_prime(uint64_t num)   // kmerSet.cpp:86-95
+{
+    if (num % 2 == 0) num++;
+    while (!ref_is_prime(num)) num += 2;
+    return num;
+}
+
+extern "C" uint64_t dbg_hash_code(uint64_t kmer) { return hash_code(kmer); }
+extern "C" uint64_t dbg_hash_code_wide(uint64_t lo, uint64_t hi) { return hash_code_wide(lo, hi); }
+
+extern "C" int dbg_host_alloc(void **p, uint64_t bytes)
+{
+    if (!p) return set_err(DBG_ERR_INVALID, "dbg_host_alloc: NULL");
+    CU_TRY(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return DBG_OK;
+}
+
+extern "C" int dbg_host_free(void *p)
+{
+    if (p) CU_TRY(cudaFreeHost(p));
+    return DBG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+static const uint64_t SUB_BASES = 64ull << 20;   // host submit is cut into sub-blocks so copies overlap kernels
+static const uint64_t SUB_READS = 2ull << 20;
+static const uint64_t MARGIN_SLOTS = 1ull << 16; // overflow zone past a shard's home range (no wrap in the hot loop)
+
+struct EvPair { cudaEvent_t a, b; };
+
+struct dbg_ctx {
+    dbg_params prm;
+    bool wide, track;
+    int device;
+    uint64_t P, M, max_cutoff;
+    float lf;
+    uint64_t shard_lo, shard_hi, shard_size, n_local;
+    int n_shards;
+    cudaStream_t stream, copy_stream;
+    Node *d_nodes;
+    u64 *d_counters, *d_polyA;
+    // host-submit staging (double buffered)
+    char *d_bases[2];
+    u64 *d_offs[2];
+    uint64_t cap_bases, cap_reads;
+    cudaEvent_t ev_free[2];
+    int cur;
+    u64 *d_chunk_first;
+    uint64_t cap_chunks;
+    // finalize / export
+    bool finalized;
+    u64 *d_owner;
+    void *d_out;
+    u32 *d_nul32;
+    u64 polyA_links;
+    // links scratch
+    unsigned short *d_klink;
+    u32 *d_del32, *d_tile_counts;
+    u64 *d_tile_offs, *d_small;   // d_small: hist[256] + stats3[3] + totals[4]
+    int links_cutoff;             // cutoff the scratch currently reflects (INT32_MIN = none)
+    // bookkeeping
+    uint64_t reads_total, next_read_index, launches;
+    dbg_stats st;
+    std::vector<EvPair> build_ev;
+    float ms[8];
+};
+
+static int node_bytes(const dbg_ctx *c) { return c->wide ? 32 : 16; }
+
+static TableView view_of(dbg_ctx *c)
+{
+    TableView t;
+    t.nodes = c->d_nodes; t.P = c->P; t.M = c->M; t.lo = c->shard_lo; t.n_local = c->n_local;
+    t.counters = c->d_counters; t.polyA = c->d_polyA;
+    return t;
+}
+
+static int ev_begin(dbg_ctx *c, cudaStream_t s, EvPair *p)
+{
+    CU_TRY(cudaEventCreate(&p->a));
+    CU_TRY(cudaEventCreate(&p->b));
+    CU_TRY(cudaEventRecord(p->a, s));
+    return DBG_OK;
+}
+
+static void free_finalize_buffers(dbg_ctx *c)
+{
+    cudaFree(c->d_owner); cudaFree(c->d_out); cudaFree(c->d_nul32);
+    cudaFree(c->d_klink); cudaFree(c->d_del32); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offs); cudaFree(c->d_small);
+    c->d_owner = nullptr; c->d_out = nullptr; c->d_nul32 = nullptr;
+    c->d_klink = nullptr; c->d_del32 = nullptr; c->d_tile_counts = nullptr; c->d_tile_offs = nullptr; c->d_small = nullptr;
+    c->links_cutoff = INT32_MIN;
+}
+
+extern "C" void dbg_destroy(dbg_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_finalize_buffers(c);
+    for (auto &e : c->build_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_bases[i]); cudaFree(c->d_offs[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+static int clear_table(dbg_ctx *c)
+{
+    EvPair e;
+    int rc = ev_begin(c, c->stream, &e);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(c->d_nodes, 0, c->n_local * sizeof(Node), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(u64), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_polyA, 0, 8 * sizeof(u64), c->stream));
+    CU_TRY(cudaEventRecord(e.b, c->stream));
+    CU_TRY(cudaEventSynchronize(e.b));
+    CU_TRY(cudaEventElapsedTime(&c->ms[0], e.a, e.b));
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    return DBG_OK;
+}
+
+extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
+{
+    if (!out || !p) return set_err(DBG_ERR_INVALID, "dbg_create: NULL argument");
+    *out = nullptr;
+    if (p->K < 1 || p->K > 63) return set_err(DBG_ERR_INVALID, "K=%d outside 1..63", p->K);
+    if (p->max_read_len < 1 || p->max_read_len > 65535) return set_err(DBG_ERR_INVALID, "max_read_len=%d outside 1..65535", p->max_read_len);
+    int n_shards = p->shard_count > 1 ? p->shard_count : 1;
+    if (p->shard_rank < 0 || p->shard_rank >= n_shards) return set_err(DBG_ERR_INVALID, "shard_rank %d / %d", p->shard_rank, n_shards);
+    int ndev = dbg_device_count();
+    if (ndev == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible: libdbgb200 has no CPU fallback");
+    if (p->device < 0 || p->device >= ndev) return set_err(DBG_ERR_INVALID, "device %d of %d", p->device, ndev);
+    CU_TRY(cudaSetDevice(p->device));
+
+    dbg_ctx *c = new dbg_ctx();
+    memset(&c->st, 0, sizeof(c->st));
+    c->prm = *p;
+    c->wide = p->K > 31 || p->force_wide;
+    c->track = p->track_order != 0;
+    c->device = p->device;
+    // init_kmerset_parallel, kmerSet.cpp:98-115
+    uint64_t size = p->init_slots < 3 ? 3 : dbg_find_next_prime(p->init_slots);
+    float lf = p->load_factor;
+    if (lf <= 0) lf = 0.25f; else if (lf >= 1) lf = 0.75f;
+    c->P = size; c->lf = lf;
+    c->max_cutoff = (uint64_t)(size * lf);            // uint64 * float -> float, as in the reference
+    c->M = (uint64_t)((((unsigned __int128)1) << 64) / size);
+    c->n_shards = n_shards;
+    c->shard_size = (size + n_shards - 1) / n_shards;
+    c->shard_lo = (uint64_t)p->shard_rank * c->shard_size;
+    if (c->shard_lo > size) c->shard_lo = size;
+    c->shard_hi = c->shard_lo + c->shard_size < size ? c->shard_lo + c->shard_size : size;
+    c->n_local = (c->shard_hi - c->shard_lo) + MARGIN_SLOTS;
+    c->links_cutoff = INT32_MIN;
+    *out = c;   // from here on the caller can dbg_destroy() after a failure
+
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * sizeof(Node)));
+    CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
+    return clear_table(c);
+}
+
+extern "C" int dbg_reset(dbg_ctx *c)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    for (auto &e : c->build_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    c->build_ev.clear();
+    c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
+    c->links_cutoff = INT32_MIN;
+    for (int i = 1; i < 8; i++) c->ms[i] = 0;
+    return clear_table(c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// build: launch helpers
+// ---------------------------------------------------------------------------------------------------
+static uint32_t stage_words_for(int R) { return (uint32_t)((CB + ((R + 15) / 16) * 16) / 16 + 8); }
+static size_t build_smem(uint32_t stage_words) { return (size_t)(stage_words + MAXR + MAXR + 1) * sizeof(u32); }
+
+static int ensure_chunks(dbg_ctx *c, uint64_t n_chunks)
+{
+    if (n_chunks + 1 <= c->cap_chunks) return DBG_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_chunk_first);
+    c->d_chunk_first = nullptr;
+    c->cap_chunks = n_chunks + 1 + n_chunks / 4;
+    CU_TRY(cudaMalloc(&c->d_chunk_first, c->cap_chunks * sizeof(u64)));
+    return DBG_OK;
+}
+
+template <bool WIDE, class Sink>
+static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_chunks, cudaStream_t s)
+{
+    size_t smem = build_smem(a.stage_words);
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_build<WIDE, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_build<WIDE, Sink><<<(unsigned)n_chunks, BLOCK, smem, s>>>(a, sink);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return DBG_OK;
+}
+
+// d_bases: pointer such that d_bases[off] is base `off` of the global offset space
+static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint64_t n_reads, uint64_t first_base,
+                        uint64_t total_bases, uint64_t read_index0, cudaStream_t s,
+                        int n_parts, void *d_tuples, uint64_t bucket_stride, u64 *d_counts)
+{
+    if (n_reads == 0 || total_bases == 0) return DBG_OK;
+    uint64_t abase = first_base & ~15ull;
+    if (((uintptr_t)(d_bases + abase) & 15) != 0) return set_err(DBG_ERR_INVALID, "device base buffer must be 16-byte aligned");
+    uint64_t n_chunks = (first_base + total_bases - abase + CB - 1) / CB;
+    if (n_chunks > 0x7fffffffull) return set_err(DBG_ERR_INVALID, "block too large: %llu chunks", (unsigned long long)n_chunks);
+    int rc = ensure_chunks(c, n_chunks);
+    if (rc) return rc;
+
+    EvPair ev;
+    rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    unsigned gb = (unsigned)((n_reads + 1 + 255) / 256);
+    k_chunk_first<<<gb, 256, 0, s>>>(d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+
+    BuildArgs a;
+    a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
+    a.chunk_first = c->d_chunk_first; a.read_index0 = read_index0; a.K = c->prm.K; a.R = c->prm.max_read_len;
+    a.stage_words = stage_words_for(c->prm.max_read_len);
+
+    if (n_parts > 0) {
+        if (c->wide) {
+            BucketSink<true> sk; sk.t = view_of(c); sk.shard_size = (c->P + n_parts - 1) / n_parts; sk.n_parts = n_parts;
+            sk.tuples = (u64 *)d_tuples; sk.bucket_stride = bucket_stride; sk.counts = d_counts;
+            rc = launch_build<true>(c, a, sk, n_chunks, s);
+        } else {
+            BucketSink<false> sk; sk.t = view_of(c); sk.shard_size = (c->P + n_parts - 1) / n_parts; sk.n_parts = n_parts;
+            sk.tuples = (u64 *)d_tuples; sk.bucket_stride = bucket_stride; sk.counts = d_counts;
+            rc = launch_build<false>(c, a, sk, n_chunks, s);
+        }
+    } else if (c->wide) {
+        if (c->track) { InsertSink<true, true> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
+        else { InsertSink<true, false> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
+    } else {
+        if (c->track) { InsertSink<false, true> sk; sk.t = view_of(c); rc = launch_build<false>(c, a, sk, n_chunks, s); }
+        else { InsertSink<false, false> sk; sk.t = view_of(c); rc = launch_build<false>(c, a, sk, n_chunks, s); }
+    }
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+static int ensure_staging(dbg_ctx *c, uint64_t bases, uint64_t reads)
+{
+    if (bases <= c->cap_bases && reads <= c->cap_reads && c->d_bases[0]) return DBG_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    uint64_t nb = bases > c->cap_bases ? bases : c->cap_bases;
+    uint64_t nr = reads > c->cap_reads ? reads : c->cap_reads;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_bases[i]); cudaFree(c->d_offs[i]);
+        c->d_bases[i] = nullptr; c->d_offs[i] = nullptr;
+        CU_TRY(cudaMalloc(&c->d_bases[i], nb + 64));
+        CU_TRY(cudaMalloc(&c->d_offs[i], (nr + 1) * sizeof(u64)));
+        if (!c->ev_free[i]) CU_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+    c->cap_bases = nb; c->cap_reads = nr;
+    return DBG_OK;
+}
+
+extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
+{
+    if (!c || (!bases && n_reads) || (!offs && n_reads)) return set_err(DBG_ERR_INVALID, "dbg_submit_reads: NULL argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
+    if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        // cut a sub-block: at most SUB_BASES bases / SUB_READS reads (at least one read)
+        uint64_t r1 = r0 + 1;
+        {
+            uint64_t lim = r0 + SUB_READS < n_reads ? r0 + SUB_READS : n_reads;
+            // binary search for the last r1 <= lim with offs[r1]-offs[r0] <= SUB_BASES
+            uint64_t lo = r0 + 1, hi = lim;
+            while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offs[mid] - offs[r0] <= SUB_BASES) lo = mid; else hi = mid - 1; }
+            r1 = lo;
+        }
+        uint64_t nb = offs[r1] - offs[r0], nr = r1 - r0;
+        if (offs[r1] < offs[r0]) return set_err(DBG_ERR_INVALID, "offsets must be non-decreasing");
+        int rc = ensure_staging(c, (nb > SUB_BASES ? nb : SUB_BASES) + 16, nr > SUB_READS ? nr : SUB_READS);
+        if (rc) return rc;
+        int b = c->cur; c->cur ^= 1;
+        // wait until the kernels that last read buffer b are done, then copy on the copy stream
+        CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+        uint64_t pad = offs[r0] & 15;
+        EvPair ev;
+        rc = ev_begin(c, c->copy_stream, &ev);
+        if (rc) return rc;
+        if (nb) CU_TRY(cudaMemcpyAsync(c->d_bases[b] + pad, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->copy_stream));
+        CU_TRY(cudaMemcpyAsync(c->d_offs[b], offs + r0, (nr + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->copy_stream));
+        CU_TRY(cudaEventRecord(ev.b, c->copy_stream));
+        CU_TRY(cudaEventSynchronize(ev.b));          // host buffer is reusable from here on
+        float t = 0; CU_TRY(cudaEventElapsedTime(&t, ev.a, ev.b)); c->ms[4] += t;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+        const char *virt = c->d_bases[b] + pad - offs[r0];
+        rc = build_device(c, virt, c->d_offs[b], nr, offs[r0], nb, c->next_read_index, c->stream, 0, nullptr, 0, nullptr);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(c->ev_free[b], c->stream));
+        c->next_read_index += nr; c->reads_total += nr;
+        r0 = r1;
+    }
+    return DBG_OK;
+}
+
+extern "C" int dbg_submit_reads_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                                       uint64_t first_base, uint64_t total_bases, uint64_t first_read_index, void *stream)
+{
+    if (!c || (!d_bases && n_reads) || (!d_offs && n_reads)) return set_err(DBG_ERR_INVALID, "dbg_submit_reads_device: NULL argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
+    if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t idx0 = first_read_index == UINT64_MAX ? c->next_read_index : first_read_index;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    int rc = build_device(c, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, idx0, s, 0, nullptr, 0, nullptr);
+    if (rc) return rc;
+    c->next_read_index = idx0 + n_reads; c->reads_total += n_reads;
+    return DBG_OK;
+}
+
+extern "C" int dbg_tuple_bytes(const dbg_ctx *c) { return c ? (c->wide ? 32 : 16) : 0; }
+
+extern "C" int dbg_extract_tuples_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                                         uint64_t first_base, uint64_t total_bases, uint64_t first_read_index,
+                                         int32_t n_parts, void *d_tuples, uint64_t bucket_stride, uint64_t *d_counts, void *stream)
+{
+    if (!c || !d_tuples || !d_counts || n_parts < 1 || n_parts > 64) return set_err(DBG_ERR_INVALID, "dbg_extract_tuples_device: bad argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemsetAsync(d_counts, 0, n_parts * sizeof(u64), s));
+    int rc = build_device(c, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, first_read_index, s,
+                          n_parts, d_tuples, bucket_stride, (u64 *)d_counts);
+    if (rc) return rc;
+    c->reads_total += n_reads;
+    return DBG_OK;
+}
+
+extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64_t n, void *stream)
+{
+    if (!c || (!d_tuples && n)) return set_err(DBG_ERR_INVALID, "dbg_insert_tuples_device: NULL argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
+    if (n == 0) return DBG_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    EvPair ev;
+    int rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    uint64_t blocks = (n + (uint64_t)BLOCK * G - 1) / ((uint64_t)BLOCK * G);
+    unsigned grid = (unsigned)(blocks < 148ull * 32 ? blocks : 148ull * 32);
+    if (c->wide) {
+        if (c->track) { InsertSink<true, true> sk; sk.t = view_of(c); k_insert_tuples<true, true><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
+        else { InsertSink<true, false> sk; sk.t = view_of(c); k_insert_tuples<true, false><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
+    } else {
+        if (c->track) { InsertSink<false, true> sk; sk.t = view_of(c); k_insert_tuples<false, true><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
+        else { InsertSink<false, false> sk; sk.t = view_of(c); k_insert_tuples<false, false><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
+    }
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+extern "C" int dbg_get_polyA_counts(dbg_ctx *c, uint64_t counts[8])
+{
+    if (!c || !counts) return set_err(DBG_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(counts, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
+    return DBG_OK;
+}
+
+extern "C" int dbg_set_polyA_counts(dbg_ctx *c, const uint64_t counts[8])
+{
+    if (!c || !counts) return set_err(DBG_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(c->d_polyA, counts, 8 * sizeof(u64), cudaMemcpyHostToDevice));
+    return DBG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize: reference slot layout + k-mer-0 node
+// ---------------------------------------------------------------------------------------------------
+static uint64_t nul_words(uint64_t P) { return (P / 8 + 1 + 3) / 4 + 1; }
+
+static int fill_stats(dbg_ctx *c, const u64 *cnt)
+{
+    dbg_stats &s = c->st;
+    s.array_size = c->P; s.max_cutoff = c->max_cutoff; s.load_factor = c->lf; s.wide = c->wide;
+    s.count = cnt[CNT_NEW] + (c->finalized && (c->n_shards <= 1) ? 1 : 0);
+    s.conflict = cnt[CNT_CONFLICT]; s.reads = c->reads_total; s.kmers_logged = cnt[CNT_LOGGED]; s.occurrences = cnt[CNT_OCC];
+    s.polyA_l = (uint32_t)c->polyA_links; s.polyA_r = (uint32_t)(c->polyA_links >> 32);
+    s.shard_lo = c->shard_lo; s.shard_hi = c->shard_hi;
+    return DBG_OK;
+}
+
+static int read_counters(dbg_ctx *c, u64 *cnt)
+{
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (cnt[CNT_ERROR] == 1) return set_err(DBG_ERR_TABLE_FULL, "probe ran off the shard (%llu slots + margin): table too full", (unsigned long long)(c->shard_hi - c->shard_lo));
+    if (cnt[CNT_ERROR] == 2) return set_err(DBG_ERR_BUFFER, "tuple bucket overflow: raise bucket_stride");
+    return DBG_OK;
+}
+
+template <bool WIDE, bool TRACK>
+static int run_layout(dbg_ctx *c)
+{
+    unsigned grid = 148 * 16;
+    k_layout_insert<WIDE, TRACK><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M);
+    CU_TRY(cudaGetLastError());
+    k_layout_place<WIDE, TRACK><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M, c->d_out, c->d_nul32);
+    CU_TRY(cudaGetLastError());
+    k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->d_owner, c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
+    CU_TRY(cudaGetLastError());
+    c->launches += 3;
+    return DBG_OK;
+}
+
+extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    u64 cnt[CNT_N];
+    int rc = read_counters(c, cnt);
+    if (rc) return rc;
+    if (!c->finalized) {
+        // build time = sum over blocks
+        float tb = 0;
+        for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); tb += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        c->build_ev.clear();
+        c->ms[1] += tb;
+        if (c->n_shards <= 1) {
+            if (cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
+            size_t nb = (size_t)node_bytes(c);
+            if (!c->d_owner) {
+                CU_TRY(cudaMalloc(&c->d_owner, c->P * sizeof(u64)));
+                CU_TRY(cudaMalloc(&c->d_out, c->P * nb));
+                CU_TRY(cudaMalloc(&c->d_nul32, nul_words(c->P) * sizeof(u32)));
+            }
+            EvPair e;
+            rc = ev_begin(c, c->stream, &e);
+            if (rc) return rc;
+            CU_TRY(cudaMemsetAsync(c->d_owner, 0xFF, c->P * sizeof(u64), c->stream));
+            CU_TRY(cudaMemsetAsync(c->d_out, 0, c->P * nb, c->stream));
+            CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
+            if (c->wide) rc = c->track ? run_layout<true, true>(c) : run_layout<true, false>(c);
+            else rc = c->track ? run_layout<false, true>(c) : run_layout<false, false>(c);
+            if (rc) return rc;
+            CU_TRY(cudaEventRecord(e.b, c->stream));
+            CU_TRY(cudaEventSynchronize(e.b));
+            CU_TRY(cudaEventElapsedTime(&c->ms[2], e.a, e.b));
+            cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+            CU_TRY(cudaMemcpy(&c->polyA_links, c->d_counters + 6, sizeof(u64), cudaMemcpyDeviceToHost));
+        }
+        c->finalized = true;
+    }
+    fill_stats(c, cnt);
+    if (stats) *stats = c->st;
+    return DBG_OK;
+}
+
+extern "C" int dbg_get_stats(dbg_ctx *c, dbg_stats *stats)
+{
+    if (!c || !stats) return set_err(DBG_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    u64 cnt[CNT_N];
+    int rc = read_counters(c, cnt);
+    if (rc) return rc;
+    fill_stats(c, cnt);
+    *stats = c->st;
+    return DBG_OK;
+}
+
+extern "C" int dbg_device_image(dbg_ctx *c, void **d_array, void **d_nul_flag)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "no finalized image (unsharded contexts only)");
+    if (d_array) *d_array = c->d_out;
+    if (d_nul_flag) *d_nul_flag = c->d_nul32;
+    return DBG_OK;
+}
+
+extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
+{
+    if (!c || !array || !nul_flag) return set_err(DBG_ERR_INVALID, "NULL argument");
+    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "dbg_export_kmerset needs dbg_finalize on an unsharded context");
+    CU_TRY(cudaSetDevice(c->device));
+    EvPair e;
+    int rc = ev_begin(c, c->stream, &e);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(array, c->d_out, c->P * (size_t)node_bytes(c), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(nul_flag, c->d_nul32, c->P / 8 + 1, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaEventRecord(e.b, c->stream));
+    CU_TRY(cudaEventSynchronize(e.b));
+    CU_TRY(cudaEventElapsedTime(&c->ms[5], e.a, e.b));
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    return DBG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// calculate_kmer_links + compaction
+// ---------------------------------------------------------------------------------------------------
+static int run_links(dbg_ctx *c, int cutoff)
+{
+    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "needs dbg_finalize on an unsharded context");
+    if (c->links_cutoff == cutoff) return DBG_OK;
+    uint64_t n_tiles = (c->P + TILE - 1) / TILE;
+    if (!c->d_klink) {
+        CU_TRY(cudaMalloc(&c->d_klink, c->P * sizeof(unsigned short)));
+        CU_TRY(cudaMalloc(&c->d_del32, nul_words(c->P) * sizeof(u32)));
+        CU_TRY(cudaMalloc(&c->d_tile_counts, n_tiles * 4 * sizeof(u32)));
+        CU_TRY(cudaMalloc(&c->d_tile_offs, n_tiles * 4 * sizeof(u64)));
+        CU_TRY(cudaMalloc(&c->d_small, (256 + 3 + 4 + 1) * sizeof(u64)));
+    }
+    EvPair e;
+    int rc = ev_begin(c, c->stream, &e);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(c->d_small, 0, (256 + 3 + 4 + 1) * sizeof(u64), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_del32, 0, nul_words(c->P) * sizeof(u32), c->stream));
+    unsigned grid = (unsigned)(n_tiles < 148ull * 8 ? n_tiles : 148ull * 8);
+    k_links_classify<<<grid, 256, 0, c->stream>>>(c->d_out, c->d_nul32, c->P, c->wide ? 1 : 0, cutoff, c->d_klink, c->d_del32,
+                                                  c->d_small, c->d_small + 256, c->d_tile_counts);
+    CU_TRY(cudaGetLastError());
+    k_scan_tiles<<<1, 1024, 0, c->stream>>>(c->d_tile_counts, n_tiles, c->d_tile_offs, c->d_small + 259);
+    CU_TRY(cudaGetLastError());
+    c->launches += 2;
+    CU_TRY(cudaEventRecord(e.b, c->stream));
+    CU_TRY(cudaEventSynchronize(e.b));
+    CU_TRY(cudaEventElapsedTime(&c->ms[3], e.a, e.b));
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    c->links_cutoff = cutoff;
+    return DBG_OK;
+}
+
+extern "C" int dbg_export_links(dbg_ctx *c, int32_t freq_cutoff, uint8_t *klink, uint8_t *del_flag, int64_t depth_hist[256],
+                                uint64_t *tips, uint64_t *n_tips, uint64_t *branches, uint64_t *n_branches, int64_t stats3[3])
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    int rc = run_links(c, freq_cutoff);
+    if (rc) return rc;
+    u64 small[264];
+    CU_TRY(cudaMemcpy(small, c->d_small, sizeof(small), cudaMemcpyDeviceToHost));
+    if (depth_hist) for (int i = 0; i < 256; i++) depth_hist[i] = (int64_t)small[i];
+    if (stats3) for (int i = 0; i < 3; i++) stats3[i] = (int64_t)small[256 + i];
+    uint64_t nt = small[259], nb = small[260];
+    if (klink) CU_TRY(cudaMemcpy(klink, c->d_klink, c->P * 2, cudaMemcpyDeviceToHost));
+    if (del_flag) CU_TRY(cudaMemcpy(del_flag, c->d_del32, c->P / 8 + 1, cudaMemcpyDeviceToHost));
+    if ((tips && n_tips) || (branches && n_branches)) {
+        uint64_t cap_t = (tips && n_tips) ? *n_tips : 0, cap_b = (branches && n_branches) ? *n_branches : 0;
+        if ((tips && cap_t < nt) || (branches && cap_b < nb)) {
+            if (n_tips) *n_tips = nt;
+            if (n_branches) *n_branches = nb;
+            return set_err(DBG_ERR_BUFFER, "tip/branch list capacity too small (%llu/%llu needed)", (unsigned long long)nt, (unsigned long long)nb);
+        }
+        u64 *d_t = nullptr, *d_b = nullptr;
+        CU_TRY(cudaMalloc(&d_t, (nt + 1) * sizeof(u64)));
+        CU_TRY(cudaMalloc(&d_b, (nb + 1) * sizeof(u64)));
+        uint64_t n_tiles = (c->P + TILE - 1) / TILE;
+        unsigned grid = (unsigned)(n_tiles < 148ull * 8 ? n_tiles : 148ull * 8);
+        k_links_lists<<<grid, 256, 0, c->stream>>>(c->d_klink, c->d_nul32, c->P, c->d_tile_offs, d_t, nt, d_b, nb);
+        c->launches++;
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);
+        if (e1 == cudaSuccess && tips && nt) e1 = cudaMemcpy(tips, d_t, nt * sizeof(u64), cudaMemcpyDeviceToHost);
+        if (e1 == cudaSuccess && branches && nb) e1 = cudaMemcpy(branches, d_b, nb * sizeof(u64), cudaMemcpyDeviceToHost);
+        cudaFree(d_t); cudaFree(d_b);
+        CU_TRY(e1);
+    }
+    if (n_tips) *n_tips = nt;
+    if (n_branches) *n_branches = nb;
+    return DBG_OK;
+}
+
+extern "C" int dbg_dump_compact(dbg_ctx *c, int32_t freq_cutoff, uint64_t *slots, uint64_t *kmers_lo, uint64_t *kmers_hi,
+                                uint32_t *l_link, uint32_t *r_link, uint64_t *n)
+{
+    if (!c || !n) return set_err(DBG_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    int which = freq_cutoff < 0 ? 3 : 2;
+    int rc = run_links(c, freq_cutoff < 0 ? (c->links_cutoff != INT32_MIN ? c->links_cutoff : 0) : freq_cutoff);
+    if (rc) return rc;
+    u64 totals[4];
+    CU_TRY(cudaMemcpy(totals, c->d_small + 259, sizeof(totals), cudaMemcpyDeviceToHost));
+    uint64_t m = totals[which], cap = *n;
+    *n = m;
+    if (!slots && !kmers_lo && !kmers_hi && !l_link && !r_link) return DBG_OK;   // size query
+    if (cap < m) return set_err(DBG_ERR_BUFFER, "dump capacity %llu < %llu", (unsigned long long)cap, (unsigned long long)m);
+    u64 *d_s = nullptr, *d_lo = nullptr, *d_hi = nullptr; u32 *d_l = nullptr, *d_r = nullptr;
+    cudaError_t e1 = cudaSuccess;
+    if (slots) e1 = cudaMalloc(&d_s, (m + 1) * 8);
+    if (e1 == cudaSuccess && kmers_lo) e1 = cudaMalloc(&d_lo, (m + 1) * 8);
+    if (e1 == cudaSuccess && kmers_hi) e1 = cudaMalloc(&d_hi, (m + 1) * 8);
+    if (e1 == cudaSuccess && l_link) e1 = cudaMalloc(&d_l, (m + 1) * 4);
+    if (e1 == cudaSuccess && r_link) e1 = cudaMalloc(&d_r, (m + 1) * 4);
+    if (e1 == cudaSuccess) {
+        uint64_t n_tiles = (c->P + TILE - 1) / TILE;
+        unsigned grid = (unsigned)(n_tiles < 148ull * 8 ? n_tiles : 148ull * 8);
+        k_compact_nodes<<<grid, 256, 0, c->stream>>>(c->d_out, c->d_nul32, c->d_del32, c->P, c->wide ? 1 : 0, which, c->d_tile_offs, m,
+                                                     d_s, d_lo, d_hi, d_l, d_r);
+        c->launches++;
+        e1 = cudaGetLastError();
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);
+    }
+    if (e1 == cudaSuccess && slots && m) e1 = cudaMemcpy(slots, d_s, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && kmers_lo && m) e1 = cudaMemcpy(kmers_lo, d_lo, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && kmers_hi && m) e1 = cudaMemcpy(kmers_hi, d_hi, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && l_link && m) e1 = cudaMemcpy(l_link, d_l, m * 4, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && r_link && m) e1 = cudaMemcpy(r_link, d_r, m * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_s); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_l); cudaFree(d_r);
+    CU_TRY(e1);
+    return DBG_OK;
+}
+
+extern "C" int dbg_get_timings(dbg_ctx *c, float ms[8])
+{
+    if (!c || !ms) return set_err(DBG_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 8; i++) ms[i] = c->ms[i];
+    return DBG_OK;
+}
+
+extern "C" uint64_t dbg_launch_count(const dbg_ctx *c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// roofline denominator
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dbg_measure_random_rmw(int32_t device, uint64_t bytes, uint64_t n_ops, int32_t mode, float *ms)
+{
+    if (!ms || bytes < sizeof(Node)) return set_err(DBG_ERR_INVALID, "bad argument");
+    if (dbg_device_count() == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible");
+    CU_TRY(cudaSetDevice(device));
+    Node *tab = nullptr;
+    CU_TRY(cudaMalloc(&tab, bytes));
+    cudaError_t e1 = cudaMemset(tab, 0, bytes);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    uint64_t n_nodes = bytes / sizeof(Node);
+    unsigned grid = 148 * 32;
+    float best = 1e30f;
+    for (int it = 0; it < 4 && e1 == cudaSuccess; it++) {   // first iteration is warm-up
+        cudaEventRecord(a);
+        if (mode == 0) k_random_rmw<0><<<grid, 256>>>(tab, n_nodes, n_ops, 0x1234567ull * (it + 1));
+        else k_random_rmw<1><<<grid, 256>>>(tab, n_nodes, n_ops, 0x1234567ull * (it + 1));
+        cudaEventRecord(b);
+        e1 = cudaEventSynchronize(b);
+        float t = 0;
+        cudaEventElapsedTime(&t, a, b);
+        if (it > 0 && t < best) best = t;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(tab);
+    CU_TRY(e1);
+    *ms = best;
+    return DBG_OK;
+}

@@ -1,0 +1,725 @@
+// dbg_kernels.cuh -- the sm_100a kernels of the De Bruijn graph build.
+//
+//   k_chunk_first   : reads -> fixed-size base chunks (one CTA per chunk later)
+//   k_build<..>     : FUSED  stage ASCII -> 2-bit pack in shared memory -> canonical k-mer + neighbour
+//                     bases per occurrence -> sink.  Sinks: InsertSink (hash insert/update, single GPU
+//                     and the owner side of multi-GPU) and BucketSink (tuples bucketed by owner shard
+//                     for the all-to-all).
+//   k_insert_tuples : owner side of the exchange
+//   k_layout_*      : rebuild the reference's slot layout (first-occurrence priority linear probing)
+//   k_links_* / k_compact_* : calculate_kmer_links + ordered stream compaction
+//
+// Reference semantics: DBGgraph.cpp:38-213 (parse + update), kmerSet.cpp:253-273 (poly-A node),
+// contig.cpp:107-205 (link pass).  Nothing here is a translation of the pthread code: the reference
+// materialises (kmer,left,right) per block and lets T threads rescan it; here one CTA owns a chunk of
+// bases, keeps it packed in shared memory and pushes occurrences straight into the HBM table.
+#pragma once
+#include "dbg_core.cuh"
+
+namespace dbg {
+
+constexpr int CB = 16384;      // bases per chunk (one CTA)
+constexpr int BLOCK = 256;     // threads per CTA
+constexpr int MAXR = 1024;     // reads per shared-memory table pass
+constexpr int G = 4;           // consecutive occurrences per thread run (rolling k-mer + 4 probes in flight)
+constexpr u64 EMPTY_PRI = ~0ULL;
+constexpr u64 POLYA_PRI = ~0ULL - 1;
+
+struct Occ {
+    u64 klo, khi;
+    u32 lb, rb;     // 0..3 or 4 (= no neighbour: read end)
+    u64 ord;        // read_index << 16 | j
+};
+
+struct BuildArgs {
+    const char *bases;        // device pointer; global offsets index into it
+    const u64 *offs;          // n_reads + 1
+    u64 n_reads;
+    u64 abase;                // 16-B aligned byte where chunk 0 starts
+    u64 end_base;             // one past the last valid base byte
+    const u64 *chunk_first;   // n_chunks + 1: first read starting in each chunk
+    u64 read_index0;          // global index of read 0 (ordinals)
+    int K, R;
+    u32 stage_words;          // packed words staged per chunk (incl. slack)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// chunk index: chunk_first[c] = first read whose start offset lies in chunk >= c
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, u64 abase, u64 n_chunks,
+                              u64 *__restrict__ chunk_first)
+{
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    u64 c = n_chunks;
+    if (r < n_reads) { c = (offs[r] - abase) / CB; if (c > n_chunks) c = n_chunks; }
+    u64 cprev_plus1 = 0;
+    if (r > 0) { u64 cp = (offs[r - 1] - abase) / CB; if (cp > n_chunks) cp = n_chunks; cprev_plus1 = cp + 1; }
+    for (u64 cc = cprev_plus1; cc <= c; cc++) chunk_first[cc] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sinks
+// ---------------------------------------------------------------------------------------------------
+template <bool WIDE, bool TRACK>
+struct InsertSink {
+    TableView t;
+    u32 n_new, n_conf;     // per-thread, reduced at kernel end
+
+    __device__ __forceinline__ void init() { n_new = 0; n_conf = 0; }
+
+    __device__ __forceinline__ void polyA(const Occ &o)
+    {
+        // k-mer 0 never enters the table during the build (DBGgraph.cpp:153-164).  Counts above 255
+        // change nothing after clamping, so stop adding once a lane is saturated (bounds contention).
+        if (o.lb < 4 && __ldcg(t.polyA + o.lb) < 255) atomicAdd(t.polyA + o.lb, 1ULL);
+        if (o.rb < 4 && __ldcg(t.polyA + 4 + o.rb) < 255) atomicAdd(t.polyA + 4 + o.rb, 1ULL);
+    }
+
+    // thread_updatekmers for one occurrence (DBGgraph.cpp:167-205), lock-free
+    __device__ __forceinline__ void resolve(const Occ &o, Node *p, u64 idx, u64 klo, u64 khi, u64 links, u64 nord)
+    {
+        for (;;) {
+            bool mine = false;
+            if ((klo | khi) == 0) {
+                if (WIDE) {
+                    u64 olo, ohi;
+                    if (cas128(p, o.klo, o.khi, olo, ohi)) { mine = true; n_new++; }
+                    else { klo = olo; khi = ohi; }
+                } else {
+                    u64 old = atomicCAS(&p->klo, 0ULL, o.klo);
+                    if (old == 0) { mine = true; n_new++; }
+                    else klo = old;
+                }
+            }
+            if (mine || (klo == o.klo && (!WIDE || khi == o.khi))) {
+                // saturating lane update: CAS loop on the packed {l_link, r_link} word
+                u64 cur = links;
+                for (;;) {
+                    u32 l = lane_inc((u32)cur, o.lb), r = lane_inc((u32)(cur >> 32), o.rb);
+                    u64 nv = (u64)l | ((u64)r << 32);
+                    if (nv == cur) break;
+                    u64 old = atomicCAS(&p->links, cur, nv);
+                    if (old == cur) break;
+                    cur = old;
+                }
+                if (TRACK) {
+                    u64 mn = ~o.ord;
+                    if (mn > nord) atomicMax(&p->nord, mn);
+                }
+                return;
+            }
+            n_conf++;
+            idx++; p++;
+            if (idx >= t.n_local) { atomicExch(t.counters + CNT_ERROR, 1ULL); return; }
+            load_node(p, klo, khi, links, nord);
+        }
+    }
+
+    __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
+    {
+        Node *p[G]; u64 idx[G]; u64 klo[G], khi[G], links[G], nord[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (g < nv && (o[g].klo | o[g].khi) != 0) {
+                u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                idx[g] = mod_P(h, t.P, t.M) - t.lo;
+                p[g] = t.nodes + idx[g];
+                load_node(p[g], klo[g], khi[g], links[g], nord[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (g < nv) {
+                if ((o[g].klo | o[g].khi) == 0) polyA(o[g]);
+                else resolve(o[g], p[g], idx[g], klo[g], khi[g], links[g], nord[g]);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void finish()
+    {
+        u32 a = n_new, b = n_conf;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); b += __shfl_xor_sync(0xffffffffu, b, s); }
+        if ((threadIdx.x & 31) == 0) {
+            if (a) atomicAdd(t.counters + CNT_NEW, (u64)a);
+            if (b) atomicAdd(t.counters + CNT_CONFLICT, (u64)b);
+        }
+    }
+};
+
+// tuples for the exchange: 16 B (narrow) {kmer, ord<<8 | rb<<4 | lb}, 32 B (wide) {lo, hi, meta, 0}
+template <bool WIDE>
+struct BucketSink {
+    TableView t;            // P, M, polyA, counters (nodes unused)
+    u64 shard_size;         // ceil(P / n_parts)
+    int n_parts;
+    u64 *tuples;            // bucket b starts at b * bucket_stride tuples
+    u64 bucket_stride;
+    u64 *counts;            // n_parts
+
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void finish() {}
+
+    __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
+    {
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            // warp-aggregated append: all lanes take part in the ballots
+            int part = -1;
+            if (g < nv) {
+                if ((o[g].klo | o[g].khi) == 0) {
+                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
+                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                } else {
+                    u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                    u64 home = mod_P(h, t.P, t.M);
+                    part = 0;
+                    for (int q = 1; q < n_parts; q++) part += (home >= (u64)q * shard_size);
+                }
+            }
+            const u32 active = 0xffffffffu;   // consume() is called by every thread of the CTA
+            for (int q = 0; q < n_parts; q++) {
+                u32 m = __ballot_sync(active, part == q);
+                if (m == 0) continue;
+                int leader = __ffs(m) - 1;
+                u64 base = 0;
+                if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counts + q, (u64)__popc(m));
+                base = __shfl_sync(active, base, leader);
+                if (part == q) {
+                    u64 pos = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
+                    if (pos < bucket_stride) {
+                        u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+                        if (WIDE) {
+                            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * ((u64)q * bucket_stride + pos);
+                            dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
+                            dst[1] = make_ulonglong2(meta, 0ULL);
+                        } else {
+                            reinterpret_cast<ulonglong2 *>(tuples)[(u64)q * bucket_stride + pos] = make_ulonglong2(o[g].klo, meta);
+                        }
+                    } else {
+                        atomicExch(t.counters + CNT_ERROR, 2ULL);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the fused build kernel: one CTA per chunk of CB bases
+// ---------------------------------------------------------------------------------------------------
+template <bool WIDE, class Sink>
+__global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
+{
+    extern __shared__ u32 smem[];
+    u32 *pk = smem;                          // a.stage_words
+    u32 *rstart = pk + a.stage_words;        // MAXR
+    u32 *rpre = rstart + MAXR;               // MAXR + 1
+    __shared__ u32 warp_tot[BLOCK / 32];
+
+    const int tid = threadIdx.x;
+    const u64 chunk = blockIdx.x;
+    const u64 cbase = a.abase + chunk * CB;
+    const int K = a.K;
+
+    sink.init();
+
+    // ---- (1) coalesced 16-B loads of ASCII bases, 2-bit pack, stage in shared memory -------------------
+    {
+        u64 avail = a.end_base > cbase ? a.end_base - cbase : 0;
+        u64 want = (u64)(a.stage_words - 4) * 16;
+        u32 nvec = (u32)(((avail < want ? avail : want) + 15) / 16);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.bases + cbase);
+        for (u32 v = tid; v < a.stage_words; v += BLOCK)
+            pk[v] = (v < nvec) ? pack16(__ldg(src + v)) : 0u;
+    }
+
+    const u64 r_lo = a.chunk_first[chunk], r_hi = a.chunk_first[chunk + 1];
+    u64 logged = 0, n_occ = 0;
+
+    for (u64 rb = r_lo; rb < r_hi; rb += MAXR) {
+        const u32 nr = (u32)((r_hi - rb) < (u64)MAXR ? (r_hi - rb) : (u64)MAXR);
+        __syncthreads();   // staging done / previous pass finished with the tables
+
+        // ---- (2) per-read k-mer counts + exclusive scan (4 reads per thread) ---------------------------
+        u32 c[4]; u32 tsum = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            u32 i = tid * 4 + e;
+            c[e] = 0;
+            if (i < nr) {
+                u64 s0 = a.offs[rb + i], s1 = a.offs[rb + i + 1];
+                u64 len = s1 - s0;
+                u64 klen = len < (u64)a.R ? len : (u64)a.R;                 // trim to -r (DBGgraph.cpp:63)
+                if (klen >= (u64)K) c[e] = (u32)(klen - K + 1);             // skip reads shorter than K (:51-53)
+                if (len >= (u64)K) logged += len - K + 1;                   // Kmer_total_num quirk (:101)
+                rstart[i] = (u32)(s0 - cbase);
+            }
+            tsum += c[e];
+        }
+        u32 incl = tsum;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, s); if ((tid & 31) >= s) incl += v; }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        u32 wbase = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; w++) if (w < (tid >> 5)) wbase += warp_tot[w];
+        u32 ex = wbase + incl - tsum;
+#pragma unroll
+        for (int e = 0; e < 4; e++) { rpre[tid * 4 + e] = ex; ex += c[e]; }
+        if (tid == BLOCK - 1) rpre[MAXR] = ex;
+        __syncthreads();
+        const u32 S = rpre[MAXR];
+        if (tid == 0) n_occ += S;
+
+        // ---- (3) occurrences: each thread takes runs of G consecutive ones ----------------------------
+        // (block-uniform trip count: every thread calls sink.consume, so sinks may use full-warp collectives)
+        for (u32 ob = 0; ob < S; ob += BLOCK * G) {
+            const u32 o0 = ob + tid * G;
+            Occ occ[G];
+            int nv = 0;
+            if (o0 < S) {
+            u32 lo = 0, hi = nr;
+            while (lo < hi) { u32 mid = (lo + hi) >> 1; if (rpre[mid] <= o0) lo = mid + 1; else hi = mid; }
+            u32 i = lo - 1;
+            u32 j = o0 - rpre[i];
+            u32 ci = rpre[i + 1] - rpre[i];
+            bool fresh = true;
+            u64 flo = 0, fhi = 0, rlo = 0, rhi = 0;   // forward / reverse-complement words
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (o0 + g < S) {
+                    if (j >= ci) {
+                        do { i++; ci = rpre[i + 1] - rpre[i]; } while (ci == 0);
+                        j = 0; fresh = true;
+                    }
+                    const u32 p = rstart[i] + j;
+                    if (fresh) {
+                        // first k-mer of a run: read the window straight out of the packed stream
+                        if (WIDE) { U128 f = window128(pk, p, K); U128 r = revcomp128(f, K); flo = f.lo; fhi = f.hi; rlo = r.lo; rhi = r.hi; }
+                        else { flo = window64(pk, p, K); rlo = revcomp64(flo, K); }
+                        fresh = false;
+                    } else {
+                        // rolling update (DBGgraph.cpp:71-73)
+                        u32 b = code_at(pk, p + K - 1);
+                        if (WIDE) {
+                            fhi = (fhi << 2) | (flo >> 62); flo = (flo << 2) | b;
+                            int top = 2 * K - 64;   // bits of the k-mer living in the high word (K > 32) or <= 0
+                            if (top > 0) fhi &= (top >= 64 ? ~0ULL : ((1ULL << top) - 1));
+                            else { fhi = 0; if (2 * K < 64) flo &= (1ULL << (2 * K)) - 1; }
+                            rlo = (rlo >> 2) | (rhi << 62); rhi >>= 2;
+                            int sh = 2 * (K - 1);
+                            if (sh >= 64) rhi |= (u64)(3 - b) << (sh - 64); else rlo |= (u64)(3 - b) << sh;
+                        } else {
+                            flo = ((flo << 2) | b) & ((1ULL << (2 * K)) - 1);
+                            rlo = (rlo >> 2) | ((u64)(3 - b) << (2 * (K - 1)));
+                        }
+                    }
+                    u32 left = (j > 0) ? code_at(pk, p - 1) : 4u;
+                    u32 right = (j + 1 < ci) ? code_at(pk, p + K) : 4u;
+                    bool fwd = WIDE ? (fhi < rhi || (fhi == rhi && flo <= rlo)) : (flo <= rlo);   // tie -> forward (:80)
+                    Occ &q = occ[g];
+                    if (fwd) { q.klo = flo; q.khi = fhi; q.lb = left; q.rb = right; }
+                    else {
+                        q.klo = rlo; q.khi = rhi;
+                        q.rb = (left < 4) ? 3 - left : 4u;       // DBGgraph.cpp:85-89
+                        q.lb = (right < 4) ? 3 - right : 4u;
+                    }
+                    q.ord = ((a.read_index0 + rb + i) << 16) | j;
+                    j++; nv = g + 1;
+                }
+            }
+            }
+            sink.consume(occ, nv);
+        }
+    }
+
+    sink.finish();
+    // Kmer_total_num / occurrence counters
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) logged += __shfl_xor_sync(0xffffffffu, logged, s);
+    if ((tid & 31) == 0 && logged) atomicAdd(sink.t.counters + CNT_LOGGED, logged);
+    if (tid == 0 && n_occ) atomicAdd(sink.t.counters + CNT_OCC, n_occ);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// owner side of the exchange: insert received tuples
+// ---------------------------------------------------------------------------------------------------
+template <bool WIDE, bool TRACK>
+__global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, InsertSink<WIDE, TRACK> sink)
+{
+    sink.init();
+    const u64 stride = (u64)gridDim.x * BLOCK * G;
+    for (u64 base0 = (u64)blockIdx.x * BLOCK * G; base0 < n; base0 += stride) {   // block-uniform trip count
+        const u64 base = base0 + (u64)threadIdx.x * G;
+        Occ occ[G]; int nv = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (base + g < n) {
+                u64 klo, khi = 0, meta;
+                if (WIDE) {
+                    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g));
+                    ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g) + 1);
+                    klo = x.x; khi = x.y; meta = y.x;
+                } else {
+                    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + base + g);
+                    klo = x.x; meta = x.y;
+                }
+                occ[g].klo = klo; occ[g].khi = khi; occ[g].lb = (u32)(meta & 15); occ[g].rb = (u32)((meta >> 4) & 15);
+                occ[g].ord = meta >> 8;
+                nv = g + 1;
+            }
+        }
+        sink.consume(occ, nv);
+    }
+    sink.finish();
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sink.t.counters + CNT_OCC, n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reference slot layout: the reference places a key in the first free
+// slot from hash%P at the moment of its FIRST occurrence.  That layout is the unique one in which every
+// key k at slot s has only earlier-first-seen keys in [home(k), s); priority linear probing with
+// atomicMin on the ordinal builds it in any execution order.  owner[] holds the ordinal per slot.
+// ---------------------------------------------------------------------------------------------------
+template <bool WIDE, bool TRACK>
+__global__ void k_layout_insert(const Node *__restrict__ nodes, u64 n_local, u64 lo_slot, u64 *owner, u64 P, u64 M)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
+        u64 klo = __ldg(&nodes[i].klo), khi = WIDE ? __ldg(&nodes[i].khi) : 0;
+        if ((klo | khi) == 0) continue;
+        u64 cur = TRACK ? ~__ldg(&nodes[i].nord) : (lo_slot + i);
+        u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
+        u64 s = mod_P(h, P, M);
+        for (;;) {
+            u64 old = atomicMin(owner + s, cur);
+            if (old == EMPTY_PRI) break;
+            if (old > cur) cur = old;      // we took the slot; carry the displaced key onwards
+            s = (s + 1 == P) ? 0 : s + 1;
+        }
+    }
+}
+
+template <bool WIDE, bool TRACK>
+__global__ void k_layout_place(const Node *__restrict__ nodes, u64 n_local, u64 lo_slot, const u64 *__restrict__ owner,
+                               u64 P, u64 M, void *out, u32 *nul32)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
+        u64 klo, khi, links, nord;
+        load_node(nodes + i, klo, khi, links, nord);
+        if ((klo | khi) == 0) continue;
+        u64 pri = TRACK ? ~nord : (lo_slot + i);
+        u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
+        u64 s = mod_P(h, P, M);
+        while (__ldg(owner + s) != pri) s = (s + 1 == P) ? 0 : s + 1;
+        if (WIDE) {
+            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + 2 * s;
+            dst[0] = make_ulonglong2(klo, khi);
+            dst[1] = make_ulonglong2(links, 0ULL);
+        } else {
+            reinterpret_cast<ulonglong2 *>(out)[s] = make_ulonglong2(klo, links);
+        }
+        atomicOr(nul32 + (s >> 5), flag_mask(s));
+    }
+}
+
+// add_node_to_kmerset(kset, PolyA) (kmerSet.cpp:253-273, DBGgraph.cpp:418): last, always, first null slot
+template <bool WIDE>
+__global__ void k_polyA_insert(u64 *owner, u64 P, u64 M, const u64 *__restrict__ polyA, void *out, u32 *nul32, u64 *links_out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u32 l = 0, r = 0;
+    for (int b = 0; b < 4; b++) {
+        u64 cl = polyA[b], cr = polyA[4 + b];
+        l |= (u32)(cl > 255 ? 255 : cl) << (24 - 8 * b);
+        r |= (u32)(cr > 255 ? 255 : cr) << (24 - 8 * b);
+    }
+    u64 links = (u64)l | ((u64)r << 32);
+    *links_out = links;
+    u64 s = mod_P(WIDE ? hash_code_wide(0, 0) : hash_code(0), P, M);
+    while (owner[s] != EMPTY_PRI) s = (s + 1 == P) ? 0 : s + 1;
+    owner[s] = POLYA_PRI;
+    if (WIDE) {
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + 2 * s;
+        dst[0] = make_ulonglong2(0ULL, 0ULL);
+        dst[1] = make_ulonglong2(links, 0ULL);
+    } else {
+        reinterpret_cast<ulonglong2 *>(out)[s] = make_ulonglong2(0ULL, links);
+    }
+    nul32[s >> 5] |= flag_mask(s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// calculate_kmer_links (contig.cpp:107-205) + ordered compaction
+// ---------------------------------------------------------------------------------------------------
+constexpr int TILE = 2048;   // slots per compaction tile (one CTA iteration: 256 threads x 8)
+
+__device__ __forceinline__ u32 load_links_of_slot(const void *img, u64 i, bool wide, u64 &klo, u64 &khi, u64 &links)
+{
+    if (wide) {
+        ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(img) + 2 * i);
+        ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(img) + 2 * i + 1);
+        klo = a.x; khi = a.y; links = b.x;
+    } else {
+        ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(img) + i);
+        klo = a.x; khi = 0; links = a.y;
+    }
+    return 0;
+}
+
+// classify one link word: number of lanes above the cutoff (capped at 3) and the arg-max base
+// (first maximum wins: strict `<`, contig.cpp:137-141)
+__device__ __forceinline__ void classify(u32 link, int cutoff, u32 &num, u32 &base, u32 *hist_nonzero, u32 &zeros)
+{
+    num = 0; base = 0; int maxd = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int d = (link >> (24 - 8 * j)) & 0xFF;
+        if (d == 0) zeros++; else atomicAdd(hist_nonzero + d, 1u);
+        if (d > cutoff) {
+            if (num < 3) num++;
+            if (maxd < d) { maxd = d; base = j; }
+        }
+    }
+}
+
+// pass 1: klink, del_flag, depth histogram, per-tile counts of tips / branches / survivors / filled
+__global__ void __launch_bounds__(256) k_links_classify(const void *__restrict__ img, const u32 *__restrict__ nul32, u64 P, int wide,
+                                                        int cutoff, unsigned short *klink, u32 *del32,
+                                                        u64 *depth_hist, u64 *stats3, u32 *tile_counts /* 4 per tile */)
+{
+    __shared__ u32 hist[256];
+    __shared__ u32 cnt[4];
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    u32 zeros = 0; u64 total = 0, deleted = 0, linear = 0;
+    const u64 n_tiles = (P + TILE - 1) / TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid < 4) cnt[tid] = 0;
+        __syncthreads();
+        u32 c_tip = 0, c_br = 0, c_surv = 0, c_fill = 0;
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++) {
+            u64 i = tile * TILE + (u64)e * 256 + tid;
+            bool in = i < P;
+            bool filled = in && (nul32[i >> 5] & flag_mask(i));
+            bool del = false;
+            unsigned short kl = 0;
+            if (filled) {
+                u64 klo, khi, links;
+                load_links_of_slot(img, i, wide, klo, khi, links);
+                u32 ln, lb, rn, rb;
+                classify((u32)links, cutoff, ln, lb, hist, zeros);
+                classify((u32)(links >> 32), cutoff, rn, rb, hist, zeros);
+                u32 lin = (ln == 1 && rn == 1);
+                kl = (unsigned short)(ln | (lb << 2) | (rn << 4) | (rb << 6) | (lin << 8));
+                total++; linear += lin; c_fill++;
+                if (ln == 0 && rn == 0) { del = true; deleted++; } else c_surv++;
+                if (ln + rn == 1) c_tip++;
+                if (ln > 1 || rn > 1) c_br++;
+            }
+            if (in) klink[i] = kl;
+            // del_flag: 32 consecutive slots -> one u32 of the MSB-first byte bitmap
+            u32 bal = __ballot_sync(0xffffffffu, del);
+            if ((tid & 31) == 0 && in) del32[i >> 5] = __byte_perm(__brev(bal), 0, 0x0123);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            c_tip += __shfl_xor_sync(0xffffffffu, c_tip, s); c_br += __shfl_xor_sync(0xffffffffu, c_br, s);
+            c_surv += __shfl_xor_sync(0xffffffffu, c_surv, s); c_fill += __shfl_xor_sync(0xffffffffu, c_fill, s);
+        }
+        if ((tid & 31) == 0) { atomicAdd(&cnt[0], c_tip); atomicAdd(&cnt[1], c_br); atomicAdd(&cnt[2], c_surv); atomicAdd(&cnt[3], c_fill); }
+        __syncthreads();
+        if (tid < 4) tile_counts[tile * 4 + tid] = cnt[tid];
+        __syncthreads();
+    }
+    // flush
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        zeros += __shfl_xor_sync(0xffffffffu, zeros, s);
+        total += __shfl_xor_sync(0xffffffffu, total, s); deleted += __shfl_xor_sync(0xffffffffu, deleted, s);
+        linear += __shfl_xor_sync(0xffffffffu, linear, s);
+    }
+    if ((tid & 31) == 0) {
+        if (zeros) atomicAdd(depth_hist, (u64)zeros);
+        if (total) atomicAdd(stats3, total);
+        if (deleted) atomicAdd(stats3 + 1, deleted);
+        if (linear) atomicAdd(stats3 + 2, linear);
+    }
+    __syncthreads();
+    if (tid > 0 && hist[tid]) atomicAdd(depth_hist + tid, (u64)hist[tid]);
+}
+
+// exclusive scan of tile_counts (4 interleaved streams) by one CTA; totals[4] out
+__global__ void __launch_bounds__(1024) k_scan_tiles(const u32 *__restrict__ tile_counts, u64 n_tiles, u64 *tile_offs, u64 *totals)
+{
+    __shared__ u64 wsum[32][4];
+    __shared__ u64 carry[4];
+    const int tid = threadIdx.x;
+    if (tid < 4) carry[tid] = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n_tiles; base += 1024) {
+        u64 t = base + tid;
+        u64 v[4], inc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (t < n_tiles) ? tile_counts[t * 4 + k] : 0; inc[k] = v[k]; }
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+#pragma unroll
+            for (int k = 0; k < 4; k++) { u64 x = __shfl_up_sync(0xffffffffu, inc[k], s); if ((tid & 31) >= s) inc[k] += x; }
+        if ((tid & 31) == 31)
+#pragma unroll
+            for (int k = 0; k < 4; k++) wsum[tid >> 5][k] = inc[k];
+        __syncthreads();
+        u64 wb[4] = {0, 0, 0, 0};
+        for (int w = 0; w < (tid >> 5); w++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) wb[k] += wsum[w][k];
+        if (t < n_tiles)
+#pragma unroll
+            for (int k = 0; k < 4; k++) tile_offs[t * 4 + k] = carry[k] + wb[k] + inc[k] - v[k];
+        __syncthreads();
+        if (tid == 1023)
+#pragma unroll
+            for (int k = 0; k < 4; k++) carry[k] += wb[k] + inc[k];
+        __syncthreads();
+    }
+    if (tid < 4) totals[tid] = carry[tid];
+}
+
+// block-wide exclusive scan of a 0/1 flag over TILE slots laid out e-major (slot = e*256 + tid):
+// returns this thread's rank for element e in ranks[e].  wcnt: TILE/32 + 1 words of shared memory.
+__device__ __forceinline__ void tile_rank(const bool (&flag)[TILE / 256], u32 (&ranks)[TILE / 256], u32 *wcnt)
+{
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < TILE / 256; e++) {
+        u32 bal = __ballot_sync(0xffffffffu, flag[e]);
+        ranks[e] = __popc(bal & ((1u << (tid & 31)) - 1));
+        if ((tid & 31) == 0) wcnt[e * 8 + (tid >> 5)] = __popc(bal);   // slot order: e major, warp minor
+    }
+    __syncthreads();
+    if (tid < 64) {   // exclusive scan of the 64 warp counts by two warps
+        u32 v = wcnt[tid], inc = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { u32 x = __shfl_up_sync(0xffffffffu, inc, s); if ((tid & 31) >= s) inc += x; }
+        if (tid == 31) wcnt[64] = inc;
+        __syncwarp();
+        wcnt[tid] = inc - v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < TILE / 256; e++) {
+        int me = e * 8 + (tid >> 5);
+        ranks[e] += wcnt[me] + (me >= 32 ? wcnt[64] : 0u);
+    }
+    __syncthreads();
+}
+
+// pass 2: index-ordered tip and branch lists (contig.cpp:175-180 push_back order = slot order)
+__global__ void __launch_bounds__(256) k_links_lists(const unsigned short *__restrict__ klink, const u32 *__restrict__ nul32, u64 P,
+                                                     const u64 *__restrict__ tile_offs, u64 *tips, u64 cap_tips,
+                                                     u64 *branches, u64 cap_br)
+{
+    __shared__ u32 wcnt[TILE / 32 + 1];
+    const int tid = threadIdx.x;
+    const u64 n_tiles = (P + TILE - 1) / TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        bool is_tip[TILE / 256], is_br[TILE / 256];
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++) {
+            u64 i = tile * TILE + (u64)e * 256 + tid;
+            bool filled = i < P && (nul32[i >> 5] & flag_mask(i));
+            u32 kl = filled ? klink[i] : 0;
+            u32 ln = kl & 3, rn = (kl >> 4) & 3;
+            is_tip[e] = filled && (ln + rn == 1);
+            is_br[e] = filled && (ln > 1 || rn > 1);
+        }
+        u32 rk[TILE / 256];
+        tile_rank(is_tip, rk, wcnt);
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++)
+            if (is_tip[e]) { u64 pos = tile_offs[tile * 4 + 0] + rk[e]; if (pos < cap_tips) tips[pos] = tile * TILE + (u64)e * 256 + tid; }
+        tile_rank(is_br, rk, wcnt);
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++)
+            if (is_br[e]) { u64 pos = tile_offs[tile * 4 + 1] + rk[e]; if (pos < cap_br) branches[pos] = tile * TILE + (u64)e * 256 + tid; }
+    }
+}
+
+// pass 2': slot-ordered dump of the surviving (or all filled) nodes
+__global__ void __launch_bounds__(256) k_compact_nodes(const void *__restrict__ img, const u32 *__restrict__ nul32,
+                                                       const u32 *__restrict__ del32, u64 P, int wide, int which /*2 surv, 3 filled*/,
+                                                       const u64 *__restrict__ tile_offs, u64 cap, u64 *slots, u64 *klo_out,
+                                                       u64 *khi_out, u32 *l_out, u32 *r_out)
+{
+    __shared__ u32 wcnt[TILE / 32 + 1];
+    const int tid = threadIdx.x;
+    const u64 n_tiles = (P + TILE - 1) / TILE;
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        bool keep[TILE / 256];
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++) {
+            u64 i = tile * TILE + (u64)e * 256 + tid;
+            bool filled = i < P && (nul32[i >> 5] & flag_mask(i));
+            bool del = filled && which == 2 && (del32[i >> 5] & flag_mask(i));
+            keep[e] = filled && !del;
+        }
+        u32 rk[TILE / 256];
+        tile_rank(keep, rk, wcnt);
+#pragma unroll
+        for (int e = 0; e < TILE / 256; e++) {
+            if (!keep[e]) continue;
+            u64 i = tile * TILE + (u64)e * 256 + tid;
+            u64 pos = tile_offs[tile * 4 + which] + rk[e];
+            if (pos >= cap) continue;
+            u64 klo, khi, links;
+            load_links_of_slot(img, i, wide, klo, khi, links);
+            if (slots) slots[pos] = i;
+            if (klo_out) klo_out[pos] = klo;
+            if (khi_out) khi_out[pos] = khi;
+            if (l_out) l_out[pos] = (u32)links;
+            if (r_out) r_out[pos] = (u32)(links >> 32);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// roofline denominator: uniformly random 32-B sector read-modify-writes
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 splitmix(u64 z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_random_rmw(Node *tab, u64 n_nodes, u64 n_ops, u64 seed)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x * G;
+    for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * G; base < n_ops; base += stride) {
+        Node *p[G]; u64 klo[G], khi[G], links[G], nord[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            u64 h = splitmix(seed + base + g);
+            p[g] = tab + __umul64hi(h, n_nodes);
+            load_node(p[g], klo[g], khi[g], links[g], nord[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (base + g < n_ops) {
+                if (MODE == 0) p[g]->links = links[g] + 1;
+                else atomicCAS(&p[g]->links, links[g], links[g] + 1);
+            }
+        }
+    }
+}
+
+}  // namespace dbg

@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's build interface (DBG_contig/DBGgraph.h:25-66, kmerSet.h:88-99) on
+top of the C ABI.  Names, argument meaning and error behaviour follow the reference:
+
+    KmerSet            <- struct KmerSet (kmerSet.h:88-99): size, count, max, load_factor, array, nul_flag, del_flag
+    build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_format=1, initHashSize=1.0, ...)
+                       <- DBGgraph.cpp:364 + the globals main.cpp:166-193 sets from the command line
+    calculate_kmer_links(kset, KmerFreqCutoff=2)   <- contig.cpp:107-205
+
+All computation happens in libdbgb200.so on the GPU; this file only moves buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import sys
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+NODE16 = np.dtype([("kmer", "<u8"), ("l_link", "<u4"), ("r_link", "<u4")])
+NODE32 = np.dtype([("kmer", "<u8"), ("kmer_hi", "<u8"), ("l_link", "<u4"), ("r_link", "<u4"), ("pad", "<u8")])
+UINT64_MAX = (1 << 64) - 1
+
+
+def init_slots_from_g(init_hash_size_g: float) -> int:
+    """(uint64)(initHashSize * 1000000000), DBGgraph.cpp:381"""
+    return int(float(init_hash_size_g) * 1000000000)
+
+
+class DBGBuilder:
+    """One dbg_ctx: create -> submit* -> finalize -> export*.  Context manager; frees the device table."""
+
+    def __init__(self, K=31, max_read_len=250, init_slots=None, init_g=None, load_factor=0.7, device=0,
+                 track_order=True, shard_rank=0, shard_count=1, force_wide=False):
+        self.L = capi.load()
+        if init_slots is None:
+            init_slots = init_slots_from_g(1.0 if init_g is None else init_g)
+        p = capi.dbg_params()
+        p.K, p.max_read_len, p.init_slots = int(K), int(max_read_len), int(init_slots)
+        p.load_factor, p.device, p.track_order = float(load_factor), int(device), int(bool(track_order))
+        p.shard_rank, p.shard_count, p.force_wide = int(shard_rank), int(shard_count), int(bool(force_wide))
+        self.K, self.device = int(K), int(device)
+        self.h = C.c_void_p()
+        rc = self.L.dbg_create(C.byref(self.h), C.byref(p))
+        if rc != capi.DBG_OK:
+            msg = self.L.dbg_last_error().decode()
+            if self.h:
+                self.L.dbg_destroy(self.h)
+                self.h = C.c_void_p()
+            raise capi.DbgError(rc, "dbg_create", msg)
+        self.wide = int(K) > 31 or bool(force_wide)
+        self.stats = None
+
+    # ---- life cycle ----
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dbg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        capi.check(self.L.dbg_reset(self.h), "dbg_reset")
+        self.stats = None
+
+    # ---- input ----
+    def submit(self, bases, offs):
+        """one reader block from host memory: reads are bases[offs[i]:offs[i+1]] (ASCII uint8)"""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = len(offs) - 1
+        if n <= 0:
+            return
+        bp = bases.ctypes.data if bases.size else 0
+        capi.check(self.L.dbg_submit_reads(self.h, bp or None, offs.ctypes.data, n), "dbg_submit_reads")
+
+    def submit_ptr(self, bases_ptr, offs_ptr, n_reads):
+        capi.check(self.L.dbg_submit_reads(self.h, bases_ptr, offs_ptr, int(n_reads)), "dbg_submit_reads")
+
+    def submit_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index=None, stream=None):
+        idx = UINT64_MAX if first_read_index is None else int(first_read_index)
+        capi.check(self.L.dbg_submit_reads_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base),
+                                                  int(total_bases), idx, stream), "dbg_submit_reads_device")
+
+    def extract_tuples_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index,
+                              n_parts, d_tuples_ptr, bucket_stride, d_counts_ptr, stream=None):
+        capi.check(self.L.dbg_extract_tuples_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base),
+                                                    int(total_bases), int(first_read_index), int(n_parts), d_tuples_ptr,
+                                                    int(bucket_stride), d_counts_ptr, stream), "dbg_extract_tuples_device")
+
+    def insert_tuples_device(self, d_tuples_ptr, n, stream=None):
+        capi.check(self.L.dbg_insert_tuples_device(self.h, d_tuples_ptr, int(n), stream), "dbg_insert_tuples_device")
+
+    @property
+    def tuple_bytes(self):
+        return int(self.L.dbg_tuple_bytes(self.h))
+
+    def get_polyA_counts(self):
+        a = np.zeros(8, dtype=np.uint64)
+        capi.check(self.L.dbg_get_polyA_counts(self.h, a.ctypes.data), "dbg_get_polyA_counts")
+        return a
+
+    def set_polyA_counts(self, a):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        capi.check(self.L.dbg_set_polyA_counts(self.h, a.ctypes.data), "dbg_set_polyA_counts")
+
+    # ---- results ----
+    def finalize(self):
+        st = capi.dbg_stats()
+        capi.check(self.L.dbg_finalize(self.h, C.byref(st)), "dbg_finalize")
+        self.stats = st.as_dict()
+        return self.stats
+
+    def get_stats(self):
+        st = capi.dbg_stats()
+        capi.check(self.L.dbg_get_stats(self.h, C.byref(st)), "dbg_get_stats")
+        return st.as_dict()
+
+    def export_kmerset(self, array=None, nul_flag=None):
+        """-> (array[P] of NODE16/NODE32 in reference slot layout, nul_flag[P/8+1])"""
+        P = self.stats["array_size"] if self.stats else self.get_stats()["array_size"]
+        dt = NODE32 if self.wide else NODE16
+        if array is None:
+            array = np.empty(P, dtype=dt)
+        if nul_flag is None:
+            nul_flag = np.empty(P // 8 + 1, dtype=np.uint8)
+        capi.check(self.L.dbg_export_kmerset(self.h, array.ctypes.data, nul_flag.ctypes.data), "dbg_export_kmerset")
+        return array, nul_flag
+
+    def export_links(self, freq_cutoff=2, lists=True):
+        P = self.stats["array_size"]
+        klink = np.empty(2 * P, dtype=np.uint8)
+        del_flag = np.empty(P // 8 + 1, dtype=np.uint8)
+        depth = np.zeros(256, dtype=np.int64)
+        stats3 = np.zeros(3, dtype=np.int64)
+        nt, nb = C.c_uint64(0), C.c_uint64(0)
+        # size query first (lists NULL), then exact-size lists
+        capi.check(self.L.dbg_export_links(self.h, int(freq_cutoff), klink.ctypes.data, del_flag.ctypes.data, depth.ctypes.data,
+                                           None, C.byref(nt), None, C.byref(nb), stats3.ctypes.data), "dbg_export_links")
+        tips = np.zeros(max(nt.value, 1), dtype=np.uint64)
+        branches = np.zeros(max(nb.value, 1), dtype=np.uint64)
+        if lists:
+            ct, cb = C.c_uint64(len(tips)), C.c_uint64(len(branches))
+            capi.check(self.L.dbg_export_links(self.h, int(freq_cutoff), None, None, None, tips.ctypes.data, C.byref(ct),
+                                               branches.ctypes.data, C.byref(cb), None), "dbg_export_links")
+        return dict(klink=klink, del_flag=del_flag, depth_stat=depth, tips=tips[:nt.value], branches=branches[:nb.value],
+                    total=int(stats3[0]), deleted=int(stats3[1]), linear=int(stats3[2]))
+
+    def dump_compact(self, freq_cutoff=-1):
+        n = C.c_uint64(0)
+        capi.check(self.L.dbg_dump_compact(self.h, int(freq_cutoff), None, None, None, None, None, C.byref(n)), "dbg_dump_compact")
+        m = max(n.value, 1)
+        out = dict(slot=np.zeros(m, np.uint64), kmer=np.zeros(m, np.uint64), kmer_hi=np.zeros(m, np.uint64),
+                   l=np.zeros(m, np.uint32), r=np.zeros(m, np.uint32))
+        cap = C.c_uint64(m)
+        capi.check(self.L.dbg_dump_compact(self.h, int(freq_cutoff), out["slot"].ctypes.data, out["kmer"].ctypes.data,
+                                           out["kmer_hi"].ctypes.data, out["l"].ctypes.data, out["r"].ctypes.data,
+                                           C.byref(cap)), "dbg_dump_compact")
+        return {k: v[:n.value] for k, v in out.items()}
+
+    def device_image(self):
+        a, f = C.c_void_p(), C.c_void_p()
+        capi.check(self.L.dbg_device_image(self.h, C.byref(a), C.byref(f)), "dbg_device_image")
+        return a.value, f.value
+
+    def timings(self):
+        ms = np.zeros(8, dtype=np.float32)
+        capi.check(self.L.dbg_get_timings(self.h, ms.ctypes.data), "dbg_get_timings")
+        return dict(clear_ms=float(ms[0]), build_ms=float(ms[1]), layout_ms=float(ms[2]), links_ms=float(ms[3]),
+                    h2d_ms=float(ms[4]), d2h_ms=float(ms[5]))
+
+    @property
+    def launches(self):
+        return int(self.L.dbg_launch_count(self.h))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-shaped interface
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class KmerSet:
+    """struct KmerSet, kmerSet.h:88-99"""
+    e_size: int
+    size: int
+    count: int
+    count_conflict: int
+    max: int
+    load_factor: float
+    iter_ptr: int
+    array: np.ndarray
+    nul_flag: np.ndarray
+    del_flag: np.ndarray
+    # extras (not in the reference struct)
+    Total_reads_num: int = 0
+    Kmer_total_num: int = 0
+    occurrences: int = 0
+    timings: dict = field(default_factory=dict)
+
+    def is_entity_null(self, idx):   # kmerSet.h:144-147
+        return 1 - ((int(self.nul_flag[idx // 8]) >> (7 - idx % 8)) & 1)
+
+    def filled_slots(self):
+        bits = np.unpackbits(self.nul_flag)[: self.size]
+        return np.nonzero(bits)[0].astype(np.uint64)
+
+
+def read_reads_file(path, Input_file_format=1):
+    """The reference's reader (DBGgraph.cpp:244-272): -f 1: a line starting with '@' -> next line is the
+    read, two more lines skipped; -f 2: a line starting with '>' -> next single line is the read.  Plain or
+    gzip files (gzstream).  Returns (bases uint8, offs uint64)."""
+    opener = gzip.open if _is_gzip(path) else open
+    seqs = []
+    with opener(path, "rb") as f:
+        if Input_file_format == 1:
+            for line in f:
+                if line[:1] == b"@":
+                    seqs.append(f.readline().rstrip(b"\n"))
+                    f.readline(); f.readline()
+        else:
+            for line in f:
+                if line[:1] == b">":
+                    seqs.append(f.readline().rstrip(b"\n"))
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    return bases, offs
+
+
+def _is_gzip(path):
+    with open(path, "rb") as f:
+        return f.read(2) == b"\x1f\x8b"
+
+
+def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_format=1, initHashSize=1.0,
+                         hashLoadFactor=0.7, BufferNum=10000, device=0, track_order=True, log=None):
+    """build_debruijn_graph (DBGgraph.cpp:364-430) with the build phase on the GPU.  `reads_files` is the
+    list reading_file_list() returns (seqKmer.cpp:101-114), or a list of (bases, offs) arrays."""
+    log = log or (lambda s: None)
+    with DBGBuilder(K=KmerSize, max_read_len=maxReadLen, init_g=initHashSize, load_factor=hashLoadFactor,
+                    device=device, track_order=track_order) as b:
+        for f in reads_files:
+            bases, offs = f if isinstance(f, tuple) else read_reads_file(f, Input_file_format)
+            b.submit(bases, offs)
+        st = b.finalize()
+        if st["count"] - 1 > st["max_cutoff"]:
+            print("Alert: node count exceeds max_cutoff; the reference may have enlarged its hash here, "
+                  "slot layout parity with the reference is not guaranteed (raise -i)", file=sys.stderr)
+        array, nul = b.export_kmerset()
+        ks = KmerSet(e_size=32 if b.wide else 16, size=st["array_size"], count=st["count"], count_conflict=st["conflict"],
+                     max=st["max_cutoff"], load_factor=st["load_factor"], iter_ptr=0, array=array, nul_flag=nul,
+                     del_flag=np.zeros(st["array_size"] // 8 + 1, dtype=np.uint8), Total_reads_num=st["reads"],
+                     Kmer_total_num=st["kmers_logged"], occurrences=st["occurrences"], timings=b.timings())
+    return ks

@@ -1,0 +1,181 @@
+/* dbg_b200.h -- C ABI of libdbgb200.so: the B200 (sm_100a) implementation of DBG_assembly's
+ * De Bruijn graph BUILD hot path.  Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * What it replaces in the reference (paths relative to fanagislab/DBG_assembly, DBG_contig/):
+ *   the body of build_debruijn_graph()            DBGgraph.cpp:364-430
+ *     - thread_parseBlock   (2-bit encode, rolling fwd/rc k-mer, canonical pick, neighbour bases)
+ *                                                  DBGgraph.cpp:38-120, seqKmer.cpp:9-41,89-97
+ *     - thread_updatekmers  (hash_code % P, linear probing, CAS claim, 8-bit saturating link lanes,
+ *                            poly-A side node)     DBGgraph.cpp:126-213, kmerSet.h:105-116
+ *     - init_kmerset_parallel / find_next_prime / add_node_to_kmerset
+ *                                                  kmerSet.cpp:72-127,253-273
+ *   and, optionally, the first pass of build_contig_sequence(): calculate_kmer_links()
+ *                                                  contig.cpp:107-205
+ * The reference has no FFI layer; its seam is the global `KmerSet *kset` (DBGgraph.h:31) handed from
+ * build_debruijn_graph (main.cpp:204) to build_contig_sequence (main.cpp:207).  A front end keeps its
+ * getopt/main, calls dbg_create .. dbg_export_kmerset from its build_debruijn_graph(), and gets the
+ * KmerSet image in the reference's own slot layout (same as `debruijn_contig -t 1`), so that
+ * contig.cpp runs unchanged on it.  integration/DBGgraph_b200.cpp is that binding; INTEGRATION.md
+ * explains it.
+ *
+ * Conventions: every function returns 0 (DBG_OK) or a negative DBG_ERR_* code; no exceptions, no
+ * aborts.  Host buffers are caller-owned.  A context is bound to one CUDA device and must be driven
+ * from one host thread at a time (the reference enters its build from main() only, main.cpp:204).
+ * There is NO CPU fallback: without a CUDA device dbg_create fails with DBG_ERR_CUDA.
+ */
+#ifndef DBG_B200_H_
+#define DBG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBG_OK                 0
+#define DBG_ERR_INVALID       -1   /* bad argument (K out of range, NULL pointer, ...)                 */
+#define DBG_ERR_CUDA          -2   /* CUDA runtime error; dbg_last_error() has the text                */
+#define DBG_ERR_NOMEM         -3   /* device or pinned-host allocation failed                          */
+#define DBG_ERR_TABLE_FULL    -4   /* distinct k-mers exceeded the table (reference would enlarge)     */
+#define DBG_ERR_STATE         -5   /* call order violated (e.g. submit after finalize)                 */
+#define DBG_ERR_BUFFER        -6   /* caller-provided output buffer too small                          */
+
+/* reference node, kmerSet.h:70-75 (16 B, K <= 31) */
+typedef struct { uint64_t kmer; uint32_t l_link; uint32_t r_link; } dbg_node16;
+/* 128-bit twin for 31 < K <= 63 (no reference counterpart) */
+typedef struct { uint64_t kmer_lo; uint64_t kmer_hi; uint32_t l_link; uint32_t r_link; uint64_t pad; } dbg_node32;
+
+typedef struct {
+    int32_t  K;              /* -k  k-mer size; 1..31 -> 64-bit path, 32..63 -> 128-bit path (main.cpp:168)  */
+    int32_t  max_read_len;   /* -r  reads are trimmed to this length (DBGgraph.cpp:63); <= 65535            */
+    uint64_t init_slots;     /* (uint64)(-i * 1e9): raw slot request; the library applies the reference's
+                                find_next_prime (kmerSet.cpp:98-105)                                        */
+    float    load_factor;    /* -l  (clamped like kmerSet.cpp:110-111); max = (uint64)(P * load_factor)      */
+    int32_t  device;         /* CUDA device ordinal                                                          */
+    int32_t  track_order;    /* 1: record first-occurrence ordinals so dbg_export_kmerset reproduces the
+                                slot layout of the reference run with -t 1; 0: layout is
+                                a valid linear-probing layout but cluster-internal order is arbitrary        */
+    int32_t  shard_rank;     /* multi-GPU: this context owns home slots [rank*ceil(P/n), ...) of the P-slot  */
+    int32_t  shard_count;    /* table; 0/1 = unsharded                                                       */
+    int32_t  force_wide;     /* 1: use the 128-bit path even for K <= 31 (tests pin it against the 64-bit)   */
+    int32_t  reserved[5];
+} dbg_params;
+
+typedef struct {
+    uint64_t array_size;     /* P   (KmerSet.size)                                                           */
+    uint64_t max_cutoff;     /* KmerSet.max                                                                  */
+    uint64_t count;          /* distinct nodes incl. the k-mer-0 node once finalized (KmerSet.count)         */
+    uint64_t conflict;       /* probe steps on the device table (NOT comparable to the reference's counter)  */
+    uint64_t reads;          /* Total_reads_num                                                              */
+    uint64_t kmers_logged;   /* Kmer_total_num: sum of untrimmed len-K+1 (DBGgraph.cpp:101)                  */
+    uint64_t occurrences;    /* (k-mer,left,right) updates actually applied = the benchmark's unit of work   */
+    uint64_t polyA_l, polyA_r; /* the side node's link words (DBGgraph.cpp:153-164)                         */
+    uint64_t shard_lo, shard_hi; /* home-slot range owned by this context                                    */
+    float    load_factor;    /* after clamping                                                               */
+    int32_t  wide;           /* 1 if the 128-bit path is in use                                              */
+} dbg_stats;
+
+typedef struct dbg_ctx dbg_ctx;
+
+/* ---- scalar helpers kept bit-identical to the reference (also used by front ends for logging) ---- */
+uint64_t dbg_find_next_prime(uint64_t n);               /* kmerSet.cpp:72-95 incl. its float-sqrt quirk  */
+uint64_t dbg_hash_code(uint64_t kmer);                  /* kmerSet.h:105-116                             */
+uint64_t dbg_hash_code_wide(uint64_t lo, uint64_t hi);  /* == dbg_hash_code(lo) when hi == 0             */
+const char *dbg_strerror(int code);
+const char *dbg_last_error(void);                       /* thread-local text of the last failure         */
+int  dbg_device_count(void);                            /* 0 when no CUDA device is visible              */
+
+/* pinned host memory for read buffers (front ends read/decode straight into it) */
+int  dbg_host_alloc(void **p, uint64_t bytes);
+int  dbg_host_free(void *p);
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+/* init_kmerset_parallel + the globals of build_debruijn_graph (DBGgraph.cpp:371-402) */
+int  dbg_create(dbg_ctx **ctx, const dbg_params *params);
+void dbg_destroy(dbg_ctx *ctx);
+
+/* One reader block (parse_one_reads_file's hand-off, DBGgraph.cpp:244-321): reads are
+ * bases[offs[i] .. offs[i+1]) (ASCII, domain [ACGTNacgtn]), i in [0, n_reads).  Blocks are applied in
+ * call order.  Returns after the host->device copy of this block; the kernels run asynchronously and
+ * overlap the next block's copy. */
+int  dbg_submit_reads(dbg_ctx *ctx, const char *bases, const uint64_t *offs, uint64_t n_reads);
+
+/* Same, inputs already resident on this context's device (offs has n_reads+1 entries, offs[0] may be
+ * non-zero; total_bases = offs[n_reads]-offs[0]).  first_read_index = global index of read 0 (orders
+ * occurrences across ranks); pass UINT64_MAX to continue this context's own running count.
+ * stream: a cudaStream_t, or NULL for the context's stream. */
+int  dbg_submit_reads_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                             uint64_t first_base, uint64_t total_bases, uint64_t first_read_index, void *stream);
+
+/* ---- multi-GPU building blocks (owner-computes split of thread_updatekmers, DBGgraph.cpp:148) ---- */
+/* 16-B occurrence tuple (K <= 31): kmer, meta = ordinal<<8 | right<<4 | left ; wide tuples add kmer_hi
+ * (24 B, padded to 32).  Extract all occurrences of a device-resident block, bucketed by owner shard
+ * (owner = (hash % P) / ceil(P/n_parts)), into d_tuples (capacity cap tuples, laid out bucket after
+ * bucket at bucket_stride tuples); d_counts[n_parts] receives the bucket sizes. */
+int  dbg_extract_tuples_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                               uint64_t first_base, uint64_t total_bases, uint64_t first_read_index,
+                               int32_t n_parts, void *d_tuples, uint64_t bucket_stride,
+                               uint64_t *d_counts, void *stream);
+/* Insert n tuples (all owned by this context's shard) produced by dbg_extract_tuples_device. */
+int  dbg_insert_tuples_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, void *stream);
+int  dbg_tuple_bytes(const dbg_ctx *ctx);               /* 16 or 32 */
+/* add a peer's poly-A counters / read counters (tiny all-reduce done by the caller) */
+int  dbg_get_polyA_counts(dbg_ctx *ctx, uint64_t counts[8]);
+int  dbg_set_polyA_counts(dbg_ctx *ctx, const uint64_t counts[8]);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+/* Tail of build_debruijn_graph: waits for all blocks, builds the reference-layout image on the device
+ * and appends the k-mer-0 node last (DBGgraph.cpp:418).  Fills *stats (may be NULL). */
+int  dbg_finalize(dbg_ctx *ctx, dbg_stats *stats);
+int  dbg_get_stats(dbg_ctx *ctx, dbg_stats *stats);
+
+/* The KmerSet the reference's traversal consumes (kmerSet.h:88-99): array[P] in reference slot
+ * layout (16-B nodes, or 32-B nodes on the wide path) and nul_flag[P/8+1], MSB first. */
+int  dbg_export_kmerset(dbg_ctx *ctx, void *array, uint8_t *nul_flag);
+
+/* calculate_kmer_links (contig.cpp:107-205) on the device: klink[P*2] (KmerLink bit layout,
+ * contig.h:31-42), del_flag[P/8+1], depth_hist[256], index-ordered tip and branch lists (capacity
+ * *n_tips / *n_branches on input, lengths on output), stats3 = {total, deleted, linear}. */
+int  dbg_export_links(dbg_ctx *ctx, int32_t freq_cutoff, uint8_t *klink, uint8_t *del_flag,
+                      int64_t depth_hist[256], uint64_t *tips, uint64_t *n_tips,
+                      uint64_t *branches, uint64_t *n_branches, int64_t stats3[3]);
+
+/* Stream-compacted dump, slot order: nodes that survive the low-frequency link filter
+ * (freq_cutoff < 0: every filled slot).  Any output pointer may be NULL; *n = capacity in, count out. */
+int  dbg_dump_compact(dbg_ctx *ctx, int32_t freq_cutoff, uint64_t *slots, uint64_t *kmers_lo,
+                      uint64_t *kmers_hi, uint32_t *l_link, uint32_t *r_link, uint64_t *n);
+
+/* device pointers of the finalized image, for callers that stay on the GPU (bench, multi-GPU gather) */
+int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
+
+/* per-phase device time of the most recent calls, milliseconds (CUDA events on the ctx stream):
+ * [0] table clear, [1] build kernels (sum over blocks), [2] layout+polyA (finalize), [3] links pass,
+ * [4] H2D copies, [5] D2H export */
+int  dbg_get_timings(dbg_ctx *ctx, float ms[8]);
+/* number of kernel launches issued by this context so far */
+uint64_t dbg_launch_count(const dbg_ctx *ctx);
+/* re-zero the table and counters so the context can build again (bench steps) */
+int  dbg_reset(dbg_ctx *ctx);
+
+/* ---- synthetic reads: counter-based, identical on host and device ----------------- */
+typedef struct {
+    uint64_t seed;
+    uint64_t genome_len;
+    uint32_t read_len;       /* every read has this length                                    */
+    uint32_t insert;         /* paired-end fragment length (mate 1 = reverse strand of its end) */
+    uint32_t err_per_2p24;   /* substitution probability * 2^24                                */
+    uint32_t n_per_2p24;     /* 'N' probability * 2^24                                         */
+} dbg_synth_params;
+int  dbg_synth_reads_host(const dbg_synth_params *p, uint64_t first_read, uint64_t n_reads, char *out);
+int  dbg_synth_reads_device(const dbg_synth_params *p, uint64_t first_read, uint64_t n_reads, char *d_out,
+                            int32_t device, void *stream);
+
+/* ---- roofline denominators measured on the spot (bench.py) --------------------------------------- */
+/* uniformly random 32-B sector read-modify-writes over `bytes` of device memory, `n_ops` operations;
+ * returns milliseconds (CUDA events).  mode 0: plain load+store, 1: load + 64-bit atomicCAS. */
+int  dbg_measure_random_rmw(int32_t device, uint64_t bytes, uint64_t n_ops, int32_t mode, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for the CPU oracle (oracle/liboracle.so) and runner for
+the compiled reference (oracle/_ref/*).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package dbg_assembly_b200 never does (tests/test_layout.py greps for that).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+REF_DRIVER = os.path.join(REF_DIR, "ref_build_driver")
+REF_CONTIG = os.path.join(REF_DIR, "debruijn_contig_ref")
+REF_ELF = os.path.join(REF_DIR, "debruijn_contig_elf")
+B200_CONTIG = os.path.join(REF_DIR, "debruijn_contig_b200")
+
+_lib = None
+
+
+def build():
+    """(Re)build liboracle.so and, when /root/reference exists, oracle/_ref/*."""
+    subprocess.run(["make", "-C", HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    u64, u8p, u64p, u32p, i64p = C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)
+    L.orc_base_code.restype = C.c_int; L.orc_base_code.argtypes = [C.c_ubyte]
+    L.orc_seq2bit.restype = u64; L.orc_seq2bit.argtypes = [C.c_char_p, C.c_int]
+    L.orc_rev_com_kbit.restype = u64; L.orc_rev_com_kbit.argtypes = [u64, C.c_int]
+    L.orc_hash_code.restype = u64; L.orc_hash_code.argtypes = [u64]
+    L.orc_hash_code_wide.restype = u64; L.orc_hash_code_wide.argtypes = [u64, u64]
+    L.orc_rev_com_wide.restype = None; L.orc_rev_com_wide.argtypes = [u64, u64, C.c_int, u64p, u64p]
+    L.orc_is_prime.restype = C.c_int; L.orc_is_prime.argtypes = [u64]
+    L.orc_find_next_prime.restype = u64; L.orc_find_next_prime.argtypes = [u64]
+    L.orc64_parse_read.restype = C.c_int
+    L.orc64_parse_read.argtypes = [C.c_char_p, u64, C.c_int, C.c_int, u64p, u8p, u8p]
+    L.orc128_parse_read.restype = C.c_int
+    L.orc128_parse_read.argtypes = [C.c_char_p, u64, C.c_int, C.c_int, u64p, u64p, u8p, u8p]
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int, C.c_int, u64, C.c_float, u64, u64, C.c_int]
+    L.orc_destroy.restype = None; L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_add_file.restype = u64; L.orc_add_file.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64]
+    L.orc_finish.restype = None; L.orc_finish.argtypes = [C.c_void_p]
+    for name in ("size", "count", "conflict", "max", "doublings", "total_reads", "kmers_logged", "occurrences"):
+        f = getattr(L, "orc_" + name); f.restype = u64; f.argtypes = [C.c_void_p]
+    L.orc_node_bytes.restype = C.c_int; L.orc_node_bytes.argtypes = [C.c_void_p]
+    L.orc_array.restype = C.c_void_p; L.orc_array.argtypes = [C.c_void_p]
+    L.orc_nul_flag.restype = C.c_void_p; L.orc_nul_flag.argtypes = [C.c_void_p]
+    L.orc_dump.restype = u64; L.orc_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.orc_calculate_kmer_links.restype = None
+    L.orc_calculate_kmer_links.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    _lib = L
+    return L
+
+
+NODE16 = np.dtype([("kmer", "<u8"), ("l", "<u4"), ("r", "<u4")])
+NODE32 = np.dtype([("kmer", "<u8"), ("kmer_hi", "<u8"), ("l", "<u4"), ("r", "<u4"), ("pad", "<u8")])
+
+
+class OracleGraph:
+    """Sequential CPU build == reference with -t 1 (see dbg_oracle.h for the pinning status)."""
+
+    def __init__(self, K, max_read_len, init_slots, load_factor=0.7, max_double_times=10,
+                 buffer_reads=10000, wide=False):
+        self.L = lib()
+        self.K, self.wide = K, bool(wide)
+        self.h = self.L.orc_create(K, max_read_len, int(init_slots), float(load_factor),
+                                   int(max_double_times), int(buffer_reads), int(bool(wide)))
+        if not self.h:
+            raise ValueError("orc_create rejected the parameters")
+        self.finished = False
+
+    def add_file(self, bases: np.ndarray, offs: np.ndarray) -> int:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        if bases.size == 0:
+            bases = np.zeros(1, dtype=np.uint8)
+        return int(self.L.orc_add_file(self.h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1))
+
+    def finish(self):
+        if not self.finished:
+            self.L.orc_finish(self.h)
+            self.finished = True
+        return self
+
+    def __getattr__(self, name):
+        if name in ("size", "count", "conflict", "max", "doublings", "total_reads", "kmers_logged", "occurrences"):
+            return int(getattr(self.L, "orc_" + name)(self.h))
+        raise AttributeError(name)
+
+    def array(self) -> np.ndarray:
+        n = self.size
+        dt = NODE32 if self.wide else NODE16
+        p = self.L.orc_array(self.h)
+        buf = (C.c_uint8 * (n * dt.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=n).copy()
+
+    def nul_flag(self) -> np.ndarray:
+        n = self.size // 8 + 1
+        buf = (C.c_uint8 * n).from_address(self.L.orc_nul_flag(self.h))
+        return np.frombuffer(buf, dtype=np.uint8, count=n).copy()
+
+    def dump(self):
+        """filled slots in slot order -> dict of arrays slot, kmer, kmer_hi, l, r"""
+        n = self.count
+        out = {k: np.zeros(n, dtype=dt) for k, dt in
+               (("slot", np.uint64), ("kmer", np.uint64), ("kmer_hi", np.uint64), ("l", np.uint32), ("r", np.uint32))}
+        m = self.L.orc_dump(self.h, *(out[k].ctypes.data for k in ("slot", "kmer", "kmer_hi", "l", "r")))
+        assert m == n, (m, n)
+        return out
+
+    def kmer_links(self, freq_cutoff=2):
+        P, n = self.size, self.count
+        klink = np.zeros(2 * P, dtype=np.uint8)
+        del_flag = np.zeros(P // 8 + 1, dtype=np.uint8)
+        depth = np.zeros(256, dtype=np.int64)
+        tips = np.zeros(max(n, 1), dtype=np.uint64)
+        branches = np.zeros(max(n, 1), dtype=np.uint64)
+        nt, nb = C.c_uint64(0), C.c_uint64(0)
+        stats = np.zeros(3, dtype=np.int64)
+        self.L.orc_calculate_kmer_links(self.h, int(freq_cutoff), klink.ctypes.data, del_flag.ctypes.data,
+                                        depth.ctypes.data, tips.ctypes.data, C.addressof(nt),
+                                        branches.ctypes.data, C.addressof(nb), stats.ctypes.data)
+        return dict(klink=klink, del_flag=del_flag, depth_stat=depth, tips=tips[:nt.value].copy(),
+                    branches=branches[:nb.value].copy(), total=int(stats[0]), deleted=int(stats[1]),
+                    linear=int(stats[2]))
+
+    def close(self):
+        if self.h:
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def parse_read(read: bytes, K: int, max_read_len: int, wide=False):
+    L = lib()
+    n = max(0, min(len(read), max_read_len) - K + 1)
+    cap = max(n, 1)
+    lo = np.zeros(cap, np.uint64); hi = np.zeros(cap, np.uint64)
+    lb = np.zeros(cap, np.uint8); rb = np.zeros(cap, np.uint8)
+    u64p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    if wide:
+        m = L.orc128_parse_read(read, len(read), K, max_read_len, lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p),
+                                lb.ctypes.data_as(u8p), rb.ctypes.data_as(u8p))
+    else:
+        m = L.orc64_parse_read(read, len(read), K, max_read_len, lo.ctypes.data_as(u64p),
+                               lb.ctypes.data_as(u8p), rb.ctypes.data_as(u8p))
+    assert m == n
+    return lo[:m], hi[:m], lb[:m], rb[:m]
+
+
+# ---------------------------------------------------------------------------------------------------
+# the compiled reference (only where oracle/_ref exists: this container, or a box the snapshot reached)
+# ---------------------------------------------------------------------------------------------------
+def have_reference() -> bool:
+    return os.access(REF_DRIVER, os.X_OK)
+
+
+def write_fasta(path: str, bases: np.ndarray, offs: np.ndarray):
+    """one-line FASTA (-f 2), the format the reference's reader expects (DBGgraph.cpp:261-271)"""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offs = np.asarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    lens = (offs[1:] - offs[:-1]).astype(np.int64)
+    # each record: ">\n" + seq + "\n"
+    rec_len = lens + 3
+    out_offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rec_len, out=out_offs[1:])
+    out = np.empty(int(out_offs[-1]), dtype=np.uint8)
+    out[out_offs[:-1]] = ord(">")
+    out[out_offs[:-1] + 1] = ord("\n")
+    out[out_offs[1:] - 1] = ord("\n")
+    # scatter sequences: index arithmetic instead of a python loop
+    if bases.size:
+        dst = np.arange(int(offs[-1]), dtype=np.int64)
+        read_id = np.repeat(np.arange(n, dtype=np.int64), lens)
+        dst += (out_offs[:-1] + 2 - offs[:-1].astype(np.int64))[read_id]
+        out[dst] = bases[: int(offs[-1])]
+    with open(path, "wb") as f:
+        f.write(out.tobytes())
+
+
+def run_ref_build(files, K, max_read_len, init_g, threads=1, load=0.7, max_double=10, buffer_reads=10000,
+                  fmt=2, dump=True):
+    """Run the reference build phase (oracle/_ref/ref_build_driver).  Returns (stats, dump dict|None)."""
+    with tempfile.TemporaryDirectory() as td:
+        dump_path = os.path.join(td, "dump.bin")
+        cmd = [REF_DRIVER, "-k", str(K), "-r", str(max_read_len), "-f", str(fmt), "-t", str(threads),
+               "-i", repr(float(init_g)), "-l", repr(float(load)), "-e", str(max_double), "-b", str(buffer_reads)]
+        if dump:
+            cmd += ["-d", dump_path]
+        cmd += list(files)
+        p = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        stats = json.loads(p.stdout.decode().strip().splitlines()[-1])
+        d = None
+        if dump:
+            raw = open(dump_path, "rb").read()
+            magic, size, count = struct.unpack("<QQQ", raw[:24])
+            assert magic == 0x4442474B53455431
+            rec = np.frombuffer(raw, dtype=np.dtype([("slot", "<u8"), ("kmer", "<u8"), ("l", "<u4"), ("r", "<u4")]),
+                                offset=24, count=count)
+            d = dict(size=size, count=count, slot=rec["slot"].copy(), kmer=rec["kmer"].copy(),
+                     l=rec["l"].copy(), r=rec["r"].copy())
+        return stats, d
