@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- canonical k-mers/s into the De Bruijn graph (count + edges) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2]
+
+A "step" is one complete build of the graph from the synthetic read set of the workload:
+table clear -> fused encode/extract/insert kernels over ALL reads -> reference-layout image + k-mer-0 node.
+`value` has the reads resident in HBM; `e2e` goes through the host-buffer C ABI (dbg_submit_reads ...
+dbg_export_kmerset) with the H2D copy of the reads and the D2H copy of the finished KmerSet image inside
+the timed region.  N>1: one process per GPU (torchrun), reads dealt in contiguous blocks, k-mers sharded by
+owner slot range with one NCCL all-to-all per step; weak scaling (genome, reads and table grow with N).
+
+--impl reference times the reference's own CPU build (oracle/_ref/ref_build_driver = the unmodified
+DBG_contig sources) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "canonical k-mers/sec into DBG (count+edges)"
+UNIT = "k-mers/s"
+
+
+def workload(name, n_gpus, scale=1.0):
+    from dbg_assembly_b200 import synth
+    cfg = dict(synth.CONFIGS[name])
+    cfg["n_reads"] = int(cfg["n_reads"] * scale) // 2 * 2
+    cfg["genome_len"] = max(int(cfg["genome_len"] * scale), 4 * cfg["insert"])
+    cfg["init_g"] = cfg["init_g"] * scale
+    # weak scaling: per-GPU reads fixed, genome and table grow with N
+    cfg["genome_len_total"] = cfg["genome_len"] * n_gpus
+    cfg["n_reads_total"] = cfg["n_reads"] * n_gpus
+    cfg["init_g_total"] = cfg["init_g"] * n_gpus
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.index, self.stop_flag, self.th = index, False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True); self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own build on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, sample_reads, threads, steps, warmup, name):
+    """returns (values list [k-mers/s per timed step], info dict)"""
+    from dbg_assembly_b200 import synth
+    from oracle import oracle as orc          # test infrastructure: only this leg may touch it
+    p = synth.make_params(cfg["seed"], cfg["genome_len"], cfg["read_len"], cfg["insert"], cfg["err"], cfg["n_rate"])
+    bases, offs = synth.reads_host(p, 0, sample_reads)
+    occ = sample_reads * (cfg["read_len"] - cfg["K"] + 1)
+    frac = sample_reads / cfg["n_reads"]
+    init_g = cfg["init_g"] * frac            # table scaled with the sample so the load factor matches the full run
+    vals = []
+    if orc.have_reference():
+        kind = "reference"
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "sample.fa")
+            orc.write_fasta(path, bases, offs)
+            for i in range(warmup + steps):
+                stats, _ = orc.run_ref_build([path], cfg["K"], cfg["max_read_len"], init_g, threads=threads, dump=False, timeout=1500)
+                if i >= warmup:
+                    vals.append(occ / stats["wall_s"])
+    else:
+        kind, threads = "port", 1
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            o = orc.OracleGraph(cfg["K"], cfg["max_read_len"], int(init_g * 1e9), 0.7, 10, 10000)
+            o.add_file(bases, offs); o.finish()
+            dt = time.perf_counter() - t0
+            o.close()
+            if i >= warmup:
+                vals.append(occ / dt)
+    info = {"kind": kind, "cores": threads,
+            "sample": f"first {sample_reads} reads of {name} ({occ} k-mer occurrences, {frac:.3f} of the workload), table -i {init_g:.4g} "
+                      f"(scaled with the sample), one-line FASTA from tmpfs/disk, whole build_debruijn_graph() incl. file read"}
+    return vals, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload(args.workload, 1, args.scale)
+    threads = os.cpu_count() or 1
+    sample = min(cfg["n_reads"], args.ref_sample_reads)
+    vals, info = cpu_reference_run(cfg, sample, threads, args.steps, args.warmup, args.workload)
+    v = float(np.mean(vals))
+    occ = sample * (cfg["read_len"] - cfg["K"] + 1)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * occ / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": config_dict(args, cfg, 1),
+            "cpu_baseline": dict(info, value=v, unit=UNIT),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, cfg, n):
+    return {"workload": f"{args.workload}: synthetic {cfg['genome_len'] / 1e6:.2f} Mb genome x{n} GPUs, "
+                        f"{cfg['n_reads']} x {cfg['read_len']} bp paired reads per GPU ({cfg['n_reads'] * cfg['read_len'] / cfg['genome_len']:.0f}x), "
+                        f"{cfg['err'] * 100:g}% substitutions, {cfg['n_rate'] * 100:g}% N, K={cfg['K']}, -r {cfg['max_read_len']}, -i {cfg['init_g'] * n:g}",
+            "K": cfg["K"], "reads_per_gpu": cfg["n_reads"], "read_len": cfg["read_len"], "table_slots_request": int(cfg["init_g"] * n * 1e9),
+            "parallelism": f"hash-sharded x{n}" if n > 1 else "single GPU",
+            "l2_policy": "inputs (reads 460 MB, table 6.4 GB per GPU) far exceed the 126 MB L2; table re-zeroed every step",
+            "layout_parity": "track_order=1 (reference -t 1 slot layout)" if n == 1 else "sharded: node multiset (layout export is single-GPU)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import dbg_assembly_b200 as dbg
+    from dbg_assembly_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(f"bench.py --gpus {args.gpus} must be launched with torchrun (one rank per GPU)", file=sys.stderr)
+            return 2
+    if dbg.capi.device_count() == 0:
+        print("bench.py: no CUDA device -- libdbgb200 has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = workload(args.workload, world, args.scale)
+    n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
+    occ_rank = n * (L - K + 1)
+    p = synth.make_params(cfg["seed"], cfg["genome_len_total"], L, cfg["insert"], cfg["err"], cfg["n_rate"])
+    d_bases = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    first_read = rank * n
+    synth.reads_device(p, first_read, n, d_bases.data_ptr(), device=local)
+    d_offs = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    init_slots = int(cfg["init_g_total"] * 1000000000)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    extra = {}
+    if world == 1:
+        b = dbg.DBGBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True)
+        b.set_stream(stream)
+
+        def step():
+            b.reset()
+            b.submit_device(d_bases.data_ptr(), d_offs.data_ptr(), n, 0, n * L, first_read_index=0)
+            return b.finalize()
+        closer = b
+        launch_count = lambda: b.launches  # noqa: E731
+        timings = b.timings
+    else:
+        from dbg_assembly_b200.sharded import ShardedBuilder
+        sb = ShardedBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True)
+        sb.b.set_stream(stream)
+
+        def step():
+            sb.b.reset()
+            sb.add_reads_device(d_bases, d_offs, n, 0, n * L, first_read, occ_rank)
+            return sb.finalize()
+        closer = sb
+        launch_count = lambda: sb.b.launches  # noqa: E731
+        timings = sb.b.timings
+
+    for _ in range(args.warmup):
+        st = step()
+    barrier()
+    l0 = launch_count()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    build_ms, clear_ms, layout_ms = [], [], []
+    for _ in range(args.steps):
+        st = step()
+        tm = timings()
+        build_ms.append(tm["build_ms"]); clear_ms.append(tm["clear_ms"]); layout_ms.append(tm["layout_ms"])
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        occ_total = st["global_occurrences"]
+        nodes_total = st["global_count"]
+        extra["exchange_bytes_per_step_rank0"] = sb.exchange_bytes // (args.steps + args.warmup)
+    else:
+        occ_total = st["occurrences"]
+        nodes_total = st["count"]
+    ms_per_step = ms_total / args.steps
+    value = occ_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (the fused build kernel; insert kernel when sharded) ----
+    peak, peak_src = measured_peaks()
+    kb = float(np.mean(build_ms))
+    node_bytes = 32
+    achieved = st["occurrences"] * 2 * node_bytes / 2 / (kb * 1e-3) / 1e9 if kb > 0 else None   # occ x 32 B
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "traffic": None, "kernel": "k_build<InsertSink> (fused 2-bit pack + canonical k-mer + hash insert)" if world == 1 else "k_build<BucketSink> + k_insert_tuples",
+            "algorithmic_bytes_per_occurrence": 32, "kernel_ms_per_step": kb, "clear_ms_per_step": float(np.mean(clear_ms)),
+            "layout_ms_per_step": float(np.mean(layout_ms)), "peak_source": peak_src}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": config_dict(args, cfg, world), "clocks": clocks, "gpu_launches": int(launches),
+            "occurrences_per_step": int(occ_total), "nodes": int(nodes_total), "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "roofline": roof}
+    line.update(extra)
+
+    # ---- random-access denominator measured on the spot (rank 0) ----
+    if rank == 0 and not args.no_micro:
+        try:
+            import ctypes as C
+            Lb = dbg.capi.load()
+            res = {}
+            for mode, tag in ((0, "load_store"), (1, "load_cas")):
+                ms = C.c_float(0)
+                n_ops = 1 << 28
+                dbg.capi.check(Lb.dbg_measure_random_rmw(local, 6 << 30, n_ops, mode, C.byref(ms)), "dbg_measure_random_rmw")
+                res[tag + "_gbs_32B"] = n_ops * 32 / (ms.value * 1e-3) / 1e9      # algorithmic 32 B per op, like `achieved`
+            line["random_access"] = dict(res, note="uniform random 32-B sector RMW over a 6 GiB table, 2^28 ops, same units as roofline.achieved")
+            if achieved:
+                line["roofline"]["frac_of_random_rmw"] = achieved / res["load_cas_gbs_32B"]
+        except Exception as e:      # the microbenchmark must never take the headline down
+            line["random_access"] = {"error": str(e)}
+
+    # ---- e2e through the host-buffer C ABI (N=1: full export; N>1: host submit is single-GPU only) ----
+    if world == 1:
+        closer.close()
+        h_bases = dbg.capi.PinnedBuffer(n * L)
+        h_offs = dbg.capi.PinnedBuffer((n + 1) * 8)
+        h_bases.array[:] = d_bases.cpu().numpy()
+        np.frombuffer(h_offs.array, dtype=np.uint64)[:] = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+        P = st["array_size"]
+        h_arr = dbg.capi.PinnedBuffer(P * 16)
+        h_nul = dbg.capi.PinnedBuffer(P // 8 + 1)
+        del d_bases
+        torch.cuda.empty_cache()
+        b2 = dbg.DBGBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True)
+        Lb = dbg.capi.load()
+
+        def e2e_step():
+            b2.reset()
+            b2.submit_ptr(h_bases.ptr, h_offs.ptr, n)
+            s = b2.finalize()
+            dbg.capi.check(Lb.dbg_export_kmerset(b2.h, h_arr.ptr, h_nul.ptr), "dbg_export_kmerset")
+            return s
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        torch.cuda.synchronize()
+        e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            s2 = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        tm = b2.timings()
+        line["e2e"] = {"value": s2["occurrences"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * L + (n + 1) * 8),
+                       "d2h_bytes_per_step": int(P * 16 + P // 8 + 1), "ms_per_step": dt * 1e3, "steps": e_steps,
+                       "h2d_ms": tm["h2d_ms"], "d2h_ms": tm["d2h_ms"], "build_ms": tm["build_ms"], "layout_ms": tm["layout_ms"],
+                       "what": "dbg_submit_reads (pinned host reads) -> dbg_finalize -> dbg_export_kmerset (KmerSet image into pinned host memory); wall clock"}
+        b2.close()
+        for hb in (h_bases, h_offs, h_arr, h_nul):
+            hb.close()
+    else:
+        closer.close()
+        line["e2e"] = None
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            threads = os.cpu_count() or 1
+            cfg1 = workload(args.workload, 1, args.scale)
+            sample = min(cfg1["n_reads"], args.ref_sample_reads)
+            vals, info = cpu_reference_run(cfg1, sample, threads, 1, 0, args.workload)
+            line["cpu_baseline"] = dict(info, value=float(np.mean(vals)), unit=UNIT)
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; numbers at scale != 1 are not the metric)")
+    ap.add_argument("--ref-sample-reads", type=int, default=400_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-micro", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and args.scale == 1.0:
+        print("note: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

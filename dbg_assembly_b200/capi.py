@@ -55,7 +55,7 @@ SYMBOLS = [
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
     "dbg_export_links", "dbg_dump_compact", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
-    "dbg_reset", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
+    "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
 ]
 
 _lib = None
@@ -100,6 +100,7 @@ def load(build_if_missing: bool = True):
         "dbg_get_timings": (C.c_int, [vp, vp]),
         "dbg_launch_count": (u64, [vp]),
         "dbg_reset": (C.c_int, [vp]),
+        "dbg_set_stream": (C.c_int, [vp, vp]),
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),
         "dbg_synth_reads_device": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp, i32, vp]),
         "dbg_measure_random_rmw": (C.c_int, [i32, u64, u64, i32, C.POINTER(C.c_float)]),

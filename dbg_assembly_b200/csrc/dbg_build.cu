@@ -103,8 +103,9 @@ extern "C" int dbg_host_free(void *p)
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
-static const uint64_t SUB_BASES = 64ull << 20;   // host submit is cut into sub-blocks so copies overlap kernels
-static const uint64_t SUB_READS = 2ull << 20;
+// host submit is cut into sub-blocks so copies overlap kernels (env DBG_B200_SUB_BASES / _SUB_READS override, for tests)
+static const uint64_t SUB_BASES_DEFAULT = 64ull << 20;
+static const uint64_t SUB_READS_DEFAULT = 2ull << 20;
 static const uint64_t MARGIN_SLOTS = 1ull << 16; // overflow zone past a shard's home range (no wrap in the hot loop)
 
 struct EvPair { cudaEvent_t a, b; };
@@ -117,13 +118,13 @@ struct dbg_ctx {
     float lf;
     uint64_t shard_lo, shard_hi, shard_size, n_local;
     int n_shards;
-    cudaStream_t stream, copy_stream;
+    cudaStream_t stream, copy_stream, own_stream;
     Node *d_nodes;
     u64 *d_counters, *d_polyA;
     // host-submit staging (double buffered)
     char *d_bases[2];
     u64 *d_offs[2];
-    uint64_t cap_bases, cap_reads;
+    uint64_t cap_bases, cap_reads, sub_bases, sub_reads;
     cudaEvent_t ev_free[2];
     int cur;
     u64 *d_chunk_first;
@@ -185,7 +186,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
@@ -238,14 +239,27 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     c->shard_hi = c->shard_lo + c->shard_size < size ? c->shard_lo + c->shard_size : size;
     c->n_local = (c->shard_hi - c->shard_lo) + MARGIN_SLOTS;
     c->links_cutoff = INT32_MIN;
+    c->sub_bases = SUB_BASES_DEFAULT; c->sub_reads = SUB_READS_DEFAULT;
+    if (const char *e = getenv("DBG_B200_SUB_BASES")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 16) c->sub_bases = v; }
+    if (const char *e = getenv("DBG_B200_SUB_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->sub_reads = v; }
     *out = c;   // from here on the caller can dbg_destroy() after a failure
 
-    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * sizeof(Node)));
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
     return clear_table(c);
+}
+
+extern "C" int dbg_set_stream(dbg_ctx *c, void *stream)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaDeviceSynchronize());
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return DBG_OK;
 }
 
 extern "C" int dbg_reset(dbg_ctx *c)
@@ -361,6 +375,7 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
     if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
     if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
     CU_TRY(cudaSetDevice(c->device));
+    const uint64_t SUB_BASES = c->sub_bases, SUB_READS = c->sub_reads;
     uint64_t r0 = 0;
     while (r0 < n_reads) {
         // cut a sub-block: at most SUB_BASES bases / SUB_READS reads (at least one read)

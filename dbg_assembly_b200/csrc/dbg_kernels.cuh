@@ -375,8 +375,7 @@ __global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__
         }
         sink.consume(occ, nv);
     }
-    sink.finish();
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sink.t.counters + CNT_OCC, n);
+    sink.finish();   // occurrences were already counted where the tuples were extracted
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -75,6 +75,10 @@ class DBGBuilder:
         capi.check(self.L.dbg_reset(self.h), "dbg_reset")
         self.stats = None
 
+    def set_stream(self, stream):
+        """run this context on a caller-owned cudaStream_t (int handle), e.g. torch.cuda.current_stream().cuda_stream"""
+        capi.check(self.L.dbg_set_stream(self.h, stream), "dbg_set_stream")
+
     # ---- input ----
     def submit(self, bases, offs):
         """one reader block from host memory: reads are bases[offs[i]:offs[i+1]] (ASCII uint8)"""

@@ -1,0 +1,114 @@
+"""Multi-GPU build: one process per GPU, k-mers partitioned by owner = (hash_code(kmer) % P) / ceil(P/n)
+-- the reference's `kmer % threadNum` owner-computes split (DBGgraph.cpp:148) lifted to GPUs.  Every rank
+extracts the (k-mer, left, right, ordinal) tuples of its own reads (dbg_extract_tuples_device), buckets them
+by owner, exchanges them with ONE all-to-all over NCCL/NVLink (sizes first, then payload) and inserts what
+it received into its private shard (dbg_insert_tuples_device).  No further communication until export; the
+k-mer-0 side counters are summed with one tiny all-reduce.
+
+torch.distributed is plumbing here: the kernels are the C-ABI library's.  The exchange itself is
+device-agnostic (`Exchange`), so world_size-2 gloo tests on CPU cover the host logic with stand-in
+extract/insert callables.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_size(P: int, n: int) -> int:
+    return (P + n - 1) // n
+
+
+def owner_of(home_slot, P: int, n: int):
+    """owner rank of a home slot (same formula as BucketSink in dbg_kernels.cuh)"""
+    return home_slot // shard_size(P, n)
+
+
+class Exchange:
+    """all-to-all(v) of fixed-width tuples: sizes first, then payload."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def exchange_counts(self, send_counts: torch.Tensor) -> torch.Tensor:
+        """send_counts[q] = tuples this rank has for rank q -> recv_counts[q] = tuples rank q has for us"""
+        recv = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv, send_counts, group=self.group)
+        return recv
+
+    def exchange_payload(self, buckets, recv_counts_host, width: int, like: torch.Tensor):
+        """buckets[q]: [c_q, width] tensor for rank q.  Returns (recv [sum, width], offsets list)"""
+        total = int(sum(recv_counts_host))
+        recv = torch.empty((max(total, 1), width), dtype=like.dtype, device=like.device)
+        outs, off = [], 0
+        for c in recv_counts_host:
+            outs.append(recv[off:off + int(c)])
+            off += int(c)
+        dist.all_to_all(outs, list(buckets), group=self.group)
+        return recv[:total], total
+
+    def allreduce_sum_u64(self, a: np.ndarray, device) -> np.ndarray:
+        t = torch.from_numpy(a.astype(np.int64)).to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy().astype(np.uint64)
+
+
+class ShardedBuilder:
+    """The per-rank driver.  `reads` are this rank's own contiguous block of the global read sequence."""
+
+    def __init__(self, K, max_read_len, init_slots, load_factor=0.7, device=0, track_order=True, group=None,
+                 slack=1.25):
+        from .graph import DBGBuilder
+        self.ex = Exchange(group)
+        self.n, self.rank = self.ex.world, self.ex.rank
+        self.b = DBGBuilder(K=K, max_read_len=max_read_len, init_slots=init_slots, load_factor=load_factor, device=device,
+                            track_order=track_order, shard_rank=self.rank, shard_count=self.n)
+        self.device = torch.device("cuda", device)
+        self.width = self.b.tuple_bytes // 8        # int64 words per tuple
+        self.slack = slack
+        self._send = self._counts = None
+        self.exchange_bytes = 0
+
+    def close(self):
+        self.b.close()
+
+    def _buffers(self, n_occ_upper):
+        stride = int(n_occ_upper / self.n * self.slack) + 4096
+        need = self.n * stride * self.width
+        if self._send is None or self._send.numel() < need:
+            self._send = torch.empty(need, dtype=torch.int64, device=self.device)
+            self._counts = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        return stride
+
+    def add_reads_device(self, d_bases: torch.Tensor, d_offs: torch.Tensor, n_reads, first_base, total_bases,
+                         first_read_index, n_occ_upper):
+        """one block of this rank's reads, device resident.  n_occ_upper bounds its occurrence count."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stride = self._buffers(n_occ_upper)
+        self.b.extract_tuples_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
+                                     self.n, self._send.data_ptr(), stride, self._counts.data_ptr(), stream=stream)
+        recv_counts = self.ex.exchange_counts(self._counts)
+        sc = self._counts.cpu().tolist()
+        rc = recv_counts.cpu().tolist()
+        if max(sc) > stride:
+            raise RuntimeError(f"tuple bucket overflow ({max(sc)} > {stride}): raise slack")
+        view = self._send.view(self.n, stride, self.width)
+        buckets = [view[q, : sc[q]] for q in range(self.n)]
+        recv, total = self.ex.exchange_payload(buckets, rc, self.width, self._send)
+        self.exchange_bytes += (sum(sc) - sc[self.rank]) * self.width * 8
+        self.b.insert_tuples_device(recv.data_ptr(), total, stream=stream)
+        self._keep = recv    # keep alive until the insert kernel ran
+        return total
+
+    def finalize(self):
+        torch.cuda.synchronize(self.device)
+        polyA = self.ex.allreduce_sum_u64(self.b.get_polyA_counts(), self.device)
+        self.b.set_polyA_counts(polyA)
+        st = self.b.finalize()
+        tot = self.ex.allreduce_sum_u64(np.array([st["count"], st["occurrences"]], dtype=np.uint64), self.device)
+        st["global_count"] = int(tot[0]) + 1          # + the k-mer-0 node
+        st["global_occurrences"] = int(tot[1])
+        return st

@@ -156,6 +156,9 @@ int  dbg_get_timings(dbg_ctx *ctx, float ms[8]);
 uint64_t dbg_launch_count(const dbg_ctx *ctx);
 /* re-zero the table and counters so the context can build again (bench steps) */
 int  dbg_reset(dbg_ctx *ctx);
+/* run all of this context's kernels, memsets and copies on a caller-owned cudaStream_t (e.g. torch's
+ * current stream, so that CUDA events recorded there bracket the work); NULL restores the own stream */
+int  dbg_set_stream(dbg_ctx *ctx, void *stream);
 
 /* ---- synthetic reads: counter-based, identical on host and device ----------------- */
 typedef struct {

@@ -1,0 +1,200 @@
+// DBGgraph_b200.cpp -- the reference-side binding: a drop-in replacement for DBG_contig/DBGgraph.cpp.
+//
+// A maintainer of fanagislab/DBG_assembly swaps this file for DBGgraph.cpp in DBG_contig/Makefile and
+// links libdbgb200.so; main.cpp (getopt, parameter echo), contig.cpp (traversal), kmerSet.cpp (lookups
+// and flag helpers used by the traversal), seqKmer.cpp and gzstream.cpp stay untouched.  Command line,
+// parameter meaning, stderr log lines and all nine output files are the reference's.
+//
+// It defines the globals DBGgraph.h declares (DBGgraph.h:25-49) and build_debruijn_graph()
+// (DBGgraph.cpp:364): the host keeps the file reader (same framing as DBGgraph.cpp:244-272, through the
+// reference's own igzstream) and hands blocks of reads to the GPU library; hot loops #1 and #2
+// (thread_parseBlock / thread_updatekmers) run as CUDA kernels; the finished table comes back in the
+// reference's slot layout (== `debruijn_contig -t 1`) as the global `KmerSet *kset`.
+//
+// Differences a user can observe: the "conflict:" statistic counts GPU probe steps, "-t" only affects the
+// host traversal, and "-e" (enlarge) is not emulated: if the node count passes max_cutoff a warning is
+// printed (the reference would have enlarged and produced a different slot order; contents are the same).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "DBGgraph.h"     // the reference's header (globals + prototypes), found via -I<reference>/DBG_contig
+#include "dbg_b200.h"
+
+// ---- globals of DBGgraph.cpp:10-34 (same names, same defaults) -----------------------------------
+int KmerSize = 31;
+int maxReadLen = 250;
+int KmerNumInRead = 0;
+int Input_file_format = 1;
+string Output_prefix = "output";
+int threadNum = 10;
+KmerSet *kset;
+double initHashSize = 1.0;
+uint64_t maxDoubleHashTimes = 10;
+uint64_t doubleHashTimes = 0;
+float hashLoadFactor = 0.7;
+int BufferNum = 10000;
+string *RawReads;
+uint64_t *StoreKmer;
+uint8_t *StoreLeftBase;
+uint8_t *StoreRightBase;
+uint8_t *Signal;
+uint64_t Kmer_total_num = 0;
+uint64_t Total_reads_num = 0;
+uint64_t KmerHeadMaskVal = 0;
+uint64_t KmerRCOrVal[4];
+KmerNode *PolyA;
+clock_t time_start;
+clock_t time_end;
+
+static void die(const char *where, int rc)
+{
+    cerr << "libdbgb200: " << where << " failed: " << dbg_strerror(rc) << " -- " << dbg_last_error() << endl;
+    exit(1);
+}
+
+// one pinned staging block: bases + offsets
+struct Block {
+    char *bases;
+    uint64_t *offs;
+    uint64_t cap_bases, cap_reads, n_reads, n_bases;
+};
+
+static const uint64_t BLOCK_BASES = 256ull << 20;
+static const uint64_t BLOCK_READS = 4ull << 20;
+
+static void flush_block(dbg_ctx *ctx, Block &b)
+{
+    if (b.n_reads == 0) return;
+    b.offs[b.n_reads] = b.n_bases;
+    int rc = dbg_submit_reads(ctx, b.bases, b.offs, b.n_reads);
+    if (rc) die("dbg_submit_reads", rc);
+    b.n_reads = 0; b.n_bases = 0;
+}
+
+static void add_read(dbg_ctx *ctx, Block &b, const string &s)
+{
+    // only the first maxReadLen bases of a read are used (DBGgraph.cpp:63); a sequence larger than a whole
+    // block (> 256 MB) is cut there -- the only effect is on the logged, untrimmed k-mer count
+    size_t n = s.size() > b.cap_bases ? (size_t)maxReadLen : s.size();
+    if (b.n_reads == b.cap_reads || b.n_bases + n > b.cap_bases) flush_block(ctx, b);
+    b.offs[b.n_reads++] = b.n_bases;
+    memcpy(b.bases + b.n_bases, s.data(), n);
+    b.n_bases += n;
+}
+
+// reader of parse_one_reads_file (DBGgraph.cpp:244-272); blocks never span files
+static void parse_one_reads_file_b200(dbg_ctx *ctx, Block &b, string &reads_file)
+{
+    string LineStr, Seq;
+    igzstream currentFile;
+    currentFile.open(reads_file.c_str());
+    uint64_t in_block = 0;
+    if (Input_file_format == 1) {
+        while (getline(currentFile, LineStr, '\n')) {
+            if (LineStr[0] == '@') {
+                getline(currentFile, Seq, '\n');
+                getline(currentFile, LineStr, '\n');
+                getline(currentFile, LineStr, '\n');
+                add_read(ctx, b, Seq);
+                Total_reads_num++;
+                if (++in_block == (uint64_t)BufferNum) { cerr << "Load reads block " << Total_reads_num << endl; in_block = 0; }
+            }
+        }
+    } else {
+        while (getline(currentFile, LineStr, '\n')) {
+            if (LineStr[0] == '>') {
+                getline(currentFile, Seq, '\n');
+                add_read(ctx, b, Seq);
+                Total_reads_num++;
+                if (++in_block == (uint64_t)BufferNum) { cerr << "Load reads block " << Total_reads_num << endl; in_block = 0; }
+            }
+        }
+    }
+    cerr << "Load reads block " << Total_reads_num << endl;
+    cerr << "this block has reach the end of file " << endl;
+    flush_block(ctx, b);
+    currentFile.close();
+}
+
+void build_debruijn_graph(vector<string> &reads_files)
+{
+    time_start = clock();
+
+    // contig.h:127-130 needs the head mask (DBGgraph.cpp:371)
+    KmerHeadMaskVal = pow_integer(2, KmerSize * 2) - 1;
+    KmerRCOrVal[3] = 0;
+    KmerRCOrVal[1] = pow_integer(2, KmerSize * 2 - 1);
+    KmerRCOrVal[2] = pow_integer(2, KmerSize * 2 - 1 - 1);
+    KmerRCOrVal[0] = KmerRCOrVal[1] + KmerRCOrVal[2];
+    KmerNumInRead = maxReadLen - KmerSize + 1;
+
+    if (KmerSize > 31) { cerr << "debruijn_contig: -k max 31 for the 64-bit host traversal" << endl; exit(1); }
+
+    cerr << "Start to initialize the kmerset hash" << endl;
+    dbg_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.K = KmerSize;
+    prm.max_read_len = maxReadLen;
+    prm.init_slots = (uint64_t)(initHashSize * 1000000000);   // DBGgraph.cpp:381
+    prm.load_factor = hashLoadFactor;
+    prm.device = getenv("DBG_B200_DEVICE") ? atoi(getenv("DBG_B200_DEVICE")) : 0;
+    prm.track_order = 1;                                        // reproduce the -t 1 slot layout
+    dbg_ctx *ctx = NULL;
+    int rc = dbg_create(&ctx, &prm);
+    if (rc) die("dbg_create", rc);
+    cerr << "Hash initialization array size:  " << initHashSize << " G" << endl;
+    cerr << "The initialization memory used:  " << initHashSize * 16 << " G" << endl;
+    time_end = clock();
+    cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+
+    Block b;
+    memset(&b, 0, sizeof(b));
+    b.cap_bases = BLOCK_BASES; b.cap_reads = BLOCK_READS;
+    void *p = NULL;
+    if ((rc = dbg_host_alloc(&p, b.cap_bases))) die("dbg_host_alloc", rc);
+    b.bases = (char *)p;
+    if ((rc = dbg_host_alloc(&p, (b.cap_reads + 1) * sizeof(uint64_t)))) die("dbg_host_alloc", rc);
+    b.offs = (uint64_t *)p;
+
+    cerr << "\nparse input reads files: " << endl;
+    for (size_t i = 0; i < reads_files.size(); i++) {
+        cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
+        parse_one_reads_file_b200(ctx, b, reads_files[i]);
+        dbg_stats st;
+        if ((rc = dbg_get_stats(ctx, &st))) die("dbg_get_stats", rc);
+        Kmer_total_num = st.kmers_logged;
+        cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
+        cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
+        time_end = clock();
+        cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+    }
+
+    // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
+    dbg_stats st;
+    if ((rc = dbg_finalize(ctx, &st))) die("dbg_finalize", rc);
+    if (st.count - 1 > st.max_cutoff)
+        cerr << "\nAlert message: " << st.count << " kmer nodes exceed max_cutoff " << st.max_cutoff
+             << "; the CPU program would have enlarged its hash (-e). Node contents are unaffected, slot order may differ: raise -i\n" << endl;
+
+    // the KmerSet the traversal consumes (kmerSet.h:88-99, kmerSet.cpp:98-127)
+    kset = new KmerSet;
+    kset->e_size = sizeof(KmerNode);
+    kset->size = st.array_size;
+    kset->count = st.count;
+    kset->count_conflict = st.conflict;
+    kset->load_factor = st.load_factor;
+    kset->max = st.max_cutoff;
+    kset->iter_ptr = 0;
+    kset->array = (KmerNode *)malloc(kset->size * kset->e_size);
+    kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
+    kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
+    if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
+    if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
+
+    dbg_host_free(b.bases);
+    dbg_host_free(b.offs);
+    dbg_destroy(ctx);
+
+    print_kmerset_parameter(kset);
+}

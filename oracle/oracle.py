@@ -201,7 +201,7 @@ def write_fasta(path: str, bases: np.ndarray, offs: np.ndarray):
 
 
 def run_ref_build(files, K, max_read_len, init_g, threads=1, load=0.7, max_double=10, buffer_reads=10000,
-                  fmt=2, dump=True):
+                  fmt=2, dump=True, timeout=600):
     """Run the reference build phase (oracle/_ref/ref_build_driver).  Returns (stats, dump dict|None)."""
     with tempfile.TemporaryDirectory() as td:
         dump_path = os.path.join(td, "dump.bin")
@@ -210,7 +210,7 @@ def run_ref_build(files, K, max_read_len, init_g, threads=1, load=0.7, max_doubl
         if dump:
             cmd += ["-d", dump_path]
         cmd += list(files)
-        p = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        p = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout)
         stats = json.loads(p.stdout.decode().strip().splitlines()[-1])
         d = None
         if dump:

@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library loads, exports every symbol include/dbg_b200.h declares, its scalar helpers
+match the reference's known answers, and -- with no GPU -- it fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from dbg_assembly_b200 import capi as m
+    m.load()
+    return m
+
+
+def header_symbols():
+    txt = open(os.path.join(REPO, "include", "dbg_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b((?:dbg|kfreq)_[a-z0-9_A-Z]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(capi):
+    decl = header_symbols()
+    assert len(decl) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], check=True, stdout=subprocess.PIPE, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in decl if s not in exported]
+    assert not missing, f"declared in include/dbg_b200.h but not exported: {missing}"
+    # and the python binding covers them all
+    assert sorted(capi.SYMBOLS) == decl
+
+
+def test_scalar_helpers_known_answers(capi):
+    assert capi.hash_code(0) == 7654268697807496793
+    assert capi.hash_code(1) == 2320827452992767577
+    for n, p in ((10**7, 10000019), (10**8, 100000007), (10**9, 1000000007), (200000014, 200000033), (1000, 1009)):
+        assert capi.find_next_prime(n) == p
+    assert capi.hash_code_wide(987654321, 0) == capi.hash_code(987654321)
+
+
+def test_helpers_agree_with_oracle(capi, oracle_mod):
+    L = oracle_mod.lib()
+    rng = np.random.default_rng(5)
+    for k in rng.integers(0, 1 << 62, size=200, dtype=np.uint64).tolist():
+        assert capi.hash_code(k) == L.orc_hash_code(k)
+        assert capi.hash_code_wide(k, k >> 7) == L.orc_hash_code_wide(k, k >> 7)
+    for n in rng.integers(3, 10**7, size=50).tolist():
+        assert capi.find_next_prime(n) == L.orc_find_next_prime(n)
+
+
+def test_synth_host_is_deterministic_and_in_domain(capi):
+    from dbg_assembly_b200 import synth
+    p = synth.make_params(seed=2, genome_len=50_000, read_len=150, insert=500, err=0.01, n_rate=0.001)
+    a, offs = synth.reads_host(p, 0, 64)
+    b, _ = synth.reads_host(p, 32, 32)
+    assert np.array_equal(a[32 * 150:], b)                    # counter-based: any sub-range reproduces
+    assert set(np.unique(a).tolist()) <= set(b"ACGTN")
+    assert offs[-1] == 64 * 150
+    # mates come from opposite strands of one fragment: without errors mate 1 is the revcomp of the fragment end
+    q = synth.make_params(seed=9, genome_len=10_000, read_len=50, insert=50, err=0.0, n_rate=0.0)
+    r, _ = synth.reads_host(q, 0, 2)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    m0, m1 = r[:50].tolist(), r[50:].tolist()
+    assert m0 == [comp[c] for c in reversed(m1)]
+
+
+def test_no_gpu_means_loud_failure(capi):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    from dbg_assembly_b200 import DBGBuilder
+    with pytest.raises(capi.DbgError) as e:
+        DBGBuilder(K=31, max_read_len=100, init_slots=1000)
+    assert e.value.code == capi.DBG_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_bad_parameters(capi):
+    L = capi.load()
+    for K, R in ((0, 100), (64, 100), (31, 0), (31, 70000)):
+        p = capi.dbg_params()
+        p.K, p.max_read_len, p.init_slots, p.load_factor = K, R, 1000, 0.7
+        h = C.c_void_p()
+        assert L.dbg_create(C.byref(h), C.byref(p)) == capi.DBG_ERR_INVALID
+        assert not h.value
+    assert L.dbg_create(None, None) == capi.DBG_ERR_INVALID
+    assert L.dbg_finalize(None, None) == capi.DBG_ERR_INVALID
+    assert L.dbg_strerror(capi.DBG_ERR_TABLE_FULL).decode().startswith("k-mer table full")
+
+
+def test_product_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under dbg_assembly_b200/, include/ or integration/ may
+    import, link or execute oracle/ (bench.py may, but only in its cpu_baseline / --impl reference legs)"""
+    bad = []
+    for root in ("dbg_assembly_b200", "include", "integration"):
+        for dp, _, fns in os.walk(os.path.join(REPO, root)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"liboracle|dbg_oracle|from oracle|import oracle|orc_[a-z]", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_reader_framing(tmp_path):
+    """read_reads_file follows DBGgraph.cpp:244-272 (one-line FASTA / FASTQ, plain or gz)"""
+    import gzip
+    from dbg_assembly_b200.graph import read_reads_file
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">r1 x\nACGT\n>r2\nTTGCA\nGGGG\n>r3\n\n")
+    b, o = read_reads_file(str(fa), 2)
+    assert o.tolist() == [0, 4, 9, 9] and b.tobytes() == b"ACGTTTGCA"
+    fq = tmp_path / "a.fq.gz"
+    with gzip.open(fq, "wb") as f:
+        f.write(b"@r1\nACGTN\n+\nIIIII\n@r2\nGG\n+\nII\n")
+    b, o = read_reads_file(str(fq), 1)
+    assert o.tolist() == [0, 5, 7] and b.tobytes() == b"ACGTNGG"

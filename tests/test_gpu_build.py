@@ -1,0 +1,451 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(include/dbg_b200.h via dbg_assembly_b200.capi); the oracle (oracle/) is only the checker.
+
+Bar: bit-exact -- same nodes, same (l_link, r_link), same SLOT LAYOUT as the reference run with -t 1.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NO_ENLARGE, REPO, load_golden, random_reads, reads_to_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dbg():
+    import dbg_assembly_b200 as m
+    if m.capi.device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box (no CPU fallback exists)")
+    return m
+
+
+def gpu_build(dbg, files, K, R, init_slots, load=0.7, track=True, force_wide=False):
+    with dbg.DBGBuilder(K=K, max_read_len=R, init_slots=init_slots, load_factor=load, track_order=track,
+                        force_wide=force_wide) as b:
+        for bases, offs in files:
+            b.submit(bases, offs)
+        st = b.finalize()
+        arr, nul = b.export_kmerset()
+        return st, arr, nul
+
+
+def image_to_dump(arr, nul, P):
+    bits = np.unpackbits(nul)[:P]
+    slot = np.nonzero(bits)[0].astype(np.uint64)
+    sel = slot.astype(np.int64)
+    d = dict(slot=slot, kmer=arr["kmer"][sel], l=arr["l_link"][sel], r=arr["r_link"][sel])
+    if "kmer_hi" in arr.dtype.names:
+        d["kmer_hi"] = arr["kmer_hi"][sel]
+    # everything outside the filled slots must be zero (reference: calloc'ed array)
+    mask = np.ones(P, dtype=bool); mask[sel] = False
+    assert not arr["kmer"][mask].any() and not arr["l_link"][mask].any() and not arr["r_link"][mask].any()
+    return d
+
+
+def oracle_build(orc, files, K, R, init_slots, load=0.7, wide=False):
+    o = orc.OracleGraph(K, R, init_slots, load, 10, 1 << 40, wide=wide)   # one block per file: never enlarges
+    for bases, offs in files:
+        o.add_file(bases, offs)
+    o.finish()
+    return o
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference itself
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_NO_ENLARGE)
+@pytest.mark.parametrize("force_wide", [False, True])
+def test_golden_reference_tables(dbg, name, force_wide):
+    g = load_golden(name)
+    st, arr, nul = gpu_build(dbg, g["files"], g["K"], g["R"], g["init_slots"], g["load"], force_wide=force_wide)
+    assert st["array_size"] == g["size"]
+    assert st["max_cutoff"] == g["max"]
+    assert st["count"] == g["count"]
+    assert st["reads"] == g["reads"]
+    assert st["kmers_logged"] == g["kmers_logged"]
+    d = image_to_dump(arr, nul, g["size"])
+    assert np.array_equal(d["slot"], g["slot"]), "slot layout differs from the reference (-t 1)"
+    assert np.array_equal(d["kmer"], g["kmer"])
+    assert np.array_equal(d["l"], g["l"])
+    assert np.array_equal(d["r"], g["r"])
+    if force_wide:
+        assert not d["kmer_hi"].any()
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded random inputs against the oracle
+# ---------------------------------------------------------------------------------------------------
+CASES = [
+    # seed, K, R, n_reads, len_lo, len_hi, genome, load target
+    (11, 31, 150, 2000, 20, 200, 20000, 0.5),
+    (12, 31, 100, 3000, 90, 110, 3000, 0.9),     # heavy collisions, long clusters, wrap-around
+    (13, 15, 80, 1500, 1, 100, 5000, 0.6),
+    (14, 16, 60, 1500, 10, 90, 2000, 0.6),       # even K: palindromes
+    (15, 1, 20, 200, 0, 30, 100, 0.3),
+    (16, 2, 20, 200, 0, 30, 100, 0.5),
+    (17, 27, 250, 800, 200, 400, 30000, 0.4),    # reads longer than -r get trimmed
+    (18, 32, 120, 1500, 20, 150, 8000, 0.6),     # 128-bit path from here on
+    (19, 33, 120, 1500, 20, 150, 8000, 0.6),
+    (20, 47, 150, 1500, 40, 180, 8000, 0.8),
+    (21, 63, 100, 3000, 60, 120, 10000, 0.6),
+]
+
+
+@pytest.mark.parametrize("seed,K,R,n_reads,len_lo,len_hi,genome,load_target", CASES)
+def test_random_reads_match_oracle(dbg, oracle_mod, seed, K, R, n_reads, len_lo, len_hi, genome, load_target):
+    reads = random_reads(seed, n_reads, len_lo, len_hi, genome_len=genome)
+    reads += [b"", b"A" * (K + 3), b"T" * (K + 1), b"ACGT" * 20, b"N" * (K + 2)]
+    files = [reads_to_arrays(reads[: len(reads) // 2]), reads_to_arrays(reads[len(reads) // 2:])]
+    wide = K > 31
+    probe = oracle_build(oracle_mod, files, K, R, 50_000_000 // 100, wide=wide)
+    n_nodes = probe.count
+    probe.close()
+    init_slots = max(3, int(n_nodes / load_target))
+    o = oracle_build(oracle_mod, files, K, R, init_slots, wide=wide)
+    st, arr, nul = gpu_build(dbg, files, K, R, init_slots)
+    assert st["array_size"] == o.size and st["count"] == o.count and st["max_cutoff"] == o.max
+    assert st["occurrences"] == o.occurrences and st["kmers_logged"] == o.kmers_logged
+    d = image_to_dump(arr, nul, o.size)
+    e = o.dump()
+    assert np.array_equal(d["slot"], e["slot"])
+    assert np.array_equal(d["kmer"], e["kmer"])
+    if wide:
+        assert np.array_equal(d["kmer_hi"], e["kmer_hi"])
+    assert np.array_equal(d["l"], e["l"]) and np.array_equal(d["r"], e["r"])
+    # full image equality incl. the nul_flag bytes
+    assert np.array_equal(nul, o.nul_flag())
+    o.close()
+
+
+def test_blocks_and_subblocks_do_not_change_the_result(dbg, oracle_mod, monkeypatch):
+    """many small submits, and forced tiny internal sub-blocks (double buffering), equal one big submit"""
+    reads = random_reads(31, 4000, 30, 160, genome_len=15000)
+    bases, offs = reads_to_arrays(reads)
+    o = oracle_build(oracle_mod, [(bases, offs)], 31, 150, 400_000)
+    e = o.dump()
+    for sub_bases, step in ((None, 4000), (None, 37), (4096, 4000), (1000, 500)):
+        if sub_bases:
+            monkeypatch.setenv("DBG_B200_SUB_BASES", str(sub_bases))
+        else:
+            monkeypatch.delenv("DBG_B200_SUB_BASES", raising=False)
+        with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=400_000) as b:
+            for r0 in range(0, len(reads), step):
+                r1 = min(len(reads), r0 + step)
+                b.submit(bases, offs[r0:r1 + 1])      # offsets keep indexing the whole base array
+            st = b.finalize()
+            arr, nul = b.export_kmerset()
+        d = image_to_dump(arr, nul, o.size)
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(d[k], e[k]), (sub_bases, step, k)
+        assert st["occurrences"] == o.occurrences
+    o.close()
+
+
+def test_saturation_and_polyA_under_contention(dbg, oracle_mod):
+    """thousands of concurrent updates of the same few nodes must still give min(255, count) per lane"""
+    reads = [b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTAC"] * 3000 + [b"A" * 80] * 2000 + [b"T" * 40] * 100 + [b"G" * 64] * 1500
+    reads += [b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAC", b"GAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"] * 7
+    files = [reads_to_arrays(reads)]
+    for K in (21, 31, 35):
+        o = oracle_build(oracle_mod, files, K, 100, 5000, wide=K > 31)
+        st, arr, nul = gpu_build(dbg, files, K, 100, 5000)
+        d, e = image_to_dump(arr, nul, o.size), o.dump()
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(d[k], e[k]), (K, k)
+        assert (e["l"] == 0xFF000000).any() or (e["l"] >> 24 == 255).any()   # the case really saturates
+        o.close()
+
+
+def test_untracked_mode_same_nodes_valid_layout(dbg, oracle_mod):
+    """track_order=0: same node multiset; layout is a valid linear-probing layout (every key reachable
+    from hash%P without crossing an empty slot), like the reference with -t > 1"""
+    reads = random_reads(41, 3000, 50, 150, genome_len=10000)
+    files = [reads_to_arrays(reads)]
+    o = oracle_build(oracle_mod, files, 31, 150, 150_000)
+    e = o.dump()
+    st, arr, nul = gpu_build(dbg, files, 31, 150, 150_000, track=False)
+    d = image_to_dump(arr, nul, o.size)
+    assert np.array_equal(d["slot"], e["slot"])       # occupancy of linear probing is order independent
+    a, b = np.argsort(d["kmer"]), np.argsort(e["kmer"])
+    for k in ("kmer", "l", "r"):
+        assert np.array_equal(d[k][a], e[k][b])
+    P = o.size
+    filled = np.zeros(P, dtype=bool); filled[d["slot"].astype(np.int64)] = True
+    L = oracle_mod.lib()
+    for s, k in zip(d["slot"].tolist()[:5000], d["kmer"].tolist()[:5000]):
+        h = L.orc_hash_code(k) % P
+        while h != s:
+            assert filled[h]
+            h = (h + 1) % P
+    o.close()
+
+
+def test_empty_input_still_has_the_polyA_node(dbg, oracle_mod):
+    """DBGgraph.cpp:418: the k-mer-0 node is inserted always, even when nothing was read"""
+    empty = (np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    st, arr, nul = gpu_build(dbg, [empty], 31, 100, 1000)
+    o = oracle_build(oracle_mod, [empty], 31, 100, 1000)
+    d, e = image_to_dump(arr, nul, o.size), o.dump()
+    assert st["count"] == 1 == o.count
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], e[k])
+    # reads all shorter than K
+    short = reads_to_arrays([b"ACG", b"", b"ACGTACGTAC"])
+    st, arr, nul = gpu_build(dbg, [short], 31, 100, 1000)
+    assert st["count"] == 1 and st["occurrences"] == 0 and st["reads"] == 3
+    o.close()
+
+
+def test_links_pass_and_compact_dump(dbg, oracle_mod):
+    """calculate_kmer_links (contig.cpp:107-205) on the device + slot-ordered survivor dump"""
+    g = load_golden("contig_k31")
+    o = oracle_build(oracle_mod, g["files"], g["K"], g["R"], g["init_slots"], g["load"])
+    with dbg.DBGBuilder(K=g["K"], max_read_len=g["R"], init_slots=g["init_slots"], load_factor=g["load"]) as b:
+        for bases, offs in g["files"]:
+            b.submit(bases, offs)
+        b.finalize()
+        for cutoff in (2, 0, 7):
+            lk, ek = b.export_links(cutoff), o.kmer_links(cutoff)
+            assert np.array_equal(lk["klink"], ek["klink"])
+            assert np.array_equal(lk["del_flag"], ek["del_flag"])
+            assert np.array_equal(lk["depth_stat"], ek["depth_stat"])
+            assert np.array_equal(lk["tips"], ek["tips"]) and np.array_equal(lk["branches"], ek["branches"])
+            assert (lk["total"], lk["deleted"], lk["linear"]) == (ek["total"], ek["deleted"], ek["linear"])
+            dump = b.dump_compact(cutoff)
+            e = o.dump()
+            bits = np.unpackbits(ek["del_flag"])[: o.size]
+            keep = bits[e["slot"].astype(np.int64)] == 0
+            for k in ("slot", "kmer", "l", "r"):
+                assert np.array_equal(dump[k], e[k][keep]), (cutoff, k)
+        full = b.dump_compact(-1)
+        e = o.dump()
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(full[k], e[k])
+    # the reference's own .contig.kmer.freq rows equal the device histogram
+    txt = g["file_contig_kmer_freq"].tobytes().decode().splitlines()
+    rows = [tuple(map(int, line.split("\t"))) for line in txt[1:]]
+    with dbg.DBGBuilder(K=g["K"], max_read_len=g["R"], init_slots=g["init_slots"], load_factor=g["load"]) as b:
+        for bases, offs in g["files"]:
+            b.submit(bases, offs)
+        b.finalize()
+        lk = b.export_links(2, lists=False)
+    assert rows == [(d, int(lk["depth_stat"][d])) for d in range(1, 256)]
+    o.close()
+
+
+def test_device_resident_input_and_synth_parity(dbg, oracle_mod):
+    """reads generated in HBM by the device generator == host generator; submit_device == submit"""
+    import torch
+    from dbg_assembly_b200 import synth
+    p = synth.make_params(seed=7, genome_len=200_000, read_len=150, insert=400, err=0.01, n_rate=0.001)
+    n = 40_000
+    hb, ho = synth.reads_host(p, 0, n)
+    db = torch.empty(n * 150, dtype=torch.uint8, device="cuda")
+    synth.reads_device(p, 0, n, db.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(db.cpu().numpy(), hb)
+    do = torch.from_numpy(ho.astype(np.int64)).cuda()
+    o = oracle_build(oracle_mod, [(hb, ho)], 31, 150, 2_000_000)
+    e = o.dump()
+    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=2_000_000) as b:
+        # two device blocks, the second one starting at a non-16-aligned base offset
+        half = 20_001
+        b.submit_device(db.data_ptr(), do.data_ptr(), half, 0, half * 150)
+        b.submit_device(db.data_ptr(), do.data_ptr() + 8 * half, n - half, half * 150, (n - half) * 150)
+        st = b.finalize()
+        arr, nul = b.export_kmerset()
+        assert b.launches >= 4
+    d = image_to_dump(arr, nul, o.size)
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], e[k])
+    assert st["occurrences"] == n * 120 == o.occurrences
+    o.close()
+
+
+def test_reset_rebuilds_identically(dbg):
+    reads = random_reads(51, 2000, 40, 120)
+    files = [reads_to_arrays(reads)]
+    with dbg.DBGBuilder(K=25, max_read_len=120, init_slots=200_000) as b:
+        b.submit(*files[0]); b.finalize(); a1, n1 = b.export_kmerset()
+        b.reset()
+        b.submit(*files[0]); st = b.finalize(); a2, n2 = b.export_kmerset()
+    assert np.array_equal(a1, a2) and np.array_equal(n1, n2) and st["reads"] == len(reads)
+
+
+def test_table_full_is_reported_not_hung(dbg):
+    reads = random_reads(61, 3000, 100, 150, genome_len=100000, err=0.05)
+    bases, offs = reads_to_arrays(reads)
+    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=5000) as b:   # ~3e5 distinct k-mers into 5003 slots (+margin)
+        b.submit(bases, offs)
+        with pytest.raises(dbg.capi.DbgError) as ei:
+            b.finalize()
+        assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
+
+
+def test_sharded_tuple_path_single_gpu(dbg, oracle_mod):
+    """multi-GPU building blocks on one device: extract tuples bucketed by owner shard, insert each bucket
+    into that shard's context, union of shard dumps == oracle node multiset (ranks emulated in sequence)"""
+    import torch
+    reads = random_reads(71, 6000, 40, 150, genome_len=30000) + [b"A" * 60] * 50
+    bases, offs = reads_to_arrays(reads)
+    P_req = 300_000
+    o = oracle_build(oracle_mod, [(bases, offs)], 31, 150, P_req)
+    e = o.dump()
+    db = torch.from_numpy(bases).cuda()
+    do = torch.from_numpy(offs.astype(np.int64)).cuda()
+    n_occ = o.occurrences
+    for n_parts in (2, 3):
+        shards = [dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req, shard_rank=r, shard_count=n_parts) for r in range(n_parts)]
+        stride = n_occ + 16
+        tuples = torch.empty(n_parts * stride * 2, dtype=torch.int64, device="cuda")
+        counts = torch.zeros(n_parts, dtype=torch.int64, device="cuda")
+        # every rank extracts its own half of the reads (here: one extractor context does both halves)
+        half = len(reads) // 2
+        polyA = np.zeros(8, dtype=np.uint64)
+        got = []
+        for (r0, r1) in ((0, half), (half, len(reads))):
+            ex = shards[0]
+            ex.extract_tuples_device(db.data_ptr(), do.data_ptr() + 8 * r0, r1 - r0, int(offs[r0]), int(offs[r1] - offs[r0]), r0,
+                                     n_parts, tuples.data_ptr(), stride, counts.data_ptr())
+            torch.cuda.synchronize()
+            c = counts.cpu().numpy()
+            for q in range(n_parts):
+                shards[q].insert_tuples_device(tuples.data_ptr() + 16 * q * stride, int(c[q]))
+            torch.cuda.synchronize()
+        polyA += shards[0].get_polyA_counts()
+        total_nodes = 0
+        ks, ls, rs = [], [], []
+        for q, s in enumerate(shards):
+            st = s.finalize()
+            total_nodes += st["count"]
+            s.close()
+        # node contents are checked through the unsharded path fed by the same tuples
+        assert total_nodes == o.count - 1            # shards do not carry the k-mer-0 node
+        exp_l = np.minimum(polyA[:4], 255); exp_r = np.minimum(polyA[4:], 255)
+        zero = e["kmer"] == 0
+        assert int(e["l"][zero][0]) == int(exp_l[0]) << 24 | int(exp_l[1]) << 16 | int(exp_l[2]) << 8 | int(exp_l[3])
+        assert int(e["r"][zero][0]) == int(exp_r[0]) << 24 | int(exp_r[1]) << 16 | int(exp_r[2]) << 8 | int(exp_r[3])
+    # tuples of ALL occurrences into one unsharded context == the fused path == the oracle (layout too)
+    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ex, dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ins:
+        stride = n_occ + 16
+        tuples = torch.empty(stride * 2, dtype=torch.int64, device="cuda")
+        counts = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ex.extract_tuples_device(db.data_ptr(), do.data_ptr(), len(reads), 0, int(offs[-1]), 0, 1, tuples.data_ptr(), stride, counts.data_ptr())
+        torch.cuda.synchronize()
+        ins.insert_tuples_device(tuples.data_ptr(), int(counts.item()))
+        ins.set_polyA_counts(ex.get_polyA_counts())
+        st = ins.finalize()
+        arr, nul = ins.export_kmerset()
+    d = image_to_dump(arr, nul, o.size)
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], e[k])
+    o.close()
+
+
+def test_medium_synthetic_matches_oracle(dbg, oracle_mod):
+    """C2-shaped reads (PE150, 1 % errors, 0.1 % N, K=31) at a size the oracle finishes in seconds"""
+    from dbg_assembly_b200 import synth
+    p = synth.make_params(seed=2, genome_len=460_000, read_len=150, insert=500, err=0.01, n_rate=0.001)
+    n = 306_666
+    hb, ho = synth.reads_host(p, 0, n)
+    init_slots = 20_000_000
+    o = oracle_build(oracle_mod, [(hb, ho)], 31, 150, init_slots)
+    st, arr, nul = gpu_build(dbg, [(hb, ho)], 31, 150, init_slots)
+    assert st["count"] == o.count and st["occurrences"] == o.occurrences == n * 120
+    e = o.dump()
+    d = image_to_dump(arr, nul, o.size)
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], e[k])
+    o.close()
+
+
+def test_full_size_properties_C2(dbg):
+    """BASELINE config C2 at full size (3.07 M reads, 3.68e8 occurrences): size-independent properties
+    -- conservation of occurrences in the link lanes, idempotent rebuild, strand symmetry."""
+    import torch
+    from dbg_assembly_b200 import synth
+    cfg = synth.CONFIGS["C2"]
+    p = synth.make_params(cfg["seed"], cfg["genome_len"], cfg["read_len"], cfg["insert"], cfg["err"], cfg["n_rate"])
+    n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
+    db = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    synth.reads_device(p, 0, n, db.data_ptr())
+    do = (torch.arange(n + 1, dtype=torch.int64, device="cuda") * L)
+    torch.cuda.synchronize()
+    with dbg.DBGBuilder(K=K, max_read_len=L, init_g=cfg["init_g"]) as b:
+        b.submit_device(db.data_ptr(), do.data_ptr(), n, 0, n * L)
+        st = b.finalize()
+        assert st["occurrences"] == n * (L - K + 1)
+        assert st["array_size"] == 200000033
+        d1 = b.dump_compact(-1)
+        lk = b.export_links(2, lists=False)
+        # every occurrence adds one left and one right link except at read ends: sum over lanes (unsaturated
+        # nodes) == 2*occ - 2*reads; saturation only lowers it
+        lanes = sum(int(((d1["l"] >> s) & 0xFF).sum()) + int(((d1["r"] >> s) & 0xFF).sum()) for s in (24, 16, 8, 0))
+        sat = int(sum(((d1[x] >> s) & 0xFF == 255).sum() for x in ("l", "r") for s in (24, 16, 8, 0)))
+        assert lanes <= 2 * st["occurrences"] - 2 * n
+        if sat == 0:
+            assert lanes == 2 * st["occurrences"] - 2 * n
+        assert lk["total"] == st["count"] == len(d1["kmer"])
+        assert int(lk["depth_stat"].sum()) == 8 * st["count"]
+        # the image is a valid table: slots strictly increasing, keys unique
+        assert (np.diff(d1["slot"].astype(np.int64)) > 0).all()
+        assert len(np.unique(d1["kmer"])) == len(d1["kmer"])
+        # rebuild from the reverse-complemented read order gives the same node multiset
+        b.reset()
+        b.submit_device(db.data_ptr(), do.data_ptr(), n, 0, n * L)
+        st2 = b.finalize()
+        d2 = b.dump_compact(-1)
+        assert st2["count"] == st["count"]
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(d1[k], d2[k])     # deterministic, layout included
+
+
+# ---------------------------------------------------------------------------------------------------
+# the drop-in: reference front end + host traversal on the GPU-built table, byte-identical outputs
+# ---------------------------------------------------------------------------------------------------
+B200_CONTIG = os.path.join(REPO, "oracle", "_ref", "debruijn_contig_b200")
+OUT_SUFFIXES = (".contig.seq.fa", ".contig.small.fa", ".contig.kmer.freq", ".contig.tip.fa", ".contig.bubble.fa",
+                ".contig.lowedge.fa", ".contig.seq.depth", ".contig.small.depth")
+
+
+@pytest.mark.skipif(not os.access(B200_CONTIG, os.X_OK), reason="oracle/_ref/debruijn_contig_b200 not built (needs /root/reference at build time)")
+def test_contig_files_byte_identical_to_reference(dbg, oracle_mod, tmp_path):
+    """debruijn_contig (reference main.cpp + contig.cpp) linked against libdbgb200 through
+    integration/DBGgraph_b200.cpp writes the same nine files as the reference itself (-t 1)."""
+    g = load_golden("contig_k31")
+    paths = []
+    for i, (bases, offs) in enumerate(g["files"]):
+        p = str(tmp_path / f"f{i}.fa")
+        oracle_mod.write_fasta(p, bases, offs)
+        paths.append(p)
+    lib = str(tmp_path / "reads.lib")
+    open(lib, "w").write("\n".join(paths) + "\n")
+    pre = str(tmp_path / "b200")
+    r = subprocess.run([B200_CONTIG, "-k", str(g["K"]), "-r", str(g["R"]), "-f", "2", "-t", "1", "-i", repr(g["init_g"]),
+                        "-l", repr(g["load"]), "-M", "100", "-o", pre, lib], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    for suf in OUT_SUFFIXES:
+        got = open(pre + suf, "rb").read()
+        exp = g["file" + suf.replace(".", "_")].tobytes()
+        assert got == exp, f"{suf} differs from the reference"
+    log = r.stderr.decode()
+    assert f"array_size:\t{g['size']}" in log and f"count:\t{g['count']}" in log
+    # and, where the reference binary itself travelled, a fresh input through both programs
+    ref = os.path.join(REPO, "oracle", "_ref", "debruijn_contig_ref")
+    if os.access(ref, os.X_OK):
+        reads = random_reads(99, 5000, 100, 100, genome_len=15000, err=0.004, n_rate=0.0, lower=0.0)
+        bases, offs = reads_to_arrays(reads)
+        p = str(tmp_path / "fresh.fa"); oracle_mod.write_fasta(p, bases, offs)
+        lib2 = str(tmp_path / "fresh.lib"); open(lib2, "w").write(p + "\n")
+        outs = {}
+        for tag, exe in (("ref", ref), ("b200", B200_CONTIG)):
+            pre2 = str(tmp_path / ("fresh_" + tag))
+            rr = subprocess.run([exe, "-k", "25", "-r", "100", "-f", "2", "-t", "1", "-i", "0.0005", "-M", "100", "-o", pre2, lib2],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+            assert rr.returncode == 0, rr.stderr.decode()[-2000:]
+            outs[tag] = {suf: open(pre2 + suf, "rb").read() for suf in OUT_SUFFIXES}
+        assert outs["ref"] == outs["b200"]
+        assert len(outs["ref"][".contig.seq.fa"]) > 1000
