@@ -127,8 +127,16 @@ struct dbg_ctx {
     uint64_t cap_bases, cap_reads, sub_bases, sub_reads;
     cudaEvent_t ev_free[2];
     int cur;
+    u64 *d_offs_stage;
+    uint64_t batch_bases, batch_reads, batch_read_index0;
     u64 *d_chunk_first;
     uint64_t cap_chunks;
+    // radix-partitioned build
+    int part_mode;                 // 0 never, 1 always, 2 auto
+    int part_shift;                // bucket = local slot >> part_shift
+    uint32_t n_buckets;
+    u64 *d_bcounts, *d_boffs, *d_bcursor, *d_tuples;
+    uint64_t cap_tuples, part_blocks;
     // finalize / export
     bool finalized;
     u64 *d_owner;
@@ -186,6 +194,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
+    cudaFree(c->d_offs_stage); cudaFree(c->d_bcounts); cudaFree(c->d_boffs); cudaFree(c->d_bcursor); cudaFree(c->d_tuples);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -242,6 +251,18 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     c->sub_bases = SUB_BASES_DEFAULT; c->sub_reads = SUB_READS_DEFAULT;
     if (const char *e = getenv("DBG_B200_SUB_BASES")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 16) c->sub_bases = v; }
     if (const char *e = getenv("DBG_B200_SUB_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->sub_reads = v; }
+    c->cap_bases = 1ull << 30; c->cap_reads = 16ull << 20;      // one host batch (x2 buffers)
+    if (const char *e = getenv("DBG_B200_BATCH_BASES")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 16) c->cap_bases = v; }
+    if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
+    if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
+    if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->part_mode = 2;
+    if (const char *e = getenv("DBG_B200_PARTITION")) c->part_mode = atoi(e) == 0 ? 0 : (atoi(e) == 1 ? 1 : 2);
+    // one bucket = a table slice of <= 32 MB (2^20 nodes): a few of them fit the 126 MB L2 together with the tuple stream
+    c->part_shift = 20;
+    if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
+    while (((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift) > 4096) c->part_shift++;
+    c->n_buckets = (uint32_t)((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift);
     *out = c;   // from here on the caller can dbg_destroy() after a failure
 
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -250,6 +271,9 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * sizeof(Node)));
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_bcounts, (size_t)c->n_buckets * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_boffs, ((size_t)c->n_buckets + 1) * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_bcursor, (size_t)c->n_buckets * sizeof(u64)));
     return clear_table(c);
 }
 
@@ -270,6 +294,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
     for (auto &e : c->build_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     c->build_ev.clear();
     c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
+    c->batch_reads = 0; c->batch_bases = 0; c->part_blocks = 0;
     c->links_cutoff = INT32_MIN;
     for (int i = 1; i < 8; i++) c->ms[i] = 0;
     return clear_table(c);
@@ -278,8 +303,13 @@ extern "C" int dbg_reset(dbg_ctx *c)
 // ---------------------------------------------------------------------------------------------------
 // build: launch helpers
 // ---------------------------------------------------------------------------------------------------
-static uint32_t stage_words_for(int R) { return (uint32_t)((CB + ((R + 15) / 16) * 16) / 16 + 8); }
-static size_t build_smem(uint32_t stage_words) { return (size_t)(stage_words + MAXR + MAXR + 1) * sizeof(u32); }
+static uint32_t stage_words_for(int R) { return (uint32_t)(((CB + ((R + 15) / 16) * 16) / 16 + 8 + 1) & ~1); }   // even: keeps sink smem 8-B aligned
+static size_t build_smem(uint32_t stage_words, uint32_t n_buckets)
+{
+    size_t words = (size_t)stage_words + MAXR + MAXR + 2;
+    if (n_buckets) words += ((n_buckets + 1) & ~1u) + 2 * (size_t)n_buckets;
+    return words * sizeof(u32);
+}
 
 static int ensure_chunks(dbg_ctx *c, uint64_t n_chunks)
 {
@@ -293,13 +323,78 @@ static int ensure_chunks(dbg_ctx *c, uint64_t n_chunks)
 }
 
 template <bool WIDE, class Sink>
-static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_chunks, cudaStream_t s)
+static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_chunks, cudaStream_t s, uint32_t n_buckets = 0)
 {
-    size_t smem = build_smem(a.stage_words);
+    size_t smem = build_smem(a.stage_words, n_buckets);
     if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_build<WIDE, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_build<WIDE, Sink><<<(unsigned)n_chunks, BLOCK, smem, s>>>(a, sink);
     CU_TRY(cudaGetLastError());
     c->launches++;
+    return DBG_OK;
+}
+
+template <bool WIDE, bool TRACK>
+static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s)
+{
+    uint64_t blocks = (n_upper + (uint64_t)BLOCK * G - 1) / ((uint64_t)BLOCK * G);
+    if (blocks == 0) return DBG_OK;
+    if (blocks > 0x7fffffffull) return set_err(DBG_ERR_INVALID, "too many tuples for one launch");
+    InsertSink<WIDE, TRACK> sk; sk.t = view_of(c);
+    k_insert_tuples<WIDE, TRACK><<<(unsigned)blocks, BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, sk);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return DBG_OK;
+}
+
+static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s)
+{
+    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s);
+    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s);
+}
+
+// radix-partitioned build of one device-resident block (see PartitionSink): count, scan, scatter, insert
+template <bool WIDE>
+static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t occ_upper, cudaStream_t s)
+{
+    CU_TRY(cudaMemsetAsync(c->d_bcounts, 0, c->n_buckets * sizeof(u64), s));
+    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.n_buckets = c->n_buckets;
+    cs.counts = c->d_bcounts; cs.cursor = nullptr; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
+    a.count_stats = 0;
+    int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, c->n_buckets);
+    if (rc) return rc;
+    k_scan_buckets<<<1, 1024, 0, s>>>(c->d_bcounts, c->n_buckets, c->d_boffs, c->d_bcursor);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.n_buckets = c->n_buckets;
+    ss.counts = nullptr; ss.cursor = c->d_bcursor; ss.tuples = c->d_tuples; ss.hist = nullptr; ss.base = nullptr;
+    a.count_stats = 1;
+    rc = launch_build<WIDE>(c, a, ss, n_chunks, s, c->n_buckets);
+    if (rc) return rc;
+    return insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s);
+}
+
+static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
+{
+    if (c->part_mode == 0) return false;
+    if (c->part_mode == 1) return true;
+    // auto: streaming the table slice through L2 once per block (2 x table bytes) plus 2 x 16..32 B of tuple
+    // traffic must beat one random 64-B sector round trip per occurrence at ~1/5 of the streaming rate
+    return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * sizeof(Node);
+}
+
+static int ensure_tuples(dbg_ctx *c, uint64_t need)
+{
+    if (need <= c->cap_tuples) return DBG_OK;
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t tb = c->wide ? 32 : 16;
+    size_t have = c->cap_tuples * tb;
+    if ((need + 1024) * tb > (free_b + have) * 6 / 10) return DBG_ERR_NOMEM;   // caller falls back to the direct path
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_tuples); c->d_tuples = nullptr; c->cap_tuples = 0;
+    cudaError_t e = cudaMalloc(&c->d_tuples, (need + 1024) * tb);
+    if (e != cudaSuccess) { cudaGetLastError(); return DBG_ERR_NOMEM; }
+    c->cap_tuples = need;
     return DBG_OK;
 }
 
@@ -315,6 +410,8 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     if (n_chunks > 0x7fffffffull) return set_err(DBG_ERR_INVALID, "block too large: %llu chunks", (unsigned long long)n_chunks);
     int rc = ensure_chunks(c, n_chunks);
     if (rc) return rc;
+    bool part = n_parts == 0 && want_partition(c, total_bases);
+    if (part && ensure_tuples(c, total_bases) != DBG_OK) part = false;
 
     EvPair ev;
     rc = ev_begin(c, s, &ev);
@@ -327,9 +424,12 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     BuildArgs a;
     a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
     a.chunk_first = c->d_chunk_first; a.read_index0 = read_index0; a.K = c->prm.K; a.R = c->prm.max_read_len;
-    a.stage_words = stage_words_for(c->prm.max_read_len);
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
 
-    if (n_parts > 0) {
+    if (part) {
+        rc = c->wide ? run_partitioned<true>(c, a, n_chunks, total_bases, s) : run_partitioned<false>(c, a, n_chunks, total_bases, s);
+        c->part_blocks++;
+    } else if (n_parts > 0) {
         if (c->wide) {
             BucketSink<true> sk; sk.t = view_of(c); sk.shard_size = (c->P + n_parts - 1) / n_parts; sk.n_parts = n_parts;
             sk.tuples = (u64 *)d_tuples; sk.bucket_stride = bucket_stride; sk.counts = d_counts;
@@ -352,20 +452,39 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     return DBG_OK;
 }
 
-static int ensure_staging(dbg_ctx *c, uint64_t bases, uint64_t reads)
+// ---- host submit: reads are appended to a device-resident batch (double buffered); a batch is built when
+// ---- it is full or when results are requested, so that the partitioned path sees enough occurrences per
+// ---- table slice.  Copies of batch n+1 overlap the kernels of batch n.
+static int ensure_batch(dbg_ctx *c)
 {
-    if (bases <= c->cap_bases && reads <= c->cap_reads && c->d_bases[0]) return DBG_OK;
-    CU_TRY(cudaDeviceSynchronize());
-    uint64_t nb = bases > c->cap_bases ? bases : c->cap_bases;
-    uint64_t nr = reads > c->cap_reads ? reads : c->cap_reads;
+    if (c->d_bases[0]) return DBG_OK;
     for (int i = 0; i < 2; i++) {
-        cudaFree(c->d_bases[i]); cudaFree(c->d_offs[i]);
-        c->d_bases[i] = nullptr; c->d_offs[i] = nullptr;
-        CU_TRY(cudaMalloc(&c->d_bases[i], nb + 64));
-        CU_TRY(cudaMalloc(&c->d_offs[i], (nr + 1) * sizeof(u64)));
-        if (!c->ev_free[i]) CU_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        CU_TRY(cudaMalloc(&c->d_bases[i], c->cap_bases + 64));
+        CU_TRY(cudaMalloc(&c->d_offs[i], (c->cap_reads + 2) * sizeof(u64)));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
-    c->cap_bases = nb; c->cap_reads = nr;
+    CU_TRY(cudaMalloc(&c->d_offs_stage, (c->sub_reads + 2) * sizeof(u64)));
+    return DBG_OK;
+}
+
+__global__ void k_append_offs(const u64 *__restrict__ stage, u64 n, u64 *dst, u64 base)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) dst[i] = stage[i] - stage[0] + base;
+}
+
+static int flush_batch(dbg_ctx *c)
+{
+    if (c->batch_reads == 0) return DBG_OK;
+    int b = c->cur;
+    int rc = build_device(c, c->d_bases[b], c->d_offs[b], c->batch_reads, 0, c->batch_bases, c->batch_read_index0, c->stream,
+                          0, nullptr, 0, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(c->ev_free[b], c->stream));
+    c->cur ^= 1;
+    c->batch_reads = 0; c->batch_bases = 0;
+    // the other buffer may still be read by the previous batch's kernels
+    CU_TRY(cudaEventSynchronize(c->ev_free[c->cur]));
     return DBG_OK;
 }
 
@@ -375,39 +494,48 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
     if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
     if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
     CU_TRY(cudaSetDevice(c->device));
+    int rc = ensure_batch(c);
+    if (rc) return rc;
     const uint64_t SUB_BASES = c->sub_bases, SUB_READS = c->sub_reads;
     uint64_t r0 = 0;
     while (r0 < n_reads) {
         // cut a sub-block: at most SUB_BASES bases / SUB_READS reads (at least one read)
-        uint64_t r1 = r0 + 1;
-        {
-            uint64_t lim = r0 + SUB_READS < n_reads ? r0 + SUB_READS : n_reads;
-            // binary search for the last r1 <= lim with offs[r1]-offs[r0] <= SUB_BASES
-            uint64_t lo = r0 + 1, hi = lim;
-            while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offs[mid] - offs[r0] <= SUB_BASES) lo = mid; else hi = mid - 1; }
-            r1 = lo;
-        }
-        uint64_t nb = offs[r1] - offs[r0], nr = r1 - r0;
+        uint64_t lim = r0 + SUB_READS < n_reads ? r0 + SUB_READS : n_reads;
+        uint64_t lo = r0 + 1, hi = lim;
+        while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offs[mid] - offs[r0] <= SUB_BASES) lo = mid; else hi = mid - 1; }
+        uint64_t r1 = lo;
         if (offs[r1] < offs[r0]) return set_err(DBG_ERR_INVALID, "offsets must be non-decreasing");
-        int rc = ensure_staging(c, (nb > SUB_BASES ? nb : SUB_BASES) + 16, nr > SUB_READS ? nr : SUB_READS);
-        if (rc) return rc;
-        int b = c->cur; c->cur ^= 1;
-        // wait until the kernels that last read buffer b are done, then copy on the copy stream
-        CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
-        uint64_t pad = offs[r0] & 15;
+        uint64_t nb = offs[r1] - offs[r0], nr = r1 - r0;
+        uint64_t copy_nb = nb;
+        if (nb > c->cap_bases) {
+            // a single sequence longer than a whole batch: only its first max_read_len bases are ever used
+            // (DBGgraph.cpp:63); the logged untrimmed k-mer count is the only thing that changes
+            copy_nb = (uint64_t)c->prm.max_read_len < nb ? (uint64_t)c->prm.max_read_len : nb;
+        }
+        if (c->batch_bases + copy_nb > c->cap_bases || c->batch_reads + nr > c->cap_reads) {
+            rc = flush_batch(c);
+            if (rc) return rc;
+        }
+        int b = c->cur;
+        if (c->batch_reads == 0) c->batch_read_index0 = c->next_read_index;
         EvPair ev;
         rc = ev_begin(c, c->copy_stream, &ev);
         if (rc) return rc;
-        if (nb) CU_TRY(cudaMemcpyAsync(c->d_bases[b] + pad, bases + offs[r0], nb, cudaMemcpyHostToDevice, c->copy_stream));
-        CU_TRY(cudaMemcpyAsync(c->d_offs[b], offs + r0, (nr + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->copy_stream));
+        if (copy_nb) CU_TRY(cudaMemcpyAsync(c->d_bases[b] + c->batch_bases, bases + offs[r0], copy_nb, cudaMemcpyHostToDevice, c->copy_stream));
+        if (copy_nb == nb) {
+            CU_TRY(cudaMemcpyAsync(c->d_offs_stage, offs + r0, (nr + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            uint64_t two[2] = {0, copy_nb};
+            CU_TRY(cudaMemcpyAsync(c->d_offs_stage, two, sizeof(two), cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        k_append_offs<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, c->copy_stream>>>(c->d_offs_stage, nr, c->d_offs[b] + c->batch_reads, c->batch_bases);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
         CU_TRY(cudaEventRecord(ev.b, c->copy_stream));
         CU_TRY(cudaEventSynchronize(ev.b));          // host buffer is reusable from here on
         float t = 0; CU_TRY(cudaEventElapsedTime(&t, ev.a, ev.b)); c->ms[4] += t;
         cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
-        const char *virt = c->d_bases[b] + pad - offs[r0];
-        rc = build_device(c, virt, c->d_offs[b], nr, offs[r0], nb, c->next_read_index, c->stream, 0, nullptr, 0, nullptr);
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(c->ev_free[b], c->stream));
+        c->batch_bases += copy_nb; c->batch_reads += nr;
         c->next_read_index += nr; c->reads_total += nr;
         r0 = r1;
     }
@@ -421,9 +549,11 @@ extern "C" int dbg_submit_reads_device(dbg_ctx *c, const char *d_bases, const ui
     if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
     if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
     CU_TRY(cudaSetDevice(c->device));
+    int rc = flush_batch(c);      // keep blocks in call order
+    if (rc) return rc;
     uint64_t idx0 = first_read_index == UINT64_MAX ? c->next_read_index : first_read_index;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    int rc = build_device(c, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, idx0, s, 0, nullptr, 0, nullptr);
+    rc = build_device(c, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, idx0, s, 0, nullptr, 0, nullptr);
     if (rc) return rc;
     c->next_read_index = idx0 + n_reads; c->reads_total += n_reads;
     return DBG_OK;
@@ -456,17 +586,8 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     EvPair ev;
     int rc = ev_begin(c, s, &ev);
     if (rc) return rc;
-    uint64_t blocks = (n + (uint64_t)BLOCK * G - 1) / ((uint64_t)BLOCK * G);
-    unsigned grid = (unsigned)(blocks < 148ull * 32 ? blocks : 148ull * 32);
-    if (c->wide) {
-        if (c->track) { InsertSink<true, true> sk; sk.t = view_of(c); k_insert_tuples<true, true><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
-        else { InsertSink<true, false> sk; sk.t = view_of(c); k_insert_tuples<true, false><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
-    } else {
-        if (c->track) { InsertSink<false, true> sk; sk.t = view_of(c); k_insert_tuples<false, true><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
-        else { InsertSink<false, false> sk; sk.t = view_of(c); k_insert_tuples<false, false><<<grid, BLOCK, 0, s>>>((const u64 *)d_tuples, n, sk); }
-    }
-    CU_TRY(cudaGetLastError());
-    c->launches++;
+    rc = insert_any(c, d_tuples, n, nullptr, s);
+    if (rc) return rc;
     CU_TRY(cudaEventRecord(ev.b, s));
     c->build_ev.push_back(ev);
     return DBG_OK;
@@ -476,6 +597,8 @@ extern "C" int dbg_get_polyA_counts(dbg_ctx *c, uint64_t counts[8])
 {
     if (!c || !counts) return set_err(DBG_ERR_INVALID, "NULL argument");
     CU_TRY(cudaSetDevice(c->device));
+    int frc = flush_batch(c);
+    if (frc) return frc;
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(counts, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
     return DBG_OK;
@@ -508,6 +631,8 @@ static int fill_stats(dbg_ctx *c, const u64 *cnt)
 
 static int read_counters(dbg_ctx *c, u64 *cnt)
 {
+    int frc = flush_batch(c);
+    if (frc) return frc;
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost));
     if (cnt[CNT_ERROR] == 1) return set_err(DBG_ERR_TABLE_FULL, "probe ran off the shard (%llu slots + margin): table too full", (unsigned long long)(c->shard_hi - c->shard_lo));

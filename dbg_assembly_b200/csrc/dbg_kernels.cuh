@@ -41,6 +41,7 @@ struct BuildArgs {
     u64 read_index0;          // global index of read 0 (ordinals)
     int K, R;
     u32 stage_words;          // packed words staged per chunk (incl. slack)
+    int count_stats;          // add this launch's reads/occurrences to the context counters
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -66,7 +67,7 @@ struct InsertSink {
     TableView t;
     u32 n_new, n_conf;     // per-thread, reduced at kernel end
 
-    __device__ __forceinline__ void init() { n_new = 0; n_conf = 0; }
+    __device__ __forceinline__ void init(u32 *) { n_new = 0; n_conf = 0; }
 
     __device__ __forceinline__ void polyA(const Occ &o)
     {
@@ -159,7 +160,7 @@ struct BucketSink {
     u64 bucket_stride;
     u64 *counts;            // n_parts
 
-    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void init(u32 *) {}
     __device__ __forceinline__ void finish() {}
 
     __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
@@ -207,6 +208,109 @@ struct BucketSink {
     }
 };
 
+// Radix partition by home-slot range (bucket = home >> shift), exact two-pass (count, scan, scatter): the
+// insert pass then walks the tuples bucket by bucket, so every bucket's slice of the table (<= ~32 MB)
+// is pulled into the 126 MB L2 once, updated there and written back once, instead of one random DRAM
+// read-modify-write per occurrence.  MODE 0 = count, MODE 1 = scatter.
+template <bool WIDE, int MODE>
+struct PartitionSink {
+    TableView t;
+    int shift;
+    u32 n_buckets;
+    u64 *counts;       // MODE 0: per-bucket totals (global)
+    u64 *cursor;       // MODE 1: per-bucket running write position (starts at the exclusive scan)
+    u64 *tuples;
+    u32 *hist;         // shared: n_buckets
+    u64 *base;         // shared: n_buckets (MODE 1)
+
+    __device__ __forceinline__ void init(u32 *extra)
+    {
+        hist = extra;
+        base = reinterpret_cast<u64 *>(extra + ((n_buckets + 1) & ~1u));
+        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) hist[b] = 0;
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
+    {
+        u32 bkt[G], rank[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            bkt[g] = 0xffffffffu;
+            if (g < nv) {
+                if ((o[g].klo | o[g].khi) == 0) {
+                    if (MODE == 1) {   // the k-mer-0 side node is accumulated once, in the scatter pass
+                        if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
+                        if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                    }
+                } else {
+                    u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                    bkt[g] = (u32)((mod_P(h, t.P, t.M) - t.lo) >> shift);
+                    rank[g] = atomicAdd(&hist[bkt[g]], 1u);
+                }
+            }
+        }
+        if (MODE == 0) return;
+        __syncthreads();
+        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
+            u32 c = hist[b];
+            if (c) { base[b] = atomicAdd(cursor + b, (u64)c); hist[b] = 0; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (bkt[g] != 0xffffffffu) {
+                u64 pos = base[bkt[g]] + rank[g];
+                u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+                if (WIDE) {
+                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
+                    dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
+                    dst[1] = make_ulonglong2(meta, 0ULL);
+                } else {
+                    reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(o[g].klo, meta);
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void finish()
+    {
+        if (MODE == 0) {
+            __syncthreads();
+            for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
+                u32 c = hist[b];
+                if (c) atomicAdd(counts + b, (u64)c);
+            }
+        }
+    }
+};
+
+// exclusive scan of the bucket counts (one CTA); offs[n] = total; cursor = copy of offs for the scatter pass
+__global__ void __launch_bounds__(1024) k_scan_buckets(const u64 *__restrict__ counts, u32 n, u64 *offs, u64 *cursor)
+{
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (u32 b0 = 0; b0 < n; b0 += 1024) {
+        u32 b = b0 + tid;
+        u64 v = b < n ? counts[b] : 0, inc = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { u64 x = __shfl_up_sync(0xffffffffu, inc, s); if ((tid & 31) >= s) inc += x; }
+        if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+        __syncthreads();
+        u64 wb = 0;
+        for (int w = 0; w < (tid >> 5); w++) wb += wsum[w];
+        u64 ex = carry + wb + inc - v;
+        if (b < n) { offs[b] = ex; cursor[b] = ex; }
+        __syncthreads();
+        if (tid == 1023) carry += wb + inc;
+        __syncthreads();
+    }
+    if (tid == 0) offs[n] = carry;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the fused build kernel: one CTA per chunk of CB bases
 // ---------------------------------------------------------------------------------------------------
@@ -217,6 +321,7 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
     u32 *pk = smem;                          // a.stage_words
     u32 *rstart = pk + a.stage_words;        // MAXR
     u32 *rpre = rstart + MAXR;               // MAXR + 1
+    u32 *extra = rpre + MAXR + 2;            // sink-private shared memory (8-byte aligned)
     __shared__ u32 warp_tot[BLOCK / 32];
 
     const int tid = threadIdx.x;
@@ -224,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
     const u64 cbase = a.abase + chunk * CB;
     const int K = a.K;
 
-    sink.init();
+    sink.init(extra);
 
     // ---- (1) coalesced 16-B loads of ASCII bases, 2-bit pack, stage in shared memory -------------------
     {
@@ -338,20 +443,26 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
     }
 
     sink.finish();
-    // Kmer_total_num / occurrence counters
+    // Kmer_total_num / occurrence counters (skipped by the counting pass of the partitioned build)
+    if (a.count_stats) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) logged += __shfl_xor_sync(0xffffffffu, logged, s);
-    if ((tid & 31) == 0 && logged) atomicAdd(sink.t.counters + CNT_LOGGED, logged);
-    if (tid == 0 && n_occ) atomicAdd(sink.t.counters + CNT_OCC, n_occ);
+        for (int s = 16; s > 0; s >>= 1) logged += __shfl_xor_sync(0xffffffffu, logged, s);
+        if ((tid & 31) == 0 && logged) atomicAdd(sink.t.counters + CNT_LOGGED, logged);
+        if (tid == 0 && n_occ) atomicAdd(sink.t.counters + CNT_OCC, n_occ);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // owner side of the exchange: insert received tuples
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, InsertSink<WIDE, TRACK> sink)
+__global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
+                                                         InsertSink<WIDE, TRACK> sink)
 {
-    sink.init();
+    if (n_ptr) n = *n_ptr;      // exact count produced on the device (partitioned build): no host round trip
+    sink.init(nullptr);
+    // CTA i takes tuples [i*BLOCK*G, ...): CTAs are scheduled in index order, so the resident CTAs always work
+    // on a narrow window of the (bucket-ordered) tuple array -> the table slice they touch stays in L2
     const u64 stride = (u64)gridDim.x * BLOCK * G;
     for (u64 base0 = (u64)blockIdx.x * BLOCK * G; base0 < n; base0 += stride) {   // block-uniform trip count
         const u64 base = base0 + (u64)threadIdx.x * G;
@@ -361,11 +472,11 @@ __global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__
             if (base + g < n) {
                 u64 klo, khi = 0, meta;
                 if (WIDE) {
-                    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g));
-                    ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g) + 1);
+                    ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g));   // read once: evict first
+                    ulonglong2 y = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g) + 1);
                     klo = x.x; khi = x.y; meta = y.x;
                 } else {
-                    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(tuples) + base + g);
+                    ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + base + g);
                     klo = x.x; meta = x.y;
                 }
                 occ[g].klo = klo; occ[g].khi = khi; occ[g].lb = (u32)(meta & 15); occ[g].rb = (u32)((meta >> 4) & 15);

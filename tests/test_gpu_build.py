@@ -22,6 +22,21 @@ def dbg():
     return m
 
 
+@pytest.fixture(params=["direct", "partitioned"], autouse=True)
+def build_path(request, monkeypatch):
+    """every test runs through both build paths: the fused direct-insert kernel, and the radix-partitioned
+    path (count / scan / scatter / insert) forced on with tiny buckets and tiny host batches so that many
+    buckets, many batches and the double-buffered batch hand-off are exercised even at test sizes"""
+    if request.param == "direct":
+        monkeypatch.setenv("DBG_B200_PARTITION", "0")
+    else:
+        monkeypatch.setenv("DBG_B200_PARTITION", "1")
+        monkeypatch.setenv("DBG_B200_PART_SHIFT", "8")
+        monkeypatch.setenv("DBG_B200_BATCH_BASES", "150000")
+        monkeypatch.setenv("DBG_B200_BATCH_READS", "3000")
+    return request.param
+
+
 def gpu_build(dbg, files, K, R, init_slots, load=0.7, track=True, force_wide=False):
     with dbg.DBGBuilder(K=K, max_read_len=R, init_slots=init_slots, load_factor=load, track_order=track,
                         force_wide=force_wide) as b:
@@ -362,10 +377,15 @@ def test_medium_synthetic_matches_oracle(dbg, oracle_mod):
     o.close()
 
 
-def test_full_size_properties_C2(dbg):
+def test_full_size_properties_C2(dbg, build_path, monkeypatch):
     """BASELINE config C2 at full size (3.07 M reads, 3.68e8 occurrences): size-independent properties
-    -- conservation of occurrences in the link lanes, idempotent rebuild, strand symmetry."""
+    -- conservation of occurrences in the link lanes, idempotent rebuild, and the direct and the
+    partitioned build paths agreeing bit for bit (layout included)."""
     import torch
+    if build_path != "direct":
+        pytest.skip("runs once; compares both paths itself")
+    for k in ("DBG_B200_PARTITION", "DBG_B200_PART_SHIFT", "DBG_B200_BATCH_BASES", "DBG_B200_BATCH_READS"):
+        monkeypatch.delenv(k, raising=False)      # library defaults: auto path selection (partitioned at this size)
     from dbg_assembly_b200 import synth
     cfg = synth.CONFIGS["C2"]
     p = synth.make_params(cfg["seed"], cfg["genome_len"], cfg["read_len"], cfg["insert"], cfg["err"], cfg["n_rate"])
@@ -393,14 +413,23 @@ def test_full_size_properties_C2(dbg):
         # the image is a valid table: slots strictly increasing, keys unique
         assert (np.diff(d1["slot"].astype(np.int64)) > 0).all()
         assert len(np.unique(d1["kmer"])) == len(d1["kmer"])
-        # rebuild from the reverse-complemented read order gives the same node multiset
+        # rebuild gives the same image (deterministic, layout included)
         b.reset()
         b.submit_device(db.data_ptr(), do.data_ptr(), n, 0, n * L)
         st2 = b.finalize()
         d2 = b.dump_compact(-1)
         assert st2["count"] == st["count"]
         for k in ("slot", "kmer", "l", "r"):
-            assert np.array_equal(d1[k], d2[k])     # deterministic, layout included
+            assert np.array_equal(d1[k], d2[k])
+    # the direct (fused random-access) path produces the identical image
+    monkeypatch.setenv("DBG_B200_PARTITION", "0")
+    with dbg.DBGBuilder(K=K, max_read_len=L, init_g=cfg["init_g"]) as b:
+        b.submit_device(db.data_ptr(), do.data_ptr(), n, 0, n * L)
+        st3 = b.finalize()
+        d3 = b.dump_compact(-1)
+    assert st3["count"] == st["count"] and st3["occurrences"] == st["occurrences"]
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d1[k], d3[k])
 
 
 # ---------------------------------------------------------------------------------------------------
