@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdbgb200.so")
+LIB_PATH = os.environ.get("DBG_B200_LIB") or os.path.join(PKG, "libdbgb200.so")   # env override: tuning experiments only
 
 DBG_OK = 0
 DBG_ERR_INVALID, DBG_ERR_CUDA, DBG_ERR_NOMEM, DBG_ERR_TABLE_FULL, DBG_ERR_STATE, DBG_ERR_BUFFER = -1, -2, -3, -4, -5, -6

@@ -258,8 +258,9 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
     c->part_mode = 2;
     if (const char *e = getenv("DBG_B200_PARTITION")) c->part_mode = atoi(e) == 0 ? 0 : (atoi(e) == 1 ? 1 : 2);
-    // one bucket = a table slice of <= 32 MB (2^20 nodes): a few of them fit the 126 MB L2 together with the tuple stream
-    c->part_shift = 20;
+    // one bucket = a table slice of 16 MB (2^18 nodes of 64 B): the slice in use, the one being prefetched and the
+    // tuple stream fit the 126 MB L2 with room to spare
+    c->part_shift = 18;
     if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
     while (((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift) > 4096) c->part_shift++;
     c->n_buckets = (uint32_t)((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift);
@@ -307,7 +308,7 @@ static uint32_t stage_words_for(int R) { return (uint32_t)(((CB + ((R + 15) / 16
 static size_t build_smem(uint32_t stage_words, uint32_t n_buckets)
 {
     size_t words = (size_t)stage_words + MAXR + MAXR + 2;
-    if (n_buckets) words += ((n_buckets + 1) & ~1u) + 2 * (size_t)n_buckets;
+    if (n_buckets) words += 2 * (size_t)((n_buckets + 1) & ~1u) + 4 * (size_t)n_buckets;   // ping-pong hist (u32) + base (u64)
     return words * sizeof(u32);
 }
 
@@ -334,22 +335,23 @@ static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_ch
 }
 
 template <bool WIDE, bool TRACK>
-static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s)
+static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed)
 {
     uint64_t blocks = (n_upper + (uint64_t)BLOCK * G - 1) / ((uint64_t)BLOCK * G);
     if (blocks == 0) return DBG_OK;
     if (blocks > 0x7fffffffull) return set_err(DBG_ERR_INVALID, "too many tuples for one launch");
     InsertSink<WIDE, TRACK> sk; sk.t = view_of(c);
-    k_insert_tuples<WIDE, TRACK><<<(unsigned)blocks, BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, sk);
+    k_insert_tuples<WIDE, TRACK><<<(unsigned)blocks, BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, sk,
+                                                                    bucketed ? c->d_boffs : nullptr, c->n_buckets, c->part_shift);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return DBG_OK;
 }
 
-static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s)
+static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed = false)
 {
-    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s);
-    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s);
+    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s, bucketed) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s, bucketed);
+    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed);
 }
 
 // radix-partitioned build of one device-resident block (see PartitionSink): count, scan, scatter, insert
@@ -370,7 +372,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     a.count_stats = 1;
     rc = launch_build<WIDE>(c, a, ss, n_chunks, s, c->n_buckets);
     if (rc) return rc;
-    return insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s);
+    return insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s, true);
 }
 
 static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
@@ -864,15 +866,15 @@ extern "C" uint64_t dbg_launch_count(const dbg_ctx *c) { return c ? c->launches 
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dbg_measure_random_rmw(int32_t device, uint64_t bytes, uint64_t n_ops, int32_t mode, float *ms)
 {
-    if (!ms || bytes < sizeof(Node)) return set_err(DBG_ERR_INVALID, "bad argument");
+    if (!ms || bytes < sizeof(Rec32)) return set_err(DBG_ERR_INVALID, "bad argument");
     if (dbg_device_count() == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible");
     CU_TRY(cudaSetDevice(device));
-    Node *tab = nullptr;
+    Rec32 *tab = nullptr;
     CU_TRY(cudaMalloc(&tab, bytes));
     cudaError_t e1 = cudaMemset(tab, 0, bytes);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    uint64_t n_nodes = bytes / sizeof(Node);
+    uint64_t n_nodes = bytes / sizeof(Rec32);
     unsigned grid = 148 * 32;
     float best = 1e30f;
     for (int it = 0; it < 4 && e1 == cudaSuccess; it++) {   // first iteration is warm-up

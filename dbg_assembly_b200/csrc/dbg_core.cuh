@@ -14,19 +14,23 @@ namespace dbg {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-// ---- device table node: exactly one 32-B DRAM sector ------------------------------------------------
-// klo/khi: canonical k-mer (khi == 0 on the 64-bit path); (0,0) = empty, like the reference, whose
-//          all-A k-mer is kept in a side node (DBGgraph.cpp:153-164).
-// links  : l_link (low 32) | r_link << 32, the reference's 2 x 4 x 8-bit saturating lanes.
-// nord   : ~ordinal of the earliest occurrence seen so far (0 = none yet); ordinal = read_index<<16 | j.
-//          Only used to reproduce the reference's slot layout at export.
-struct __align__(32) Node {
+// ---- device table node: 64 B = two 32-B sectors of one DRAM burst ------------------------------------
+// sector 0  klo/khi: canonical k-mer (khi == 0 on the 64-bit path); (0,0) = empty, like the reference, whose
+//                    all-A k-mer is kept in a side node (DBGgraph.cpp:153-164).
+//           nord   : ~ordinal of the earliest occurrence seen so far (0 = none yet); ordinal =
+//                    read_index<<16 | j.  Only used to reproduce the reference's slot layout.
+// sector 1  cnt[8] : occurrence counts per neighbour base, l lanes A,C,G,T then r lanes A,C,G,T, as plain
+//                    u32 so that an update is a fire-and-forget `red.add` (no CAS loop, no return trip).
+//                    The reference's 8-bit saturating lanes (kmerSet.cpp:56,341) are min(255, cnt) at
+//                    export; updates stop once a loaded count is >= 255, so a u32 cannot wrap.
+struct __align__(64) Node {
     u64 klo;
     u64 khi;
-    u64 links;
     u64 nord;
+    u64 pad;
+    u32 cnt[8];
 };
-static_assert(sizeof(Node) == 32, "node must be one sector");
+static_assert(sizeof(Node) == 64, "node must be two sectors");
 
 struct TableView {
     Node *nodes;      // n_local slots (shard range + overflow margin)
@@ -142,12 +146,40 @@ __device__ __forceinline__ U128 revcomp128(U128 v, int K)
 }
 
 // ---- memory helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ void load_node(const Node *p, u64 &klo, u64 &khi, u64 &links, u64 &nord)
+// one 256-bit load (LDG.E.256 on sm_100): a whole 32-B sector in ONE L2 request
+__device__ __forceinline__ void ld256_cg(const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
 {
-    // one 32-B sector; .cg: the table is only ever coherent at L2 (atomics live there)
-    ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
-    ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2 *>(p) + 1);
-    klo = a.x; khi = a.y; links = b.x; nord = b.y;
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256_cs(const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
+{
+    asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+struct NodeRegs {
+    u64 klo, khi, nord;
+    u32 cl, cr;        // the two counters this occurrence would bump (0 if it has no such neighbour)
+};
+
+// key sector (one request) + only the two counter lanes of interest (keeps the register footprint small).
+// .cg: the table is only ever coherent at L2 (atomics live there)
+__device__ __forceinline__ void load_node(const Node *p, u32 lb, u32 rb, NodeRegs &n)
+{
+    u64 pad;
+    ld256_cg(p, n.klo, n.khi, n.nord, pad);
+    n.cl = lb < 4 ? __ldcg(&p->cnt[lb]) : 0u;
+    n.cr = rb < 4 ? __ldcg(&p->cnt[4 + rb]) : 0u;
+}
+
+__device__ __forceinline__ u32 pick4(const uint4 &v, u32 i)
+{
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// the reference's link word from four u32 counts: lane of base b = bits (3-b)*8.., saturating at 255
+__device__ __forceinline__ u32 pack_link(const uint4 &c)
+{
+    return (min(c.x, 255u) << 24) | (min(c.y, 255u) << 16) | (min(c.z, 255u) << 8) | min(c.w, 255u);
 }
 
 __device__ __forceinline__ bool cas128(void *addr, u64 new_lo, u64 new_hi, u64 &old_lo, u64 &old_hi)

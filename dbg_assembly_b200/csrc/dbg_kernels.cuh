@@ -22,6 +22,10 @@ constexpr int CB = 16384;      // bases per chunk (one CTA)
 constexpr int BLOCK = 256;     // threads per CTA
 constexpr int MAXR = 1024;     // reads per shared-memory table pass
 constexpr int G = 4;           // consecutive occurrences per thread run (rolling k-mer + 4 probes in flight)
+#ifndef DBG_MIN_CTAS
+#define DBG_MIN_CTAS 3
+#endif
+constexpr int MIN_CTAS = DBG_MIN_CTAS;    // register budget of the insert kernels: CTAs (x8 warps) per SM
 constexpr u64 EMPTY_PRI = ~0ULL;
 constexpr u64 POLYA_PRI = ~0ULL - 1;
 
@@ -64,6 +68,7 @@ __global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, u64 aba
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, bool TRACK>
 struct InsertSink {
+    static constexpr int RUN = G;
     TableView t;
     u32 n_new, n_conf;     // per-thread, reduced at kernel end
 
@@ -77,64 +82,62 @@ struct InsertSink {
         if (o.rb < 4 && __ldcg(t.polyA + 4 + o.rb) < 255) atomicAdd(t.polyA + 4 + o.rb, 1ULL);
     }
 
-    // thread_updatekmers for one occurrence (DBGgraph.cpp:167-205), lock-free
-    __device__ __forceinline__ void resolve(const Occ &o, Node *p, u64 idx, u64 klo, u64 khi, u64 links, u64 nord)
-    {
-        for (;;) {
-            bool mine = false;
-            if ((klo | khi) == 0) {
-                if (WIDE) {
-                    u64 olo, ohi;
-                    if (cas128(p, o.klo, o.khi, olo, ohi)) { mine = true; n_new++; }
-                    else { klo = olo; khi = ohi; }
-                } else {
-                    u64 old = atomicCAS(&p->klo, 0ULL, o.klo);
-                    if (old == 0) { mine = true; n_new++; }
-                    else klo = old;
-                }
-            }
-            if (mine || (klo == o.klo && (!WIDE || khi == o.khi))) {
-                // saturating lane update: CAS loop on the packed {l_link, r_link} word
-                u64 cur = links;
-                for (;;) {
-                    u32 l = lane_inc((u32)cur, o.lb), r = lane_inc((u32)(cur >> 32), o.rb);
-                    u64 nv = (u64)l | ((u64)r << 32);
-                    if (nv == cur) break;
-                    u64 old = atomicCAS(&p->links, cur, nv);
-                    if (old == cur) break;
-                    cur = old;
-                }
-                if (TRACK) {
-                    u64 mn = ~o.ord;
-                    if (mn > nord) atomicMax(&p->nord, mn);
-                }
-                return;
-            }
-            n_conf++;
-            idx++; p++;
-            if (idx >= t.n_local) { atomicExch(t.counters + CNT_ERROR, 1ULL); return; }
-            load_node(p, klo, khi, links, nord);
-        }
-    }
-
+    // thread_updatekmers (DBGgraph.cpp:167-205) for G occurrences at once, lock-free.  The G probe sequences
+    // advance in lock step: every round issues all pending claims (CAS), then all pending next-slot loads, so
+    // a round costs two memory round trips no matter how many of the G are still probing.  Only a NEW key
+    // needs an atomic with a return value (the claim); counting is fire-and-forget (RED).
     __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
     {
-        Node *p[G]; u64 idx[G]; u64 klo[G], khi[G], links[G], nord[G];
+        Node *p[G]; NodeRegs n[G]; bool act[G];
+        Node *const p_end = t.nodes + t.n_local;
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            if (g < nv && (o[g].klo | o[g].khi) != 0) {
+            act[g] = g < nv && (o[g].klo | o[g].khi) != 0;
+            if (act[g]) {
                 u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                idx[g] = mod_P(h, t.P, t.M) - t.lo;
-                p[g] = t.nodes + idx[g];
-                load_node(p[g], klo[g], khi[g], links[g], nord[g]);
+                p[g] = t.nodes + (mod_P(h, t.P, t.M) - t.lo);
+                load_node(p[g], o[g].lb, o[g].rb, n[g]);
+            } else if (g < nv) {
+                polyA(o[g]);
             }
         }
+        for (;;) {
+            // (1) claims for the occurrences looking at an empty slot
+            u64 olo[G], ohi[G]; bool tried[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            if (g < nv) {
-                if ((o[g].klo | o[g].khi) == 0) polyA(o[g]);
-                else resolve(o[g], p[g], idx[g], klo[g], khi[g], links[g], nord[g]);
+            for (int g = 0; g < G; g++) {
+                tried[g] = act[g] && (n[g].klo | (WIDE ? n[g].khi : 0ULL)) == 0;
+                if (tried[g]) {
+                    if (WIDE) cas128(p[g], o[g].klo, o[g].khi, olo[g], ohi[g]);
+                    else olo[g] = atomicCAS(&p[g]->klo, 0ULL, o[g].klo);
+                }
             }
+            bool more = false;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (!act[g]) continue;
+                if (tried[g]) {
+                    if ((olo[g] | (WIDE ? ohi[g] : 0ULL)) == 0) { n_new++; n[g].klo = o[g].klo; if (WIDE) n[g].khi = o[g].khi; }
+                    else { n[g].klo = olo[g]; if (WIDE) n[g].khi = ohi[g]; }   // somebody else got the slot
+                }
+                if (n[g].klo == o[g].klo && (!WIDE || n[g].khi == o[g].khi)) {
+                    // a stale (too small) loaded count only costs a redundant add; export clamps to 255
+                    if (o[g].lb < 4 && n[g].cl < 255u) atomicAdd(&p[g]->cnt[o[g].lb], 1u);
+                    if (o[g].rb < 4 && n[g].cr < 255u) atomicAdd(&p[g]->cnt[4 + o[g].rb], 1u);
+                    if (TRACK) {
+                        u64 mn = ~o[g].ord;
+                        if (mn > n[g].nord) atomicMax(&p[g]->nord, mn);
+                    }
+                    act[g] = false;
+                } else {
+                    // (2) occupied by another key: next slot (linear probing, DBGgraph.cpp:201-204)
+                    n_conf++;
+                    p[g]++;
+                    if (p[g] >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); act[g] = false; }
+                    else { load_node(p[g], o[g].lb, o[g].rb, n[g]); more = true; }
+                }
+            }
+            if (!more) break;
         }
     }
 
@@ -153,6 +156,7 @@ struct InsertSink {
 // tuples for the exchange: 16 B (narrow) {kmer, ord<<8 | rb<<4 | lb}, 32 B (wide) {lo, hi, meta, 0}
 template <bool WIDE>
 struct BucketSink {
+    static constexpr int RUN = G;
     TableView t;            // P, M, polyA, counters (nodes unused)
     u64 shard_size;         // ceil(P / n_parts)
     int n_parts;
@@ -214,29 +218,58 @@ struct BucketSink {
 // read-modify-write per occurrence.  MODE 0 = count, MODE 1 = scatter.
 template <bool WIDE, int MODE>
 struct PartitionSink {
+    static constexpr int RUN = G;
     TableView t;
     int shift;
     u32 n_buckets;
     u64 *counts;       // MODE 0: per-bucket totals (global)
     u64 *cursor;       // MODE 1: per-bucket running write position (starts at the exclusive scan)
     u64 *tuples;
-    u32 *hist;         // shared: n_buckets
-    u64 *base;         // shared: n_buckets (MODE 1)
+    u32 *hist;         // shared: 2 x n_buckets (ping-pong)
+    u64 *base;         // shared: 2 x n_buckets (MODE 1)
+    // MODE 1 is software pipelined: round k's tuples are written during round k+1, after the barrier that
+    // publishes their reserved positions, so the reservation atomics' round trip hides behind extraction
+    u64 pklo[RUN], pkhi[WIDE ? RUN : 1], pmeta[RUN];
+    u32 pbkt[RUN], prank[RUN];
+    u32 parity;
+    bool has_prev;
+
+    __device__ __forceinline__ u32 nb2() const { return (n_buckets + 1) & ~1u; }
 
     __device__ __forceinline__ void init(u32 *extra)
     {
         hist = extra;
-        base = reinterpret_cast<u64 *>(extra + ((n_buckets + 1) & ~1u));
-        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) hist[b] = 0;
+        base = reinterpret_cast<u64 *>(extra + 2 * nb2());
+        for (u32 b = threadIdx.x; b < 2 * nb2(); b += BLOCK) hist[b] = 0;
+        parity = 0; has_prev = false;
         __syncthreads();
     }
 
-    __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
+    __device__ __forceinline__ void write_prev()
     {
-        u32 bkt[G], rank[G];
+        const u64 *bs = base + (size_t)(parity ^ 1) * n_buckets;
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            bkt[g] = 0xffffffffu;
+        for (int g = 0; g < RUN; g++) {
+            if (pbkt[g] != 0xffffffffu) {
+                u64 pos = bs[pbkt[g]] + prank[g];
+                if (WIDE) {
+                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
+                    dst[0] = make_ulonglong2(pklo[g], pkhi[WIDE ? g : 0]);
+                    dst[1] = make_ulonglong2(pmeta[g], 0ULL);
+                } else {
+                    reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(pklo[g], pmeta[g]);
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void consume(const Occ (&o)[RUN], int nv)
+    {
+        u32 *h = hist + (size_t)parity * nb2();
+        u32 bkt[RUN], rank[RUN];
+#pragma unroll
+        for (int g = 0; g < RUN; g++) {
+            bkt[g] = 0xffffffffu; rank[g] = 0;
             if (g < nv) {
                 if ((o[g].klo | o[g].khi) == 0) {
                     if (MODE == 1) {   // the k-mer-0 side node is accumulated once, in the scatter pass
@@ -244,43 +277,40 @@ struct PartitionSink {
                         if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
                     }
                 } else {
-                    u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                    bkt[g] = (u32)((mod_P(h, t.P, t.M) - t.lo) >> shift);
-                    rank[g] = atomicAdd(&hist[bkt[g]], 1u);
+                    u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                    bkt[g] = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
+                    rank[g] = atomicAdd(&h[bkt[g]], 1u);
                 }
             }
         }
         if (MODE == 0) return;
-        __syncthreads();
+        __syncthreads();                 // round k counted; round k-1's reservations are visible
+        if (has_prev) write_prev();
+        u64 *bs = base + (size_t)parity * n_buckets;
         for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
-            u32 c = hist[b];
-            if (c) { base[b] = atomicAdd(cursor + b, (u64)c); hist[b] = 0; }
+            u32 c = h[b];
+            if (c) { bs[b] = atomicAdd(cursor + b, (u64)c); h[b] = 0; }
         }
-        __syncthreads();
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            if (bkt[g] != 0xffffffffu) {
-                u64 pos = base[bkt[g]] + rank[g];
-                u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
-                if (WIDE) {
-                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
-                    dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
-                    dst[1] = make_ulonglong2(meta, 0ULL);
-                } else {
-                    reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(o[g].klo, meta);
-                }
-            }
+        for (int g = 0; g < RUN; g++) {
+            pklo[g] = o[g].klo; if (WIDE) pkhi[g] = o[g].khi;
+            pmeta[g] = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+            pbkt[g] = bkt[g]; prank[g] = rank[g];
         }
+        has_prev = true;
+        parity ^= 1;
     }
 
     __device__ __forceinline__ void finish()
     {
+        __syncthreads();
         if (MODE == 0) {
-            __syncthreads();
             for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
                 u32 c = hist[b];
                 if (c) atomicAdd(counts + b, (u64)c);
             }
+        } else if (has_prev) {
+            write_prev();
         }
     }
 };
@@ -315,7 +345,7 @@ __global__ void __launch_bounds__(1024) k_scan_buckets(const u64 *__restrict__ c
 // the fused build kernel: one CTA per chunk of CB bases
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, class Sink>
-__global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sink)
 {
     extern __shared__ u32 smem[];
     u32 *pk = smem;                          // a.stage_words
@@ -328,6 +358,7 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
     const u64 chunk = blockIdx.x;
     const u64 cbase = a.abase + chunk * CB;
     const int K = a.K;
+    constexpr int RUN = Sink::RUN;
 
     sink.init(extra);
 
@@ -380,11 +411,11 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
         const u32 S = rpre[MAXR];
         if (tid == 0) n_occ += S;
 
-        // ---- (3) occurrences: each thread takes runs of G consecutive ones ----------------------------
+        // ---- (3) occurrences: each thread takes runs of RUN consecutive ones ----------------------------
         // (block-uniform trip count: every thread calls sink.consume, so sinks may use full-warp collectives)
-        for (u32 ob = 0; ob < S; ob += BLOCK * G) {
-            const u32 o0 = ob + tid * G;
-            Occ occ[G];
+        for (u32 ob = 0; ob < S; ob += BLOCK * RUN) {
+            const u32 o0 = ob + tid * RUN;
+            Occ occ[RUN];
             int nv = 0;
             if (o0 < S) {
             u32 lo = 0, hi = nr;
@@ -395,7 +426,7 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
             bool fresh = true;
             u64 flo = 0, fhi = 0, rlo = 0, rhi = 0;   // forward / reverse-complement words
 #pragma unroll
-            for (int g = 0; g < G; g++) {
+            for (int g = 0; g < RUN; g++) {
                 if (o0 + g < S) {
                     if (j >= ci) {
                         do { i++; ci = rpre[i + 1] - rpre[i]; } while (ci == 0);
@@ -456,25 +487,59 @@ __global__ void __launch_bounds__(BLOCK) k_build(BuildArgs a, Sink sink)
 // owner side of the exchange: insert received tuples
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
-                                                         InsertSink<WIDE, TRACK> sink)
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
+                                                         InsertSink<WIDE, TRACK> sink, const u64 *__restrict__ boffs, u32 n_buckets,
+                                                         int shift)
 {
     if (n_ptr) n = *n_ptr;      // exact count produced on the device (partitioned build): no host round trip
     sink.init(nullptr);
+    // Partitioned build: tuples are in bucket order.  Random first touches of a table slice would reach DRAM
+    // one 64-B burst at a time (~1 TB/s); instead the CTAs working on bucket b stream slice b+1 into L2 with
+    // coalesced prefetches, each CTA its share, so the inserts of the next bucket find their lines on chip.
+    if (boffs != nullptr && (u64)blockIdx.x * BLOCK * G < n) {
+        const u64 first = (u64)blockIdx.x * BLOCK * G;
+        u32 lo = 0, hi = n_buckets;                 // largest b with boffs[b] <= first
+        while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(boffs + mid) <= first) lo = mid; else hi = mid; }
+        const u32 b = lo;
+        if (b + 1 < n_buckets) {
+            const u64 b0 = __ldg(boffs + b), b1 = __ldg(boffs + b + 1);
+            const u64 ctas = (b1 - b0 + (u64)BLOCK * G - 1) / ((u64)BLOCK * G);     // CTAs that start inside bucket b
+            const u64 k = (first - b0) / ((u64)BLOCK * G);
+            const u64 slice_lo = (u64)(b + 1) << shift;
+            u64 slice_n = (u64)1 << shift;
+            if (slice_lo + slice_n > sink.t.n_local) slice_n = sink.t.n_local - slice_lo;
+            const u64 lines = slice_n * sizeof(Node) / 128;                        // 128-B L2 lines in the slice
+            const u64 l0 = lines * k / ctas, l1 = lines * (k + 1) / ctas;
+            const char *basep = reinterpret_cast<const char *>(sink.t.nodes + slice_lo);
+            for (u64 l = l0 + threadIdx.x; l < l1; l += BLOCK)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
+        }
+    }
     // CTA i takes tuples [i*BLOCK*G, ...): CTAs are scheduled in index order, so the resident CTAs always work
     // on a narrow window of the (bucket-ordered) tuple array -> the table slice they touch stays in L2
     const u64 stride = (u64)gridDim.x * BLOCK * G;
     for (u64 base0 = (u64)blockIdx.x * BLOCK * G; base0 < n; base0 += stride) {   // block-uniform trip count
         const u64 base = base0 + (u64)threadIdx.x * G;
         Occ occ[G]; int nv = 0;
+        if (!WIDE && base + G <= n) {
+            // narrow tuples are 16 B: one 256-bit streaming load brings two of them (read once: evict first)
+            static_assert(G % 2 == 0, "G must be even");
+#pragma unroll
+            for (int g = 0; g < G; g += 2) {
+                u64 k0, m0, k1, m1;
+                ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + base + g, k0, m0, k1, m1);
+                occ[g].klo = k0; occ[g].khi = 0; occ[g].lb = (u32)(m0 & 15); occ[g].rb = (u32)((m0 >> 4) & 15); occ[g].ord = m0 >> 8;
+                occ[g + 1].klo = k1; occ[g + 1].khi = 0; occ[g + 1].lb = (u32)(m1 & 15); occ[g + 1].rb = (u32)((m1 >> 4) & 15); occ[g + 1].ord = m1 >> 8;
+            }
+            nv = G;
+        } else {
 #pragma unroll
         for (int g = 0; g < G; g++) {
             if (base + g < n) {
                 u64 klo, khi = 0, meta;
                 if (WIDE) {
-                    ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g));   // read once: evict first
-                    ulonglong2 y = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g) + 1);
-                    klo = x.x; khi = x.y; meta = y.x;
+                    u64 z;
+                    ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g), klo, khi, meta, z);
                 } else {
                     ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + base + g);
                     klo = x.x; meta = x.y;
@@ -483,6 +548,7 @@ __global__ void __launch_bounds__(BLOCK) k_insert_tuples(const u64 *__restrict__
                 occ[g].ord = meta >> 8;
                 nv = g + 1;
             }
+        }
         }
         sink.consume(occ, nv);
     }
@@ -500,7 +566,8 @@ __global__ void k_layout_insert(const Node *__restrict__ nodes, u64 n_local, u64
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
-        u64 klo = __ldg(&nodes[i].klo), khi = WIDE ? __ldg(&nodes[i].khi) : 0;
+        ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2 *>(nodes + i));
+        u64 klo = kk.x, khi = WIDE ? kk.y : 0;
         if ((klo | khi) == 0) continue;
         u64 cur = TRACK ? ~__ldg(&nodes[i].nord) : (lo_slot + i);
         u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
@@ -520,10 +587,13 @@ __global__ void k_layout_place(const Node *__restrict__ nodes, u64 n_local, u64 
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
-        u64 klo, khi, links, nord;
-        load_node(nodes + i, klo, khi, links, nord);
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(nodes + i);
+        ulonglong2 ka = __ldg(q);
+        u64 klo = ka.x, khi = WIDE ? ka.y : 0;
         if ((klo | khi) == 0) continue;
-        u64 pri = TRACK ? ~nord : (lo_slot + i);
+        uint4 cl = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 2), cr = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 3);
+        u64 links = (u64)pack_link(cl) | ((u64)pack_link(cr) << 32);
+        u64 pri = TRACK ? ~__ldg(&nodes[i].nord) : (lo_slot + i);
         u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
         u64 s = mod_P(h, P, M);
         while (__ldg(owner + s) != pri) s = (s + 1 == P) ? 0 : s + 1;
@@ -810,17 +880,21 @@ __device__ __forceinline__ u64 splitmix(u64 z)
     return z ^ (z >> 31);
 }
 
+struct __align__(32) Rec32 { u64 a, b, links, d; };
+
 template <int MODE>
-__global__ void __launch_bounds__(256) k_random_rmw(Node *tab, u64 n_nodes, u64 n_ops, u64 seed)
+__global__ void __launch_bounds__(256) k_random_rmw(Rec32 *tab, u64 n_nodes, u64 n_ops, u64 seed)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x * G;
     for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * G; base < n_ops; base += stride) {
-        Node *p[G]; u64 klo[G], khi[G], links[G], nord[G];
+        Rec32 *p[G]; u64 links[G];
 #pragma unroll
         for (int g = 0; g < G; g++) {
             u64 h = splitmix(seed + base + g);
             p[g] = tab + __umul64hi(h, n_nodes);
-            load_node(p[g], klo[g], khi[g], links[g], nord[g]);
+            ulonglong2 x = __ldcg(reinterpret_cast<const ulonglong2 *>(p[g]));
+            ulonglong2 y = __ldcg(reinterpret_cast<const ulonglong2 *>(p[g]) + 1);
+            links[g] = y.x + (x.x & 1);
         }
 #pragma unroll
         for (int g = 0; g < G; g++) {
