@@ -54,7 +54,7 @@ SYMBOLS = [
     "dbg_device_count", "dbg_host_alloc", "dbg_host_free", "dbg_create", "dbg_destroy", "dbg_submit_reads",
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
-    "dbg_export_links", "dbg_dump_compact", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
+    "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
 ]
 
@@ -96,6 +96,7 @@ def load(build_if_missing: bool = True):
         "dbg_export_kmerset": (C.c_int, [vp, vp, vp]),
         "dbg_export_links": (C.c_int, [vp, i32, vp, vp, vp, vp, C.POINTER(u64), vp, C.POINTER(u64), vp]),
         "dbg_dump_compact": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, C.POINTER(u64)]),
+        "dbg_dump_shard": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(u64)]),
         "dbg_device_image": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "dbg_get_timings": (C.c_int, [vp, vp]),
         "dbg_launch_count": (u64, [vp]),

@@ -852,6 +852,43 @@ extern "C" int dbg_dump_compact(dbg_ctx *c, int32_t freq_cutoff, uint64_t *slots
     return DBG_OK;
 }
 
+extern "C" int dbg_dump_shard(dbg_ctx *c, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *l_link, uint32_t *r_link,
+                              uint64_t *first_ordinal, uint64_t *n)
+{
+    if (!c || !n) return set_err(DBG_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    u64 cnt[CNT_N];
+    int rc = read_counters(c, cnt);
+    if (rc) return rc;
+    uint64_t m = cnt[CNT_NEW], cap = *n;
+    *n = m;
+    if (!kmers_lo && !kmers_hi && !l_link && !r_link && !first_ordinal) return DBG_OK;   // size query
+    if (cap < m) return set_err(DBG_ERR_BUFFER, "dump capacity %llu < %llu", (unsigned long long)cap, (unsigned long long)m);
+    u64 *d_lo = nullptr, *d_hi = nullptr, *d_ord = nullptr, *d_cur = nullptr; u32 *d_l = nullptr, *d_r = nullptr;
+    cudaError_t e1 = cudaMalloc(&d_cur, 8);
+    if (e1 == cudaSuccess) e1 = cudaMemset(d_cur, 0, 8);
+    if (e1 == cudaSuccess && kmers_lo) e1 = cudaMalloc(&d_lo, (m + 1) * 8);
+    if (e1 == cudaSuccess && kmers_hi) e1 = cudaMalloc(&d_hi, (m + 1) * 8);
+    if (e1 == cudaSuccess && first_ordinal) e1 = cudaMalloc(&d_ord, (m + 1) * 8);
+    if (e1 == cudaSuccess && l_link) e1 = cudaMalloc(&d_l, (m + 1) * 4);
+    if (e1 == cudaSuccess && r_link) e1 = cudaMalloc(&d_r, (m + 1) * 4);
+    if (e1 == cudaSuccess) {
+        if (c->wide) k_dump_shard<true><<<148 * 8, 256, 0, c->stream>>>(c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
+        else k_dump_shard<false><<<148 * 8, 256, 0, c->stream>>>(c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
+        c->launches++;
+        e1 = cudaGetLastError();
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);
+    }
+    if (e1 == cudaSuccess && kmers_lo && m) e1 = cudaMemcpy(kmers_lo, d_lo, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && kmers_hi && m) e1 = cudaMemcpy(kmers_hi, d_hi, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && first_ordinal && m) e1 = cudaMemcpy(first_ordinal, d_ord, m * 8, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && l_link && m) e1 = cudaMemcpy(l_link, d_l, m * 4, cudaMemcpyDeviceToHost);
+    if (e1 == cudaSuccess && r_link && m) e1 = cudaMemcpy(r_link, d_r, m * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_cur); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_ord); cudaFree(d_l); cudaFree(d_r);
+    CU_TRY(e1);
+    return DBG_OK;
+}
+
 extern "C" int dbg_get_timings(dbg_ctx *c, float ms[8])
 {
     if (!c || !ms) return set_err(DBG_ERR_INVALID, "NULL argument");

@@ -869,6 +869,35 @@ __global__ void __launch_bounds__(256) k_compact_nodes(const void *__restrict__ 
     }
 }
 
+// unordered dump of a shard's build table (multi-GPU: every rank hands its nodes to whoever merges them)
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_dump_shard(const Node *__restrict__ nodes, u64 n_local, u64 cap, u64 *cursor,
+                                                    u64 *klo_out, u64 *khi_out, u32 *l_out, u32 *r_out, u64 *ord_out)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n_local; i0 += stride) {
+        u64 i = i0 + threadIdx.x;
+        bool keep = false;
+        u64 klo = 0, khi = 0, nord = 0, pad;
+        if (i < n_local) { ld256_cg(nodes + i, klo, khi, nord, pad); keep = (klo | (WIDE ? khi : 0ULL)) != 0; }
+        u32 bal = __ballot_sync(0xffffffffu, keep);
+        u64 base = 0;
+        if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(cursor, (u64)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            u64 pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+            if (pos < cap) {
+                uint4 cl = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 2), cr = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 3);
+                if (klo_out) klo_out[pos] = klo;
+                if (khi_out) khi_out[pos] = WIDE ? khi : 0;
+                if (l_out) l_out[pos] = pack_link(cl);
+                if (r_out) r_out[pos] = pack_link(cr);
+                if (ord_out) ord_out[pos] = ~nord;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // roofline denominator: uniformly random 32-B sector read-modify-writes
 // ---------------------------------------------------------------------------------------------------

@@ -174,6 +174,18 @@ class DBGBuilder:
                                            C.byref(cap)), "dbg_dump_compact")
         return {k: v[:n.value] for k, v in out.items()}
 
+    def dump_shard(self):
+        """unordered nodes of this context's build table: dict kmer, kmer_hi, l, r, ord (no k-mer-0 node)"""
+        n = C.c_uint64(0)
+        capi.check(self.L.dbg_dump_shard(self.h, None, None, None, None, None, C.byref(n)), "dbg_dump_shard")
+        m = max(n.value, 1)
+        out = dict(kmer=np.zeros(m, np.uint64), kmer_hi=np.zeros(m, np.uint64), l=np.zeros(m, np.uint32),
+                   r=np.zeros(m, np.uint32), ord=np.zeros(m, np.uint64))
+        cap = C.c_uint64(m)
+        capi.check(self.L.dbg_dump_shard(self.h, out["kmer"].ctypes.data, out["kmer_hi"].ctypes.data, out["l"].ctypes.data,
+                                         out["r"].ctypes.data, out["ord"].ctypes.data, C.byref(cap)), "dbg_dump_shard")
+        return {k: v[:n.value] for k, v in out.items()}
+
     def device_image(self):
         a, f = C.c_void_p(), C.c_void_p()
         capi.check(self.L.dbg_device_image(self.h, C.byref(a), C.byref(f)), "dbg_device_image")

@@ -47,7 +47,20 @@ class Exchange:
         for c in recv_counts_host:
             outs.append(recv[off:off + int(c)])
             off += int(c)
-        dist.all_to_all(outs, list(buckets), group=self.group)
+        # one send + one recv per peer inside ONE group (ncclGroupStart/End under NCCL == all-to-all(v);
+        # also what gloo offers, so the CPU tests run the same code)
+        outs[self.rank].copy_(buckets[self.rank])
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            if buckets[q].shape[0]:
+                ops.append(dist.P2POp(dist.isend, buckets[q].contiguous(), q, group=self.group))
+            if outs[q].shape[0]:
+                ops.append(dist.P2POp(dist.irecv, outs[q], q, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
         return recv[:total], total
 
     def allreduce_sum_u64(self, a: np.ndarray, device) -> np.ndarray:

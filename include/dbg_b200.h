@@ -145,6 +145,13 @@ int  dbg_export_links(dbg_ctx *ctx, int32_t freq_cutoff, uint8_t *klink, uint8_t
 int  dbg_dump_compact(dbg_ctx *ctx, int32_t freq_cutoff, uint64_t *slots, uint64_t *kmers_lo,
                       uint64_t *kmers_hi, uint32_t *l_link, uint32_t *r_link, uint64_t *n);
 
+/* Unordered dump of THIS context's build table (any context, sharded or not; excludes the k-mer-0 side
+ * node): nodes with link words already clamped to the reference's 8-bit lanes, plus each node's
+ * first-occurrence ordinal (read_index << 16 | position) when track_order is on.  *n = capacity in,
+ * count out; all-NULL output pointers = size query. */
+int  dbg_dump_shard(dbg_ctx *ctx, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *l_link, uint32_t *r_link,
+                    uint64_t *first_ordinal, uint64_t *n);
+
 /* device pointers of the finalized image, for callers that stay on the GPU (bench, multi-GPU gather) */
 int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
 
