@@ -182,6 +182,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload(args.workload, world, args.scale)
+    if args.init_g:
+        cfg["init_g"] = args.init_g; cfg["init_g_total"] = args.init_g * world
     n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
     occ_rank = n * (L - K + 1)
     p = synth.make_params(cfg["seed"], cfg["genome_len_total"], L, cfg["insert"], cfg["err"], cfg["n_rate"])
@@ -190,7 +192,8 @@ def run_b200(args):
     synth.reads_device(p, first_read, n, d_bases.data_ptr(), device=local)
     d_offs = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    from dbg_assembly_b200.graph import torch_stream_handle
+    stream = torch_stream_handle(dev)
     init_slots = int(cfg["init_g_total"] * 1000000000)
 
     def barrier():
@@ -233,11 +236,11 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    build_ms, clear_ms, layout_ms = [], [], []
+    build_ms, clear_ms, layout_ms, insert_ms = [], [], [], []
     for _ in range(args.steps):
         st = step()
         tm = timings()
-        build_ms.append(tm["build_ms"]); clear_ms.append(tm["clear_ms"]); layout_ms.append(tm["layout_ms"])
+        build_ms.append(tm["build_ms"]); clear_ms.append(tm["clear_ms"]); layout_ms.append(tm["layout_ms"]); insert_ms.append(tm["insert_ms"])
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -257,15 +260,32 @@ def run_b200(args):
     ms_per_step = ms_total / args.steps
     value = occ_total / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (the fused build kernel; insert kernel when sharded) ----
+    # ---- roofline of the dominant kernel: the bucketed hash-insert kernel (k_insert_tuples) when the
+    # ---- partitioned path ran, else the fused direct-insert build kernel.  achieved = occurrences x 32 B
+    # ---- (one 16-B slot read + one 16-B slot write) / that kernel's CUDA-event time.
     peak, peak_src = measured_peaks()
     kb = float(np.mean(build_ms))
-    node_bytes = 32
-    achieved = st["occurrences"] * 2 * node_bytes / 2 / (kb * 1e-3) / 1e9 if kb > 0 else None   # occ x 32 B
+    ki = float(np.mean(insert_ms))
+    dom_ms = ki if ki > 0 else kb
+    achieved = st["occurrences"] * 32 / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    if world == 1:
+        kname = ("k_insert_tuples (bucket-ordered hash insert, L2-resident table slices)" if ki > 0
+                 else "k_build<InsertSink> (fused 2-bit pack + canonical k-mer + direct hash insert)")
+    else:
+        kname = "k_insert_tuples (owner-side insert of exchanged tuples)"
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "kernel": "k_build<InsertSink> (fused 2-bit pack + canonical k-mer + hash insert)" if world == 1 else "k_build<BucketSink> + k_insert_tuples",
-            "algorithmic_bytes_per_occurrence": 32, "kernel_ms_per_step": kb, "clear_ms_per_step": float(np.mean(clear_ms)),
+            "traffic": None, "kernel": kname, "algorithmic_bytes_per_occurrence": 32, "kernel_ms_per_step": dom_ms,
+            "build_kernels_ms_per_step": kb, "clear_ms_per_step": float(np.mean(clear_ms)),
             "layout_ms_per_step": float(np.mean(layout_ms)), "peak_source": peak_src}
+    traffic_file = os.path.join(REPO, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(traffic_file):
+        try:
+            tj = json.load(open(traffic_file))
+            if world == 1 and args.scale == 1.0 and ki > 0:
+                roof["traffic"] = tj.get("k_insert_tuples_dram_bytes_per_launch")
+                roof["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -360,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; numbers at scale != 1 are not the metric)")
+    ap.add_argument("--init-g", type=float, default=None, help="override the table size -i (experiments only)")
     ap.add_argument("--ref-sample-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-micro", action="store_true")

@@ -108,18 +108,18 @@ static const uint64_t SUB_BASES_DEFAULT = 64ull << 20;
 static const uint64_t SUB_READS_DEFAULT = 2ull << 20;
 static const uint64_t MARGIN_SLOTS = 1ull << 16; // overflow zone past a shard's home range (no wrap in the hot loop)
 
-struct EvPair { cudaEvent_t a, b; };
+struct EvPair { cudaEvent_t a, b; int slot; };   // slot: which ms[] entry the elapsed time is added to
 
 struct dbg_ctx {
     dbg_params prm;
     bool wide, track;
-    int device;
+    int device, n_sms;
     uint64_t P, M, max_cutoff;
     float lf;
     uint64_t shard_lo, shard_hi, shard_size, n_local;
     int n_shards;
     cudaStream_t stream, copy_stream, own_stream;
-    Node *d_nodes;
+    void *d_nodes;                 // n_local x NodeT<wide>
     u64 *d_counters, *d_polyA;
     // host-submit staging (double buffered)
     char *d_bases[2];
@@ -155,7 +155,8 @@ struct dbg_ctx {
     float ms[8];
 };
 
-static int node_bytes(const dbg_ctx *c) { return c->wide ? 32 : 16; }
+static int node_bytes(const dbg_ctx *c) { return c->wide ? 32 : 16; }            // export image
+static size_t build_node_bytes(const dbg_ctx *c) { return c->wide ? sizeof(NodeT<true>) : sizeof(NodeT<false>); }
 
 static TableView view_of(dbg_ctx *c)
 {
@@ -167,6 +168,7 @@ static TableView view_of(dbg_ctx *c)
 
 static int ev_begin(dbg_ctx *c, cudaStream_t s, EvPair *p)
 {
+    p->slot = 1;
     CU_TRY(cudaEventCreate(&p->a));
     CU_TRY(cudaEventCreate(&p->b));
     CU_TRY(cudaEventRecord(p->a, s));
@@ -205,7 +207,7 @@ static int clear_table(dbg_ctx *c)
     EvPair e;
     int rc = ev_begin(c, c->stream, &e);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(c->d_nodes, 0, c->n_local * sizeof(Node), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_nodes, 0, c->n_local * build_node_bytes(c), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(u64), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_polyA, 0, 8 * sizeof(u64), c->stream));
     CU_TRY(cudaEventRecord(e.b, c->stream));
@@ -227,8 +229,11 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (ndev == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible: libdbgb200 has no CPU fallback");
     if (p->device < 0 || p->device >= ndev) return set_err(DBG_ERR_INVALID, "device %d of %d", p->device, ndev);
     CU_TRY(cudaSetDevice(p->device));
+    int n_sms = 148;
+    CU_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, p->device));
 
     dbg_ctx *c = new dbg_ctx();
+    c->n_sms = n_sms;
     memset(&c->st, 0, sizeof(c->st));
     c->prm = *p;
     c->wide = p->K > 31 || p->force_wide;
@@ -258,9 +263,9 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
     c->part_mode = 2;
     if (const char *e = getenv("DBG_B200_PARTITION")) c->part_mode = atoi(e) == 0 ? 0 : (atoi(e) == 1 ? 1 : 2);
-    // one bucket = a table slice of 16 MB (2^18 nodes of 64 B): the slice in use, the one being prefetched and the
-    // tuple stream fit the 126 MB L2 with room to spare
-    c->part_shift = 18;
+    // one bucket = a table slice of 16 MB (2^19 nodes of 32 B, 2^18 of 64 B): the slice in use, the one being
+    // prefetched and the tuple stream fit the 126 MB L2 with room to spare
+    c->part_shift = c->wide ? 18 : 19;
     if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
     while (((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift) > 4096) c->part_shift++;
     c->n_buckets = (uint32_t)((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift);
@@ -269,7 +274,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * sizeof(Node)));
+    CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * build_node_bytes(c)));
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_bcounts, (size_t)c->n_buckets * sizeof(u64)));
@@ -337,12 +342,14 @@ static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_ch
 template <bool WIDE, bool TRACK>
 static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed)
 {
-    uint64_t blocks = (n_upper + (uint64_t)BLOCK * G - 1) / ((uint64_t)BLOCK * G);
-    if (blocks == 0) return DBG_OK;
-    if (blocks > 0x7fffffffull) return set_err(DBG_ERR_INVALID, "too many tuples for one launch");
-    InsertSink<WIDE, TRACK> sk; sk.t = view_of(c);
-    k_insert_tuples<WIDE, TRACK><<<(unsigned)blocks, BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, sk,
-                                                                    bucketed ? c->d_boffs : nullptr, c->n_buckets, c->part_shift);
+    if (n_upper == 0) return DBG_OK;
+    uint64_t tiles = (n_upper + INS_BLOCK - 1) / INS_BLOCK;
+    uint64_t persistent = (uint64_t)c->n_sms * INS_CTAS;
+    unsigned grid = (unsigned)(tiles < persistent ? tiles : persistent);
+    CU_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(u64), s));      // tile counter
+    k_insert_tuples<WIDE, TRACK><<<grid, INS_BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, view_of(c),
+                                                            bucketed ? c->d_boffs : nullptr, c->n_buckets, c->part_shift,
+                                                            c->d_counters + 7);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return DBG_OK;
@@ -372,7 +379,15 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     a.count_stats = 1;
     rc = launch_build<WIDE>(c, a, ss, n_chunks, s, c->n_buckets);
     if (rc) return rc;
-    return insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s, true);
+    EvPair ev;                       // the insert kernel alone (ms[6]): the roofline's dominant kernel
+    rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    ev.slot = 6;
+    rc = insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s, true);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
 }
 
 static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
@@ -381,7 +396,7 @@ static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
     if (c->part_mode == 1) return true;
     // auto: streaming the table slice through L2 once per block (2 x table bytes) plus 2 x 16..32 B of tuple
     // traffic must beat one random 64-B sector round trip per occurrence at ~1/5 of the streaming rate
-    return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * sizeof(Node);
+    return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * build_node_bytes(c);
 }
 
 static int ensure_tuples(dbg_ctx *c, uint64_t need)
@@ -646,9 +661,9 @@ template <bool WIDE, bool TRACK>
 static int run_layout(dbg_ctx *c)
 {
     unsigned grid = 148 * 16;
-    k_layout_insert<WIDE, TRACK><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M);
+    k_layout_insert<WIDE, TRACK><<<grid, 256, 0, c->stream>>>((const NodeT<WIDE> *)c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M);
     CU_TRY(cudaGetLastError());
-    k_layout_place<WIDE, TRACK><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M, c->d_out, c->d_nul32);
+    k_layout_place<WIDE, TRACK><<<grid, 256, 0, c->stream>>>((const NodeT<WIDE> *)c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M, c->d_out, c->d_nul32);
     CU_TRY(cudaGetLastError());
     k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->d_owner, c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
     CU_TRY(cudaGetLastError());
@@ -665,10 +680,8 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
     if (rc) return rc;
     if (!c->finalized) {
         // build time = sum over blocks
-        float tb = 0;
-        for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); tb += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         c->build_ev.clear();
-        c->ms[1] += tb;
         if (c->n_shards <= 1) {
             if (cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
             size_t nb = (size_t)node_bytes(c);
@@ -873,8 +886,8 @@ extern "C" int dbg_dump_shard(dbg_ctx *c, uint64_t *kmers_lo, uint64_t *kmers_hi
     if (e1 == cudaSuccess && l_link) e1 = cudaMalloc(&d_l, (m + 1) * 4);
     if (e1 == cudaSuccess && r_link) e1 = cudaMalloc(&d_r, (m + 1) * 4);
     if (e1 == cudaSuccess) {
-        if (c->wide) k_dump_shard<true><<<148 * 8, 256, 0, c->stream>>>(c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
-        else k_dump_shard<false><<<148 * 8, 256, 0, c->stream>>>(c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
+        if (c->wide) k_dump_shard<true><<<148 * 8, 256, 0, c->stream>>>((const NodeT<true> *)c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
+        else k_dump_shard<false><<<148 * 8, 256, 0, c->stream>>>((const NodeT<false> *)c->d_nodes, c->n_local, m, d_cur, d_lo, d_hi, d_l, d_r, d_ord);
         c->launches++;
         e1 = cudaGetLastError();
         if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->stream);
@@ -903,21 +916,29 @@ extern "C" uint64_t dbg_launch_count(const dbg_ctx *c) { return c ? c->launches 
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dbg_measure_random_rmw(int32_t device, uint64_t bytes, uint64_t n_ops, int32_t mode, float *ms)
 {
-    if (!ms || bytes < sizeof(Rec32)) return set_err(DBG_ERR_INVALID, "bad argument");
+    if (!ms || bytes < sizeof(Rec32) || mode < 0 || mode > 5) return set_err(DBG_ERR_INVALID, "bad argument");
     if (dbg_device_count() == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible");
     CU_TRY(cudaSetDevice(device));
     Rec32 *tab = nullptr;
-    CU_TRY(cudaMalloc(&tab, bytes));
-    cudaError_t e1 = cudaMemset(tab, 0, bytes);
+    CU_TRY(cudaMalloc(&tab, bytes + 8));
+    cudaError_t e1 = cudaMemset(tab, 0, bytes + 8);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     uint64_t n_nodes = bytes / sizeof(Rec32);
+    u64 *sink = reinterpret_cast<u64 *>(reinterpret_cast<char *>(tab) + (bytes & ~7ull));
     unsigned grid = 148 * 32;
     float best = 1e30f;
     for (int it = 0; it < 4 && e1 == cudaSuccess; it++) {   // first iteration is warm-up
         cudaEventRecord(a);
-        if (mode == 0) k_random_rmw<0><<<grid, 256>>>(tab, n_nodes, n_ops, 0x1234567ull * (it + 1));
-        else k_random_rmw<1><<<grid, 256>>>(tab, n_nodes, n_ops, 0x1234567ull * (it + 1));
+        u64 seed = 0x1234567ull * (it + 1);
+        switch (mode) {
+        case 0: k_random_rmw<0><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        case 1: k_random_rmw<1><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        case 2: k_random_rmw<2><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        case 3: k_random_rmw<3><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        case 4: k_random_rmw<4><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        default: k_random_rmw<5><<<grid, 256>>>(tab, n_nodes, n_ops, seed, sink); break;
+        }
         cudaEventRecord(b);
         e1 = cudaEventSynchronize(b);
         float t = 0;

@@ -8,32 +8,35 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 namespace dbg {
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-// ---- device table node: 64 B = two 32-B sectors of one DRAM burst ------------------------------------
-// sector 0  klo/khi: canonical k-mer (khi == 0 on the 64-bit path); (0,0) = empty, like the reference, whose
-//                    all-A k-mer is kept in a side node (DBGgraph.cpp:153-164).
-//           nord   : ~ordinal of the earliest occurrence seen so far (0 = none yet); ordinal =
-//                    read_index<<16 | j.  Only used to reproduce the reference's slot layout.
-// sector 1  cnt[8] : occurrence counts per neighbour base, l lanes A,C,G,T then r lanes A,C,G,T, as plain
-//                    u32 so that an update is a fire-and-forget `red.add` (no CAS loop, no return trip).
-//                    The reference's 8-bit saturating lanes (kmerSet.cpp:56,341) are min(255, cnt) at
-//                    export; updates stop once a loaded count is >= 255, so a u32 cannot wrap.
-struct __align__(64) Node {
-    u64 klo;
-    u64 khi;
-    u64 nord;
-    u64 pad;
-    u32 cnt[8];
-};
-static_assert(sizeof(Node) == 64, "node must be two sectors");
+// ---- device table node ------------------------------------------------------------------------------
+// K <= 31: 32 B = exactly ONE DRAM sector   { klo | nord | 8 x f16 counts }
+// K <= 63: 64 B = two sectors of one burst  { klo khi nord pad | 8 x f16 counts, 16 B pad }
+//   klo/khi: canonical k-mer; (0,0) = empty, like the reference, whose all-A k-mer is kept in a side node
+//            (DBGgraph.cpp:153-164).
+//   nord   : ~ordinal of the earliest occurrence seen so far (0 = none yet); ordinal = read_index<<16 | j.
+//            Only used to reproduce the reference's slot layout at export.
+//   counts : occurrences per neighbour base, l lanes A,C,G,T then r lanes A,C,G,T, as IEEE half floats, so
+//            that one occurrence is ONE fire-and-forget 128-bit vector reduction
+//            (red.global.add.noftz.v4.f16x2 -> SASS REDG.E.ADD.F16x8) adding 1.0 to its two lanes: no CAS
+//            loop, no return trip, one L2 request.  Halves count integers exactly up to 2048 and then stay
+//            at 2048 (2048 + 1 rounds back to 2048), so a lane can never overflow; the reference's 8-bit
+//            saturating lanes (kmerSet.cpp:56,341) are min(255, count) at export.
+template <bool WIDE> struct NodeT;
+template <> struct __align__(32) NodeT<false> { u64 klo; u64 nord; u64 c0; u64 c1; };
+template <> struct __align__(64) NodeT<true> { u64 klo; u64 khi; u64 nord; u64 pad; u64 c0; u64 c1; u64 pad2[2]; };
+static_assert(sizeof(NodeT<false>) == 32 && sizeof(NodeT<true>) == 64, "node sizes");
+constexpr u32 HALF_ONE = 0x3C00u;     // 1.0
+constexpr u32 HALF_255 = 0x5BF8u;     // 255.0; positive halves order like their bit patterns
 
 struct TableView {
-    Node *nodes;      // n_local slots (shard range + overflow margin)
+    void *nodes;      // n_local NodeT<WIDE> slots (shard range + overflow margin)
     u64 P;            // reference table size (find_next_prime)
     u64 M;            // floor(2^64 / P) for the Barrett reduction of hash % P
     u64 lo;           // first home slot owned by this shard
@@ -158,28 +161,65 @@ __device__ __forceinline__ void ld256_cs(const void *p, u64 &a, u64 &b, u64 &c, 
 
 struct NodeRegs {
     u64 klo, khi, nord;
-    u32 cl, cr;        // the two counters this occurrence would bump (0 if it has no such neighbour)
+    u64 c0, c1;        // l lanes / r lanes, 4 halves each
 };
 
-// key sector (one request) + only the two counter lanes of interest (keeps the register footprint small).
 // .cg: the table is only ever coherent at L2 (atomics live there)
-__device__ __forceinline__ void load_node(const Node *p, u32 lb, u32 rb, NodeRegs &n)
+__device__ __forceinline__ void load_node(const NodeT<false> *p, NodeRegs &n)
+{
+    ld256_cg(p, n.klo, n.nord, n.c0, n.c1);    // the whole node: one request
+    n.khi = 0;
+}
+__device__ __forceinline__ void load_node(const NodeT<true> *p, NodeRegs &n)
 {
     u64 pad;
     ld256_cg(p, n.klo, n.khi, n.nord, pad);
-    n.cl = lb < 4 ? __ldcg(&p->cnt[lb]) : 0u;
-    n.cr = rb < 4 ? __ldcg(&p->cnt[4 + rb]) : 0u;
+    ulonglong2 c = __ldcg(reinterpret_cast<const ulonglong2 *>(p) + 2);
+    n.c0 = c.x; n.c1 = c.y;
 }
 
-__device__ __forceinline__ u32 pick4(const uint4 &v, u32 i)
+// what the insert path keeps of a probed node: key, ordinal and the two lanes this occurrence would bump
+struct ProbeRegs {
+    u64 klo, khi, nord;
+    u32 lanes;         // half bits of l lane lb | r lane rb << 16 (0 when the occurrence has no such neighbour)
+};
+
+template <bool WIDE>
+__device__ __forceinline__ void probe_node(const NodeT<WIDE> *p, u32 lb, u32 rb, ProbeRegs &q)
 {
-    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+    NodeRegs n;
+    load_node(p, n);
+    q.klo = n.klo; q.khi = n.khi; q.nord = n.nord;
+    u32 l = lb < 4 ? ((u32)(n.c0 >> (16 * lb)) & 0xFFFFu) : 0xFFFFu;      // 0xFFFF: "nothing to add on this side"
+    u32 r = rb < 4 ? ((u32)(n.c1 >> (16 * rb)) & 0xFFFFu) : 0xFFFFu;
+    q.lanes = l | (r << 16);
 }
 
-// the reference's link word from four u32 counts: lane of base b = bits (3-b)*8.., saturating at 255
-__device__ __forceinline__ u32 pack_link(const uint4 &c)
+// one occurrence: +1.0 on lane lb of the l counts and lane rb of the r counts (skipping lanes that are
+// absent or already known to be >= 255), as ONE 128-bit vector reduction
+template <bool WIDE>
+__device__ __forceinline__ void bump_counts(NodeT<WIDE> *p, u32 lanes, u32 lb, u32 rb)
 {
-    return (min(c.x, 255u) << 24) | (min(c.y, 255u) << 16) | (min(c.z, 255u) << 8) | min(c.w, 255u);
+    u64 al = 0, ar = 0;
+    if ((lanes & 0xFFFFu) < HALF_255) al = (u64)HALF_ONE << (16 * (lb & 3));
+    if ((lanes >> 16) < HALF_255) ar = (u64)HALF_ONE << (16 * (rb & 3));
+    if ((al | ar) == 0) return;
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(&p->c0), "r"((u32)al), "r"((u32)(al >> 32)),
+                 "r"((u32)ar), "r"((u32)(ar >> 32))
+                 : "memory");
+}
+
+// the reference's link word from four half counts: lane of base b = bits (3-b)*8.., saturating at 255
+__device__ __forceinline__ u32 pack_link(u64 c)
+{
+    u32 w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        float f = __half2float(__ushort_as_half((unsigned short)(c >> (16 * b))));
+        u32 v = (u32)f;
+        w |= (v > 255u ? 255u : v) << (24 - 8 * b);
+    }
+    return w;
 }
 
 __device__ __forceinline__ bool cas128(void *addr, u64 new_lo, u64 new_hi, u64 &old_lo, u64 &old_hi)

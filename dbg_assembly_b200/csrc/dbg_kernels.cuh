@@ -23,7 +23,7 @@ constexpr int BLOCK = 256;     // threads per CTA
 constexpr int MAXR = 1024;     // reads per shared-memory table pass
 constexpr int G = 4;           // consecutive occurrences per thread run (rolling k-mer + 4 probes in flight)
 #ifndef DBG_MIN_CTAS
-#define DBG_MIN_CTAS 3
+#define DBG_MIN_CTAS 2
 #endif
 constexpr int MIN_CTAS = DBG_MIN_CTAS;    // register budget of the insert kernels: CTAs (x8 warps) per SM
 constexpr u64 EMPTY_PRI = ~0ULL;
@@ -66,6 +66,47 @@ __global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, u64 aba
 // ---------------------------------------------------------------------------------------------------
 // sinks
 // ---------------------------------------------------------------------------------------------------
+// thread_updatekmers for ONE occurrence (DBGgraph.cpp:167-205), lock-free: load the whole node with one
+// 256-bit request, claim an empty slot with a CAS (the only atomic with a return value, and only for NEW
+// keys), count with one fire-and-forget vector RED, keep the earliest ordinal with a RED.max.
+template <bool WIDE, bool TRACK>
+__device__ __forceinline__ void insert_one(const TableView &t, u64 klo, u64 khi, u32 lb, u32 rb, u64 ord, u32 &n_new, u32 &n_conf)
+{
+    typedef NodeT<WIDE> Nd;
+    u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
+    Nd *p = static_cast<Nd *>(t.nodes) + (mod_P(h, t.P, t.M) - t.lo);
+    Nd *const p_end = static_cast<Nd *>(t.nodes) + t.n_local;
+    for (;;) {
+        NodeRegs n;
+        load_node(p, n);
+        if ((n.klo | n.khi) == 0) {
+            if (WIDE) {
+                u64 olo, ohi;
+                if (cas128(p, klo, khi, olo, ohi)) { n_new++; n.klo = klo; n.khi = khi; }
+                else { n.klo = olo; n.khi = ohi; }
+            } else {
+                u64 old = atomicCAS(&p->klo, 0ULL, klo);
+                if (old == 0) { n_new++; n.klo = klo; }
+                else n.klo = old;                       // somebody else got the slot
+            }
+        }
+        if (n.klo == klo && (!WIDE || n.khi == khi)) {
+            // a stale (too small) loaded count only costs a redundant add; export clamps to 255
+            u32 l = lb < 4 ? ((u32)(n.c0 >> (16 * lb)) & 0xFFFFu) : 0xFFFFu;
+            u32 r = rb < 4 ? ((u32)(n.c1 >> (16 * rb)) & 0xFFFFu) : 0xFFFFu;
+            bump_counts<WIDE>(p, l | (r << 16), lb, rb);
+            if (TRACK) {
+                u64 mn = ~ord;
+                if (mn > n.nord) atomicMax(&p->nord, mn);
+            }
+            return;
+        }
+        n_conf++;                                       // occupied by another key: next slot (DBGgraph.cpp:201-204)
+        p++;
+        if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); return; }
+    }
+}
+
 template <bool WIDE, bool TRACK>
 struct InsertSink {
     static constexpr int RUN = G;
@@ -82,62 +123,11 @@ struct InsertSink {
         if (o.rb < 4 && __ldcg(t.polyA + 4 + o.rb) < 255) atomicAdd(t.polyA + 4 + o.rb, 1ULL);
     }
 
-    // thread_updatekmers (DBGgraph.cpp:167-205) for G occurrences at once, lock-free.  The G probe sequences
-    // advance in lock step: every round issues all pending claims (CAS), then all pending next-slot loads, so
-    // a round costs two memory round trips no matter how many of the G are still probing.  Only a NEW key
-    // needs an atomic with a return value (the claim); counting is fire-and-forget (RED).
     __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
     {
-        Node *p[G]; NodeRegs n[G]; bool act[G];
-        Node *const p_end = t.nodes + t.n_local;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            act[g] = g < nv && (o[g].klo | o[g].khi) != 0;
-            if (act[g]) {
-                u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                p[g] = t.nodes + (mod_P(h, t.P, t.M) - t.lo);
-                load_node(p[g], o[g].lb, o[g].rb, n[g]);
-            } else if (g < nv) {
-                polyA(o[g]);
-            }
-        }
-        for (;;) {
-            // (1) claims for the occurrences looking at an empty slot
-            u64 olo[G], ohi[G]; bool tried[G];
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                tried[g] = act[g] && (n[g].klo | (WIDE ? n[g].khi : 0ULL)) == 0;
-                if (tried[g]) {
-                    if (WIDE) cas128(p[g], o[g].klo, o[g].khi, olo[g], ohi[g]);
-                    else olo[g] = atomicCAS(&p[g]->klo, 0ULL, o[g].klo);
-                }
-            }
-            bool more = false;
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (!act[g]) continue;
-                if (tried[g]) {
-                    if ((olo[g] | (WIDE ? ohi[g] : 0ULL)) == 0) { n_new++; n[g].klo = o[g].klo; if (WIDE) n[g].khi = o[g].khi; }
-                    else { n[g].klo = olo[g]; if (WIDE) n[g].khi = ohi[g]; }   // somebody else got the slot
-                }
-                if (n[g].klo == o[g].klo && (!WIDE || n[g].khi == o[g].khi)) {
-                    // a stale (too small) loaded count only costs a redundant add; export clamps to 255
-                    if (o[g].lb < 4 && n[g].cl < 255u) atomicAdd(&p[g]->cnt[o[g].lb], 1u);
-                    if (o[g].rb < 4 && n[g].cr < 255u) atomicAdd(&p[g]->cnt[4 + o[g].rb], 1u);
-                    if (TRACK) {
-                        u64 mn = ~o[g].ord;
-                        if (mn > n[g].nord) atomicMax(&p[g]->nord, mn);
-                    }
-                    act[g] = false;
-                } else {
-                    // (2) occupied by another key: next slot (linear probing, DBGgraph.cpp:201-204)
-                    n_conf++;
-                    p[g]++;
-                    if (p[g] >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); act[g] = false; }
-                    else { load_node(p[g], o[g].lb, o[g].rb, n[g]); more = true; }
-                }
-            }
-            if (!more) break;
+        for (int g = 0; g < nv; g++) {
+            if ((o[g].klo | o[g].khi) == 0) polyA(o[g]);
+            else insert_one<WIDE, TRACK>(t, o[g].klo, o[g].khi, o[g].lb, o[g].rb, o[g].ord, n_new, n_conf);
         }
     }
 
@@ -484,75 +474,68 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sin
 }
 
 // ---------------------------------------------------------------------------------------------------
-// owner side of the exchange: insert received tuples
+// owner side: insert tuples (partitioned build and multi-GPU exchange)
 // ---------------------------------------------------------------------------------------------------
+// Persistent CTAs; CTA c takes tiles c, c+grid, ... of 256 tuples, ONE tuple per thread per tile: the kernel is
+// a memory-latency machine (a dependent tuple -> node -> [claim] chain per occurrence), so it keeps the code
+// and the register footprint small and the number of independent chains per SM at the hardware maximum.
+// Partitioned build: tuples are in bucket order, so all CTAs work inside a window of grid*256 tuples, i.e. one
+// or two 16-MB table slices that stay in the 126 MB L2.  Random first touches of a slice would still reach
+// DRAM one sector at a time; instead every tile also streams its proportional share of the NEXT slice into
+// L2 with coalesced prefetches.
+constexpr int INS_BLOCK = 256;
+constexpr int INS_CTAS = 6;      // per SM -> 48 warps
+
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
-                                                         InsertSink<WIDE, TRACK> sink, const u64 *__restrict__ boffs, u32 n_buckets,
-                                                         int shift)
+__global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
+                                                                       TableView t, const u64 *__restrict__ boffs, u32 n_buckets, int shift,
+                                                                       u64 *tile_counter)
 {
     if (n_ptr) n = *n_ptr;      // exact count produced on the device (partitioned build): no host round trip
-    sink.init(nullptr);
-    // Partitioned build: tuples are in bucket order.  Random first touches of a table slice would reach DRAM
-    // one 64-B burst at a time (~1 TB/s); instead the CTAs working on bucket b stream slice b+1 into L2 with
-    // coalesced prefetches, each CTA its share, so the inserts of the next bucket find their lines on chip.
-    if (boffs != nullptr && (u64)blockIdx.x * BLOCK * G < n) {
-        const u64 first = (u64)blockIdx.x * BLOCK * G;
-        u32 lo = 0, hi = n_buckets;                 // largest b with boffs[b] <= first
-        while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(boffs + mid) <= first) lo = mid; else hi = mid; }
-        const u32 b = lo;
-        if (b + 1 < n_buckets) {
-            const u64 b0 = __ldg(boffs + b), b1 = __ldg(boffs + b + 1);
-            const u64 ctas = (b1 - b0 + (u64)BLOCK * G - 1) / ((u64)BLOCK * G);     // CTAs that start inside bucket b
-            const u64 k = (first - b0) / ((u64)BLOCK * G);
-            const u64 slice_lo = (u64)(b + 1) << shift;
-            u64 slice_n = (u64)1 << shift;
-            if (slice_lo + slice_n > sink.t.n_local) slice_n = sink.t.n_local - slice_lo;
-            const u64 lines = slice_n * sizeof(Node) / 128;                        // 128-B L2 lines in the slice
-            const u64 l0 = lines * k / ctas, l1 = lines * (k + 1) / ctas;
-            const char *basep = reinterpret_cast<const char *>(sink.t.nodes + slice_lo);
-            for (u64 l = l0 + threadIdx.x; l < l1; l += BLOCK)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
+    u32 n_new = 0, n_conf = 0;
+    u32 b = 0;                  // current bucket of this CTA's tile (monotone)
+    u64 b0 = 0, b1 = 0;
+    if (boffs) { b0 = __ldg(boffs); b1 = __ldg(boffs + 1); }
+    __shared__ u64 s_tile;
+    // tiles are handed out by a global counter, so at any moment the resident CTAs hold the NEXT gridDim tiles of
+    // the bucket-ordered stream: the window of table slices they touch cannot drift apart (static round-robin
+    // let fast CTAs run buckets ahead and the slices fell out of L2)
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ULL);
+        __syncthreads();
+        const u64 tile = s_tile * INS_BLOCK;
+        __syncthreads();
+        if (tile >= n) break;
+        const u64 i = tile + threadIdx.x;
+        u64 klo = 0, khi = 0, meta = 0;
+        if (i < n) {
+            if (WIDE) { u64 z; ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * i, klo, khi, meta, z); }   // read once: evict first
+            else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + i); klo = x.x; meta = x.y; }
         }
-    }
-    // CTA i takes tuples [i*BLOCK*G, ...): CTAs are scheduled in index order, so the resident CTAs always work
-    // on a narrow window of the (bucket-ordered) tuple array -> the table slice they touch stays in L2
-    const u64 stride = (u64)gridDim.x * BLOCK * G;
-    for (u64 base0 = (u64)blockIdx.x * BLOCK * G; base0 < n; base0 += stride) {   // block-uniform trip count
-        const u64 base = base0 + (u64)threadIdx.x * G;
-        Occ occ[G]; int nv = 0;
-        if (!WIDE && base + G <= n) {
-            // narrow tuples are 16 B: one 256-bit streaming load brings two of them (read once: evict first)
-            static_assert(G % 2 == 0, "G must be even");
-#pragma unroll
-            for (int g = 0; g < G; g += 2) {
-                u64 k0, m0, k1, m1;
-                ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + base + g, k0, m0, k1, m1);
-                occ[g].klo = k0; occ[g].khi = 0; occ[g].lb = (u32)(m0 & 15); occ[g].rb = (u32)((m0 >> 4) & 15); occ[g].ord = m0 >> 8;
-                occ[g + 1].klo = k1; occ[g + 1].khi = 0; occ[g + 1].lb = (u32)(m1 & 15); occ[g + 1].rb = (u32)((m1 >> 4) & 15); occ[g + 1].ord = m1 >> 8;
-            }
-            nv = G;
-        } else {
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            if (base + g < n) {
-                u64 klo, khi = 0, meta;
-                if (WIDE) {
-                    u64 z;
-                    ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * (base + g), klo, khi, meta, z);
-                } else {
-                    ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + base + g);
-                    klo = x.x; meta = x.y;
-                }
-                occ[g].klo = klo; occ[g].khi = khi; occ[g].lb = (u32)(meta & 15); occ[g].rb = (u32)((meta >> 4) & 15);
-                occ[g].ord = meta >> 8;
-                nv = g + 1;
+        if (boffs) {
+            while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
+            if (b + 1 < n_buckets && b1 > b0) {
+                const u64 slice_lo = (u64)(b + 1) << shift;
+                u64 slice_n = (u64)1 << shift;
+                if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
+                const u64 lines = slice_n * sizeof(NodeT<WIDE>) / 128;                 // 128-B L2 lines in the next slice
+                const u64 span = b1 - b0;
+                const u64 t0 = tile - b0, t1 = (t0 + INS_BLOCK < span) ? t0 + INS_BLOCK : span;
+                const u64 l0 = lines * t0 / span, l1 = lines * t1 / span;      // lines <= 2^17: no overflow
+                const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + slice_lo);
+                for (u64 l = l0 + threadIdx.x; l < l1; l += INS_BLOCK)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
             }
         }
-        }
-        sink.consume(occ, nv);
+        if (i < n)
+            insert_one<WIDE, TRACK>(t, klo, khi, (u32)(meta & 15), (u32)((meta >> 4) & 15), meta >> 8, n_new, n_conf);
     }
-    sink.finish();   // occurrences were already counted where the tuples were extracted
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { n_new += __shfl_xor_sync(0xffffffffu, n_new, s); n_conf += __shfl_xor_sync(0xffffffffu, n_conf, s); }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_new) atomicAdd(t.counters + CNT_NEW, (u64)n_new);
+        if (n_conf) atomicAdd(t.counters + CNT_CONFLICT, (u64)n_conf);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -562,14 +545,16 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_insert_tuples(const u64 *__
 // atomicMin on the ordinal builds it in any execution order.  owner[] holds the ordinal per slot.
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, bool TRACK>
-__global__ void k_layout_insert(const Node *__restrict__ nodes, u64 n_local, u64 lo_slot, u64 *owner, u64 P, u64 M)
+__global__ void k_layout_insert(const NodeT<WIDE> *__restrict__ nodes, u64 n_local, u64 lo_slot, u64 *owner, u64 P, u64 M)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
-        ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2 *>(nodes + i));
-        u64 klo = kk.x, khi = WIDE ? kk.y : 0;
+        NodeRegs n;
+        if (WIDE) { u64 pad; ld256_cg(nodes + i, n.klo, n.khi, n.nord, pad); }
+        else { ulonglong2 kk = __ldcg(reinterpret_cast<const ulonglong2 *>(nodes + i)); n.klo = kk.x; n.nord = kk.y; n.khi = 0; }
+        u64 klo = n.klo, khi = n.khi;
         if ((klo | khi) == 0) continue;
-        u64 cur = TRACK ? ~__ldg(&nodes[i].nord) : (lo_slot + i);
+        u64 cur = TRACK ? ~n.nord : (lo_slot + i);
         u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
         u64 s = mod_P(h, P, M);
         for (;;) {
@@ -582,18 +567,17 @@ __global__ void k_layout_insert(const Node *__restrict__ nodes, u64 n_local, u64
 }
 
 template <bool WIDE, bool TRACK>
-__global__ void k_layout_place(const Node *__restrict__ nodes, u64 n_local, u64 lo_slot, const u64 *__restrict__ owner,
+__global__ void k_layout_place(const NodeT<WIDE> *__restrict__ nodes, u64 n_local, u64 lo_slot, const u64 *__restrict__ owner,
                                u64 P, u64 M, void *out, u32 *nul32)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
-        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(nodes + i);
-        ulonglong2 ka = __ldg(q);
-        u64 klo = ka.x, khi = WIDE ? ka.y : 0;
+        NodeRegs n;
+        load_node(nodes + i, n);
+        u64 klo = n.klo, khi = n.khi;
         if ((klo | khi) == 0) continue;
-        uint4 cl = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 2), cr = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 3);
-        u64 links = (u64)pack_link(cl) | ((u64)pack_link(cr) << 32);
-        u64 pri = TRACK ? ~__ldg(&nodes[i].nord) : (lo_slot + i);
+        u64 links = (u64)pack_link(n.c0) | ((u64)pack_link(n.c1) << 32);
+        u64 pri = TRACK ? ~n.nord : (lo_slot + i);
         u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
         u64 s = mod_P(h, P, M);
         while (__ldg(owner + s) != pri) s = (s + 1 == P) ? 0 : s + 1;
@@ -871,15 +855,16 @@ __global__ void __launch_bounds__(256) k_compact_nodes(const void *__restrict__ 
 
 // unordered dump of a shard's build table (multi-GPU: every rank hands its nodes to whoever merges them)
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_dump_shard(const Node *__restrict__ nodes, u64 n_local, u64 cap, u64 *cursor,
+__global__ void __launch_bounds__(256) k_dump_shard(const NodeT<WIDE> *__restrict__ nodes, u64 n_local, u64 cap, u64 *cursor,
                                                     u64 *klo_out, u64 *khi_out, u32 *l_out, u32 *r_out, u64 *ord_out)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n_local; i0 += stride) {
         u64 i = i0 + threadIdx.x;
         bool keep = false;
-        u64 klo = 0, khi = 0, nord = 0, pad;
-        if (i < n_local) { ld256_cg(nodes + i, klo, khi, nord, pad); keep = (klo | (WIDE ? khi : 0ULL)) != 0; }
+        NodeRegs n; n.klo = 0; n.khi = 0; n.nord = 0; n.c0 = 0; n.c1 = 0;
+        if (i < n_local) { load_node(nodes + i, n); keep = (n.klo | n.khi) != 0; }
+        const u64 klo = n.klo, khi = n.khi, nord = n.nord;
         u32 bal = __ballot_sync(0xffffffffu, keep);
         u64 base = 0;
         if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(cursor, (u64)__popc(bal));
@@ -887,11 +872,10 @@ __global__ void __launch_bounds__(256) k_dump_shard(const Node *__restrict__ nod
         if (keep) {
             u64 pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
             if (pos < cap) {
-                uint4 cl = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 2), cr = __ldg(reinterpret_cast<const uint4 *>(nodes + i) + 3);
                 if (klo_out) klo_out[pos] = klo;
                 if (khi_out) khi_out[pos] = WIDE ? khi : 0;
-                if (l_out) l_out[pos] = pack_link(cl);
-                if (r_out) r_out[pos] = pack_link(cr);
+                if (l_out) l_out[pos] = pack_link(n.c0);
+                if (r_out) r_out[pos] = pack_link(n.c1);
                 if (ord_out) ord_out[pos] = ~nord;
             }
         }
@@ -911,28 +895,40 @@ __device__ __forceinline__ u64 splitmix(u64 z)
 
 struct __align__(32) Rec32 { u64 a, b, links, d; };
 
+// MODE 0: 32-B load + store, 1: 32-B load + 64-bit CAS, 2: u32 RED, 3: f16x8 vector RED, 4: 32-B load only,
+// 5: 32-B load then f16x8 RED on the same sector (the insert kernel's hit path)
 template <int MODE>
-__global__ void __launch_bounds__(256) k_random_rmw(Rec32 *tab, u64 n_nodes, u64 n_ops, u64 seed)
+__global__ void __launch_bounds__(256) k_random_rmw(Rec32 *tab, u64 n_nodes, u64 n_ops, u64 seed, u64 *sink)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x * G;
+    u64 acc = 0;
     for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * G; base < n_ops; base += stride) {
         Rec32 *p[G]; u64 links[G];
 #pragma unroll
         for (int g = 0; g < G; g++) {
             u64 h = splitmix(seed + base + g);
             p[g] = tab + __umul64hi(h, n_nodes);
-            ulonglong2 x = __ldcg(reinterpret_cast<const ulonglong2 *>(p[g]));
-            ulonglong2 y = __ldcg(reinterpret_cast<const ulonglong2 *>(p[g]) + 1);
-            links[g] = y.x + (x.x & 1);
+            links[g] = 0;
+            if (MODE == 0 || MODE == 1 || MODE == 4 || MODE == 5) {
+                u64 a, b, c, d;
+                ld256_cg(p[g], a, b, c, d);
+                links[g] = c + (a & 1) + (b & 1) + (d & 1);
+            }
         }
 #pragma unroll
         for (int g = 0; g < G; g++) {
             if (base + g < n_ops) {
                 if (MODE == 0) p[g]->links = links[g] + 1;
-                else atomicCAS(&p[g]->links, links[g], links[g] + 1);
+                else if (MODE == 1) atomicCAS(&p[g]->links, links[g], links[g] + 1);
+                else if (MODE == 2) atomicAdd(reinterpret_cast<u32 *>(&p[g]->links), 1u);
+                else if (MODE == 3 || MODE == 5) {
+                    u32 one = HALF_ONE + (u32)(links[g] >> 63);
+                    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(&p[g]->links), "r"(one), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                } else acc += links[g];
             }
         }
     }
+    if (MODE == 4 && acc == 0x123456789ULL) *sink = acc;
 }
 
 }  // namespace dbg

@@ -24,6 +24,16 @@ NODE32 = np.dtype([("kmer", "<u8"), ("kmer_hi", "<u8"), ("l_link", "<u4"), ("r_l
 UINT64_MAX = (1 << 64) - 1
 
 
+CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the C ABI reads a NULL stream as "the context's own stream"
+
+
+def torch_stream_handle(device=None) -> int:
+    """cudaStream_t of torch's current stream as an int the C ABI accepts (the default stream's handle is 0,
+    which the ABI would read as NULL, so it is mapped to cudaStreamLegacy)"""
+    import torch
+    return int(torch.cuda.current_stream(device).cuda_stream) or CUDA_STREAM_LEGACY
+
+
 def init_slots_from_g(init_hash_size_g: float) -> int:
     """(uint64)(initHashSize * 1000000000), DBGgraph.cpp:381"""
     return int(float(init_hash_size_g) * 1000000000)
@@ -195,7 +205,7 @@ class DBGBuilder:
         ms = np.zeros(8, dtype=np.float32)
         capi.check(self.L.dbg_get_timings(self.h, ms.ctypes.data), "dbg_get_timings")
         return dict(clear_ms=float(ms[0]), build_ms=float(ms[1]), layout_ms=float(ms[2]), links_ms=float(ms[3]),
-                    h2d_ms=float(ms[4]), d2h_ms=float(ms[5]))
+                    h2d_ms=float(ms[4]), d2h_ms=float(ms[5]), insert_ms=float(ms[6]))
 
     @property
     def launches(self):

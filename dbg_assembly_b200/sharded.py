@@ -99,7 +99,8 @@ class ShardedBuilder:
     def add_reads_device(self, d_bases: torch.Tensor, d_offs: torch.Tensor, n_reads, first_base, total_bases,
                          first_read_index, n_occ_upper):
         """one block of this rank's reads, device resident.  n_occ_upper bounds its occurrence count."""
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        from .graph import torch_stream_handle
+        stream = torch_stream_handle(self.device)
         stride = self._buffers(n_occ_upper)
         self.b.extract_tuples_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
                                      self.n, self._send.data_ptr(), stride, self._counts.data_ptr(), stream=stream)

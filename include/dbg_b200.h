@@ -157,14 +157,16 @@ int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
 
 /* per-phase device time of the most recent calls, milliseconds (CUDA events on the ctx stream):
  * [0] table clear, [1] build kernels (sum over blocks), [2] layout+polyA (finalize), [3] links pass,
- * [4] H2D copies, [5] D2H export */
+ * [4] H2D copies, [5] D2H export, [6] the bucketed insert kernel alone (partitioned path; part of [1]) */
 int  dbg_get_timings(dbg_ctx *ctx, float ms[8]);
 /* number of kernel launches issued by this context so far */
 uint64_t dbg_launch_count(const dbg_ctx *ctx);
 /* re-zero the table and counters so the context can build again (bench steps) */
 int  dbg_reset(dbg_ctx *ctx);
 /* run all of this context's kernels, memsets and copies on a caller-owned cudaStream_t (e.g. torch's
- * current stream, so that CUDA events recorded there bracket the work); NULL restores the own stream */
+ * current stream, so that CUDA events recorded there bracket the work); NULL restores the own stream.
+ * NB a NULL stream argument anywhere in this API means "the context's stream": to name the legacy default
+ * stream pass cudaStreamLegacy. */
 int  dbg_set_stream(dbg_ctx *ctx, void *stream);
 
 /* ---- synthetic reads: counter-based, identical on host and device ----------------- */
@@ -182,7 +184,9 @@ int  dbg_synth_reads_device(const dbg_synth_params *p, uint64_t first_read, uint
 
 /* ---- roofline denominators measured on the spot (bench.py) --------------------------------------- */
 /* uniformly random 32-B sector read-modify-writes over `bytes` of device memory, `n_ops` operations;
- * returns milliseconds (CUDA events).  mode 0: plain load+store, 1: load + 64-bit atomicCAS. */
+ * returns milliseconds (CUDA events).  mode 0: 32-B load + store, 1: 32-B load + 64-bit atomicCAS,
+ * 2: u32 RED only, 3: f16x8 vector RED only, 4: 32-B load only, 5: 32-B load + f16x8 RED (the insert kernel's
+ * hit path).  With `bytes` below the L2 size the same call measures the on-chip (L2) transaction rates. */
 int  dbg_measure_random_rmw(int32_t device, uint64_t bytes, uint64_t n_ops, int32_t mode, float *ms);
 
 #ifdef __cplusplus

@@ -42,7 +42,8 @@ def main():
     d_offs = torch.arange(per + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
     sb = ShardedBuilder(K=a.K, max_read_len=L, init_slots=a.slots, device=local)
-    sb.b.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    from dbg_assembly_b200.graph import torch_stream_handle
+    sb.b.set_stream(torch_stream_handle(dev))
     # two blocks per rank, to exercise repeated exchanges
     half = per // 2
     occ_upper = per * L
