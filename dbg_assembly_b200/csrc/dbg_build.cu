@@ -139,7 +139,12 @@ struct dbg_ctx {
     uint64_t cap_tuples, part_blocks;
     // finalize / export
     bool finalized;
-    u64 *d_owner;
+    u64 *d_owner;                  // layout scratch (regions) or owner[P] (global method)
+    uint64_t owner_cap;
+    LayoutInfo *d_layout_info;
+    LayoutRegion *d_regions;
+    int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
+    uint32_t layout_regions;
     void *d_out;
     u32 *d_nul32;
     u64 polyA_links;
@@ -177,7 +182,8 @@ static int ev_begin(dbg_ctx *c, cudaStream_t s, EvPair *p)
 
 static void free_finalize_buffers(dbg_ctx *c)
 {
-    cudaFree(c->d_owner); cudaFree(c->d_out); cudaFree(c->d_nul32);
+    cudaFree(c->d_owner); cudaFree(c->d_out); cudaFree(c->d_nul32); cudaFree(c->d_layout_info); cudaFree(c->d_regions);
+    c->owner_cap = 0; c->d_layout_info = nullptr; c->d_regions = nullptr;
     cudaFree(c->d_klink); cudaFree(c->d_del32); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offs); cudaFree(c->d_small);
     c->d_owner = nullptr; c->d_out = nullptr; c->d_nul32 = nullptr;
     c->d_klink = nullptr; c->d_del32 = nullptr; c->d_tile_counts = nullptr; c->d_tile_offs = nullptr; c->d_small = nullptr;
@@ -261,6 +267,8 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
     if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->layout_mode = 0;
+    if (const char *e = getenv("DBG_B200_LAYOUT")) c->layout_mode = strcmp(e, "global") == 0 ? 1 : 0;
     c->part_mode = 2;
     if (const char *e = getenv("DBG_B200_PARTITION")) c->part_mode = atoi(e) == 0 ? 0 : (atoi(e) == 1 ? 1 : 2);
     // one bucket = a table slice of 16 MB (2^19 nodes of 32 B, 2^18 of 64 B): the slice in use, the one being
@@ -657,17 +665,72 @@ static int read_counters(dbg_ctx *c, u64 *cnt)
     return DBG_OK;
 }
 
+static const uint64_t SCRATCH_CAP = 16ull << 20;    // entries of the region scratch (long clusters + wrap region)
+
+// global method (fallback): atomicMin priority probing over the whole table, needs owner[P]
 template <bool WIDE, bool TRACK>
-static int run_layout(dbg_ctx *c)
+static int run_layout_global(dbg_ctx *c)
 {
-    unsigned grid = 148 * 16;
+    if (c->owner_cap < c->P) {
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(c->d_owner); c->d_owner = nullptr; c->owner_cap = 0;
+        CU_TRY(cudaMalloc(&c->d_owner, c->P * sizeof(u64)));
+        c->owner_cap = c->P;
+    }
+    size_t nb = (size_t)node_bytes(c);
+    CU_TRY(cudaMemsetAsync(c->d_owner, 0xFF, c->P * sizeof(u64), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_out, 0, c->P * nb, c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
+    unsigned grid = c->n_sms * 16;
     k_layout_insert<WIDE, TRACK><<<grid, 256, 0, c->stream>>>((const NodeT<WIDE> *)c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M);
     CU_TRY(cudaGetLastError());
     k_layout_place<WIDE, TRACK><<<grid, 256, 0, c->stream>>>((const NodeT<WIDE> *)c->d_nodes, c->n_local, c->shard_lo, c->d_owner, c->P, c->M, c->d_out, c->d_nul32);
     CU_TRY(cudaGetLastError());
-    k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->d_owner, c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
+    c->launches += 2;
+    return DBG_OK;
+}
+
+// cluster-local method: one streaming pass, regions (long clusters, wrap-around) on a small scratch
+template <bool WIDE, bool TRACK>
+static int run_layout(dbg_ctx *c)
+{
+    const NodeT<WIDE> *nodes = (const NodeT<WIDE> *)c->d_nodes;
+    bool use_global = c->layout_mode == 1;
+    if (!use_global) {
+        if (c->owner_cap < SCRATCH_CAP) {
+            CU_TRY(cudaDeviceSynchronize());
+            cudaFree(c->d_owner); c->d_owner = nullptr; c->owner_cap = 0;
+            CU_TRY(cudaMalloc(&c->d_owner, SCRATCH_CAP * sizeof(u64)));
+            c->owner_cap = SCRATCH_CAP;
+        }
+        if (!c->d_layout_info) {
+            CU_TRY(cudaMalloc(&c->d_layout_info, sizeof(LayoutInfo)));
+            CU_TRY(cudaMalloc(&c->d_regions, (size_t)MAX_REGIONS * sizeof(LayoutRegion)));
+        }
+        CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
+        k_layout_wrapscan<WIDE><<<1, 32, 0, c->stream>>>(nodes, c->n_local, c->P, c->d_layout_info, c->d_regions, SCRATCH_CAP);
+        CU_TRY(cudaGetLastError());
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * 8, LT, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
+                                                                             c->d_regions, SCRATCH_CAP);
+        CU_TRY(cudaGetLastError());
+        k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
+                                                                            c->d_regions, c->d_owner);
+        CU_TRY(cudaGetLastError());
+        c->launches += 3;
+        LayoutInfo li;
+        CU_TRY(cudaMemcpyAsync(&li, c->d_layout_info, sizeof(li), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        c->layout_regions = li.n_regions;
+        if (li.overflow) use_global = true;      // very dense table: too many / too long clusters for the scratch
+    }
+    if (use_global) {
+        int rc = run_layout_global<WIDE, TRACK>(c);
+        if (rc) return rc;
+        c->layout_regions = UINT32_MAX;
+    }
+    k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
     CU_TRY(cudaGetLastError());
-    c->launches += 3;
+    c->launches++;
     return DBG_OK;
 }
 
@@ -685,17 +748,13 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
         if (c->n_shards <= 1) {
             if (cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
             size_t nb = (size_t)node_bytes(c);
-            if (!c->d_owner) {
-                CU_TRY(cudaMalloc(&c->d_owner, c->P * sizeof(u64)));
+            if (!c->d_out) {
                 CU_TRY(cudaMalloc(&c->d_out, c->P * nb));
                 CU_TRY(cudaMalloc(&c->d_nul32, nul_words(c->P) * sizeof(u32)));
             }
             EvPair e;
             rc = ev_begin(c, c->stream, &e);
             if (rc) return rc;
-            CU_TRY(cudaMemsetAsync(c->d_owner, 0xFF, c->P * sizeof(u64), c->stream));
-            CU_TRY(cudaMemsetAsync(c->d_out, 0, c->P * nb, c->stream));
-            CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
             if (c->wide) rc = c->track ? run_layout<true, true>(c) : run_layout<true, false>(c);
             else rc = c->track ? run_layout<false, true>(c) : run_layout<false, false>(c);
             if (rc) return rc;

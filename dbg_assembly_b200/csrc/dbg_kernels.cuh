@@ -592,9 +592,221 @@ __global__ void k_layout_place(const NodeT<WIDE> *__restrict__ nodes, u64 n_loca
     }
 }
 
+// ---- cluster-local layout (the fast path) ------------------------------------------------------------
+// Linear probing never moves a key across an empty slot, and the set of occupied slots does not depend on
+// insertion order.  So the reference layout can be rebuilt one CLUSTER (maximal run of occupied slots) at a
+// time: replay the cluster's keys in first-occurrence order, each into the first free slot at or after its
+// home.  One streaming pass over the table, no atomics, no scratch: the thread that sees a cluster start
+// walks it (clusters average 2-3 slots at load 0.5), simulates the replay on a 64-bit occupancy mask and
+// writes the 16-B image nodes; clusters longer than 64 slots and the region where the table wraps around
+// go to k_layout_regions, which runs the atomicMin priority probing on a per-region scratch.
+struct LayoutInfo {
+    u64 e;              // first slot of the cluster that runs over the end of the table (== P: none)
+    u64 g;              // slots [0, g) take part in the wrap-around region
+    u64 mt;             // occupied slots in the overflow margin (>= P)
+    u64 scratch_used;   // entries of the region scratch handed out
+    u32 n_regions;
+    u32 overflow;       // region list / scratch exhausted: host falls back to the global method
+};
+struct LayoutRegion { u64 a, n, off; u64 wrap; };
+constexpr u32 MAX_REGIONS = 1u << 20;
+
+template <bool WIDE>
+__device__ __forceinline__ bool slot_occupied(const NodeT<WIDE> *nodes, u64 i)
+{
+    if (WIDE) { ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2 *>(nodes + i)); return (k.x | k.y) != 0; }
+    return __ldcg(&nodes[i].klo) != 0;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void write_image(void *out, u64 slot, u64 klo, u64 khi, u64 links)
+{
+    if (WIDE) {
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + 2 * slot;
+        dst[0] = make_ulonglong2(klo, khi);
+        dst[1] = make_ulonglong2(links, 0ULL);
+    } else {
+        reinterpret_cast<ulonglong2 *>(out)[slot] = make_ulonglong2(klo, links);
+    }
+}
+
+// one thread: where does the table wrap?  (tiny sequential scans around slot P-1 and slot 0)
+template <bool WIDE>
+__global__ void k_layout_wrapscan(const NodeT<WIDE> *__restrict__ nodes, u64 n_local, u64 P, LayoutInfo *info, LayoutRegion *regions,
+                                  u64 scratch_cap)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    LayoutInfo li; li.e = P; li.g = 0; li.mt = 0; li.scratch_used = 0; li.n_regions = 0; li.overflow = 0;
+    u64 mt = 0;
+    while (P + mt < n_local && slot_occupied<WIDE>(nodes, P + mt)) mt++;
+    if (mt > 0) {
+        u64 e = P - 1;                       // slot P-1 is occupied (a probe chain ran through it)
+        while (e > 0 && slot_occupied<WIDE>(nodes, e - 1)) e--;
+        u64 need = mt, g = 0;
+        while (need > 0 && g < e) { if (!slot_occupied<WIDE>(nodes, g)) need--; g++; }
+        li.e = e; li.g = g; li.mt = mt;
+        u64 R = (P - e) + g;
+        if (need > 0 || R > scratch_cap) li.overflow = 1;
+        else { regions[0].a = e; regions[0].n = R; regions[0].off = 0; regions[0].wrap = 1; li.n_regions = 1; li.scratch_used = R; }
+    }
+    *info = li;
+}
+
+constexpr int LT = 256;     // slots per layout tile (one CTA round)
+constexpr int LH = 64;      // halo: the longest cluster handled in shared memory
+constexpr int LW = (LT + LH) / 32;
+
+// cluster [start, end) around occupied position k of the tile's occupancy words (positions 0 .. LT+LH-1);
+// start = -1: the cluster began before the tile; end = LT+LH+1: it runs past the window
+__device__ __forceinline__ void cluster_bounds(const u32 *W, int k, bool prev_occ, int &start, int &end)
+{
+    int w = k >> 5;
+    u32 m = ~W[w] & ((1u << (k & 31)) - 1u);
+    start = -2;
+    for (;;) {
+        if (m) { start = (w << 5) + 32 - __clz(m); break; }
+        if (--w < 0) break;
+        m = ~W[w];
+    }
+    if (start == -2) start = prev_occ ? -1 : 0;
+    w = k >> 5;
+    m = ~W[w] & ~((2u << (k & 31)) - 1u);            // zeros above k in its word
+    end = LT + LH + 1;
+    for (;;) {
+        if (m) { end = (w << 5) + __ffs(m) - 1; break; }
+        if (++w >= LW) break;
+        m = ~W[w];
+    }
+}
+
+template <bool WIDE, bool TRACK>
+__global__ void __launch_bounds__(LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+                                                        LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
+{
+    // the tile's nodes, loaded coalesced and digested in parallel: key, ordinal, packed link words, home slot;
+    // then EVERY occupied slot's thread replays its own key with priority probing (atomicMin on the ordinal) in
+    // shared memory -- the same algorithm as the global method, but on chip, per tile, with no idle lanes
+    __shared__ u64 s_klo[LT + LH], s_khi[WIDE ? LT + LH : 1], s_ord[LT + LH], s_links[LT + LH], s_owner[LT + LH];
+    __shared__ u32 s_home[LT + LH];     // home - tile start (>= 0 for every cluster that starts in the tile)
+    __shared__ u32 s_W[LW];             // occupancy bitmap of the window
+    __shared__ int s_prev;
+    const u64 e_skip = info->e, g_skip = info->g;
+    const int t = threadIdx.x;
+    const u32 lane = t & 31;
+    for (u64 i0 = (u64)blockIdx.x * LT; i0 < P; i0 += (u64)gridDim.x * LT) {
+        for (int k = t; k < LT + LH; k += LT) {          // k = t, and t + LT for the first LH threads (warp uniform)
+            const u64 s = i0 + k;
+            NodeRegs nd; nd.klo = 0; nd.khi = 0; nd.nord = 0; nd.c0 = 0; nd.c1 = 0;
+            if (s < P) load_node(nodes + s, nd);
+            const bool o = (nd.klo | nd.khi) != 0;
+            s_klo[k] = nd.klo; if (WIDE) s_khi[k] = nd.khi;
+            s_owner[k] = EMPTY_PRI;
+            if (o) {
+                u64 h = WIDE ? hash_code_wide(nd.klo, nd.khi) : hash_code(nd.klo);
+                s_home[k] = (u32)(mod_P(h, P, M) - i0);
+                s_ord[k] = TRACK ? ~nd.nord : s;
+                s_links[k] = (u64)pack_link(nd.c0) | ((u64)pack_link(nd.c1) << 32);
+            }
+            const u32 bal = __ballot_sync(0xffffffffu, o);
+            if (lane == 0) {
+                s_W[k >> 5] = bal;
+                if (k < LT && s < P) nul32[s >> 5] = __byte_perm(__brev(bal), 0, 0x0123);   // MSB-first bitmap word of 32 slots
+            }
+            if (k < LT && s < P && !o) write_image<WIDE>(out, s, 0, 0, 0);
+        }
+        if (t == 0) s_prev = (i0 > 0) && slot_occupied<WIDE>(nodes, i0 - 1);
+        __syncthreads();
+        bool mine[2] = {false, false};
+        for (int r = 0, k = t; k < LT + LH; k += LT, r++) {
+            if (!((s_W[k >> 5] >> (k & 31)) & 1u)) continue;
+            int start, end;
+            cluster_bounds(s_W, k, s_prev != 0, start, end);
+            if (start < 0 || start >= LT) continue;                   // belongs to the previous / next tile
+            const u64 cs = i0 + start;
+            if (cs < g_skip || cs == e_skip) continue;                // wrap-around region: k_layout_regions
+            if (end > LT + LH || end - start > LH) {
+                // longer than the shared-memory window: measure it in global memory, hand it to k_layout_regions
+                if (k == start) {
+                    u64 len = (u64)(end > LT + LH ? LT + LH - start : end - start);
+                    while (cs + len < P && slot_occupied<WIDE>(nodes, cs + len)) len++;
+                    u32 rr = atomicAdd(&info->n_regions, 1u);
+                    u64 off = atomicAdd(&info->scratch_used, len);
+                    if (rr >= MAX_REGIONS || off + len > scratch_cap) info->overflow = 1;
+                    else { regions[rr].a = cs; regions[rr].n = len; regions[rr].off = off; regions[rr].wrap = 0; }
+                }
+                continue;
+            }
+            mine[r] = true;
+            u64 cur = s_ord[k];
+            u32 pos = s_home[k];
+            for (;;) {
+                u64 old = atomicMin(&s_owner[pos], cur);
+                if (old == EMPTY_PRI) break;
+                if (old > cur) cur = old;      // we took the slot; carry the displaced key onwards
+                pos++;
+            }
+        }
+        __syncthreads();
+        for (int r = 0, k = t; k < LT + LH; k += LT, r++) {
+            if (!mine[r]) continue;
+            const u64 pri = s_ord[k];
+            u32 pos = s_home[k];
+            while (s_owner[pos] != pri) pos++;
+            write_image<WIDE>(out, i0 + pos, s_klo[k], WIDE ? s_khi[k] : 0ULL, s_links[k]);
+        }
+        __syncthreads();
+    }
+}
+
+// long clusters and the wrap-around region: priority probing (atomicMin on the ordinal) inside a private scratch
+template <bool WIDE, bool TRACK>
+__global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+                                                        const LayoutInfo *__restrict__ info, const LayoutRegion *__restrict__ regions, u64 *scratch)
+{
+    if (info->overflow) return;
+    const u32 n_regions = info->n_regions < MAX_REGIONS ? info->n_regions : MAX_REGIONS;
+    const u64 e = info->e, mt = info->mt, g = info->g;
+    for (u32 r = blockIdx.x; r < n_regions; r += gridDim.x) {
+        const LayoutRegion rg = regions[r];
+        u64 *sc = scratch + rg.off;
+        const u64 tail = rg.wrap ? (P - e) + mt : 0;          // wrap: sources are A-slots [e, P+mt) then [0, g)
+        const u64 nsrc = rg.wrap ? tail + g : rg.n;
+        for (u64 k = threadIdx.x; k < rg.n; k += blockDim.x) sc[k] = EMPTY_PRI;
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+            for (u64 k = threadIdx.x; k < nsrc; k += blockDim.x) {
+                const u64 s = rg.wrap ? (k < tail ? e + k : k - tail) : rg.a + k;
+                NodeRegs nd;
+                load_node(nodes + s, nd);
+                if ((nd.klo | nd.khi) == 0) continue;
+                u64 h = WIDE ? hash_code_wide(nd.klo, nd.khi) : hash_code(nd.klo);
+                u64 home = mod_P(h, P, M);
+                u64 pos = rg.wrap ? (home >= e ? home - e : home + (P - e)) : home - rg.a;
+                const u64 pri = TRACK ? ~nd.nord : s;
+                if (pass == 0) {
+                    u64 cur = pri;
+                    for (;;) {
+                        u64 old = atomicMin(sc + pos, cur);
+                        if (old == EMPTY_PRI) break;
+                        if (old > cur) cur = old;      // we took the slot; carry the displaced key onwards
+                        pos++;
+                    }
+                } else {
+                    while (__ldcg(sc + pos) != pri) pos++;
+                    u64 slot = rg.wrap ? (e + pos >= P ? e + pos - P : e + pos) : rg.a + pos;
+                    u64 links = (u64)pack_link(nd.c0) | ((u64)pack_link(nd.c1) << 32);
+                    write_image<WIDE>(out, slot, nd.klo, nd.khi, links);
+                    atomicOr(nul32 + (slot >> 5), flag_mask(slot));
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // add_node_to_kmerset(kset, PolyA) (kmerSet.cpp:253-273, DBGgraph.cpp:418): last, always, first null slot
 template <bool WIDE>
-__global__ void k_polyA_insert(u64 *owner, u64 P, u64 M, const u64 *__restrict__ polyA, void *out, u32 *nul32, u64 *links_out)
+__global__ void k_polyA_insert(u64 P, u64 M, const u64 *__restrict__ polyA, void *out, u32 *nul32, u64 *links_out)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     u32 l = 0, r = 0;
@@ -606,15 +818,8 @@ __global__ void k_polyA_insert(u64 *owner, u64 P, u64 M, const u64 *__restrict__
     u64 links = (u64)l | ((u64)r << 32);
     *links_out = links;
     u64 s = mod_P(WIDE ? hash_code_wide(0, 0) : hash_code(0), P, M);
-    while (owner[s] != EMPTY_PRI) s = (s + 1 == P) ? 0 : s + 1;
-    owner[s] = POLYA_PRI;
-    if (WIDE) {
-        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out) + 2 * s;
-        dst[0] = make_ulonglong2(0ULL, 0ULL);
-        dst[1] = make_ulonglong2(links, 0ULL);
-    } else {
-        reinterpret_cast<ulonglong2 *>(out)[s] = make_ulonglong2(0ULL, links);
-    }
+    while (nul32[s >> 5] & flag_mask(s)) s = (s + 1 == P) ? 0 : s + 1;
+    write_image<WIDE>(out, s, 0, 0, links);
     nul32[s >> 5] |= flag_mask(s);
 }
 

@@ -90,6 +90,36 @@ def test_golden_reference_tables(dbg, name, force_wide):
         assert not d["kmer_hi"].any()
 
 
+@pytest.mark.parametrize("name", ["ragged_k31", "saturate_k21", "tiny_k3", "contig_k31"])
+def test_golden_tables_global_layout_method(dbg, name, monkeypatch):
+    """the fallback layout method (atomicMin priority probing over the whole table) gives the same image as
+    the default cluster-local method"""
+    monkeypatch.setenv("DBG_B200_LAYOUT", "global")
+    g = load_golden(name)
+    st, arr, nul = gpu_build(dbg, g["files"], g["K"], g["R"], g["init_slots"], g["load"])
+    d = image_to_dump(arr, nul, g["size"])
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], g[k]), k
+
+
+def test_dense_table_long_clusters_and_wraparound(dbg, oracle_mod):
+    """load factor 0.97: clusters of hundreds of slots (region path / global fallback) and a probe chain that
+    runs over the end of the table into the first slots"""
+    reads = random_reads(81, 1500, 60, 100, genome_len=20000, err=0.03)
+    files = [reads_to_arrays(reads)]
+    probe = oracle_build(oracle_mod, files, 31, 100, 2_000_000)
+    n_nodes = probe.count
+    probe.close()
+    for load in (0.97, 0.999):
+        init_slots = int(n_nodes / load)
+        o = oracle_build(oracle_mod, files, 31, 100, init_slots)
+        st, arr, nul = gpu_build(dbg, files, 31, 100, init_slots)
+        d, e = image_to_dump(arr, nul, o.size), o.dump()
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(d[k], e[k]), (load, k)
+        o.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # seeded random inputs against the oracle
 # ---------------------------------------------------------------------------------------------------
