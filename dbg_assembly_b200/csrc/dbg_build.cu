@@ -135,8 +135,9 @@ struct dbg_ctx {
     int part_mode;                 // 0 never, 1 always, 2 auto
     int part_shift;                // bucket = local slot >> part_shift
     uint32_t n_buckets;
-    u64 *d_bcounts, *d_boffs, *d_bcursor, *d_tuples;
-    uint64_t cap_tuples, part_blocks;
+    u64 *d_boffs, *d_tuples, *d_tile_sums;
+    u32 *d_matrix;
+    uint64_t cap_tuples, cap_matrix, part_blocks;
     // finalize / export
     bool finalized;
     u64 *d_owner;                  // layout scratch (regions) or owner[P] (global method)
@@ -202,7 +203,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
-    cudaFree(c->d_offs_stage); cudaFree(c->d_bcounts); cudaFree(c->d_boffs); cudaFree(c->d_bcursor); cudaFree(c->d_tuples);
+    cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -285,9 +286,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * build_node_bytes(c)));
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
-    CU_TRY(cudaMalloc(&c->d_bcounts, (size_t)c->n_buckets * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_boffs, ((size_t)c->n_buckets + 1) * sizeof(u64)));
-    CU_TRY(cudaMalloc(&c->d_bcursor, (size_t)c->n_buckets * sizeof(u64)));
     return clear_table(c);
 }
 
@@ -321,7 +320,7 @@ static uint32_t stage_words_for(int R) { return (uint32_t)(((CB + ((R + 15) / 16
 static size_t build_smem(uint32_t stage_words, uint32_t n_buckets)
 {
     size_t words = (size_t)stage_words + MAXR + MAXR + 2;
-    if (n_buckets) words += 2 * (size_t)((n_buckets + 1) & ~1u) + 4 * (size_t)n_buckets;   // ping-pong hist (u32) + base (u64)
+    if (n_buckets) words += 2 * (size_t)n_buckets;   // hist + base (u32 each)
     return words * sizeof(u32);
 }
 
@@ -373,25 +372,31 @@ static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const 
 template <bool WIDE>
 static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t occ_upper, cudaStream_t s)
 {
-    CU_TRY(cudaMemsetAsync(c->d_bcounts, 0, c->n_buckets * sizeof(u64), s));
-    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.n_buckets = c->n_buckets;
-    cs.counts = c->d_bcounts; cs.cursor = nullptr; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
+    const uint32_t nb = c->n_buckets;
+    const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
+    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.n_buckets = nb;
+    cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
     a.count_stats = 0;
-    int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, c->n_buckets);
+    int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
     if (rc) return rc;
-    k_scan_buckets<<<1, 1024, 0, s>>>(c->d_bcounts, c->n_buckets, c->d_boffs, c->d_bcursor);
+    dim3 g1((unsigned)n_tiles, (nb + 255) / 256);
+    k_part_scan1<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums);
     CU_TRY(cudaGetLastError());
-    c->launches++;
-    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.n_buckets = c->n_buckets;
-    ss.counts = nullptr; ss.cursor = c->d_bcursor; ss.tuples = c->d_tuples; ss.hist = nullptr; ss.base = nullptr;
+    k_part_scan2<<<1, 1024, 0, s>>>(c->d_tile_sums, n_tiles, nb, c->d_boffs);
+    CU_TRY(cudaGetLastError());
+    k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_boffs);
+    CU_TRY(cudaGetLastError());
+    c->launches += 3;
+    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.n_buckets = nb;
+    ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
-    rc = launch_build<WIDE>(c, a, ss, n_chunks, s, c->n_buckets);
+    rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
     if (rc) return rc;
     EvPair ev;                       // the insert kernel alone (ms[6]): the roofline's dominant kernel
     rc = ev_begin(c, s, &ev);
     if (rc) return rc;
     ev.slot = 6;
-    rc = insert_any(c, c->d_tuples, occ_upper, c->d_boffs + c->n_buckets, s, true);
+    rc = insert_any(c, c->d_tuples, occ_upper, c->d_boffs + nb, s, true);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ev.b, s));
     c->build_ev.push_back(ev);
@@ -407,8 +412,24 @@ static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
     return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * build_node_bytes(c);
 }
 
+static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks)
+{
+    uint64_t cells = n_chunks * (uint64_t)c->n_buckets;
+    if (cells > (1ull << 28)) return DBG_ERR_NOMEM;          // > 1 GiB of offsets: not worth it, use the direct path
+    if (cells <= c->cap_matrix) return DBG_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
+    c->d_matrix = nullptr; c->d_tile_sums = nullptr; c->cap_matrix = 0;
+    uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
+    if (cudaMalloc(&c->d_matrix, (cells + 16) * sizeof(u32)) != cudaSuccess) { cudaGetLastError(); return DBG_ERR_NOMEM; }
+    if (cudaMalloc(&c->d_tile_sums, (n_tiles + 1) * c->n_buckets * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); cudaFree(c->d_matrix); c->d_matrix = nullptr; return DBG_ERR_NOMEM; }
+    c->cap_matrix = cells;
+    return DBG_OK;
+}
+
 static int ensure_tuples(dbg_ctx *c, uint64_t need)
 {
+    if (need >= (1ull << 32)) return DBG_ERR_NOMEM;          // write offsets are 32-bit
     if (need <= c->cap_tuples) return DBG_OK;
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -436,7 +457,7 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     int rc = ensure_chunks(c, n_chunks);
     if (rc) return rc;
     bool part = n_parts == 0 && want_partition(c, total_bases);
-    if (part && ensure_tuples(c, total_bases) != DBG_OK) part = false;
+    if (part && (ensure_tuples(c, total_bases) != DBG_OK || ensure_matrix(c, n_chunks) != DBG_OK)) part = false;
 
     EvPair ev;
     rc = ev_begin(c, s, &ev);

@@ -202,64 +202,42 @@ struct BucketSink {
     }
 };
 
-// Radix partition by home-slot range (bucket = home >> shift), exact two-pass (count, scan, scatter): the
-// insert pass then walks the tuples bucket by bucket, so every bucket's slice of the table (<= ~32 MB)
+// Radix partition by home-slot range (bucket = home >> shift), exact and atomic-free in global memory:
+//   pass 1 (MODE 0)  every chunk CTA histograms its occurrences per bucket in shared memory and stores the row
+//                    M[chunk][bucket];
+//   k_part_scan*     column-wise exclusive scan turns M into the exact write offset of every (chunk, bucket);
+//   pass 2 (MODE 1)  the chunk CTA regenerates its occurrences and writes each tuple to
+//                    M[chunk][bucket] + (shared-memory rank): no global atomics, no barriers per round.
+// The insert pass then walks the tuples bucket by bucket, so every bucket's slice of the table (16 MB)
 // is pulled into the 126 MB L2 once, updated there and written back once, instead of one random DRAM
-// read-modify-write per occurrence.  MODE 0 = count, MODE 1 = scatter.
+// read-modify-write per occurrence.
 template <bool WIDE, int MODE>
 struct PartitionSink {
     static constexpr int RUN = G;
     TableView t;
     int shift;
     u32 n_buckets;
-    u64 *counts;       // MODE 0: per-bucket totals (global)
-    u64 *cursor;       // MODE 1: per-bucket running write position (starts at the exclusive scan)
+    u32 *matrix;       // [n_chunks][n_buckets]: counts after pass 1, write offsets after the scan
     u64 *tuples;
-    u32 *hist;         // shared: 2 x n_buckets (ping-pong)
-    u64 *base;         // shared: 2 x n_buckets (MODE 1)
-    // MODE 1 is software pipelined: round k's tuples are written during round k+1, after the barrier that
-    // publishes their reserved positions, so the reservation atomics' round trip hides behind extraction
-    u64 pklo[RUN], pkhi[WIDE ? RUN : 1], pmeta[RUN];
-    u32 pbkt[RUN], prank[RUN];
-    u32 parity;
-    bool has_prev;
-
-    __device__ __forceinline__ u32 nb2() const { return (n_buckets + 1) & ~1u; }
+    u32 *hist;         // shared: n_buckets running counts of this chunk
+    u32 *base;         // shared: n_buckets write offsets of this chunk (MODE 1)
 
     __device__ __forceinline__ void init(u32 *extra)
     {
         hist = extra;
-        base = reinterpret_cast<u64 *>(extra + 2 * nb2());
-        for (u32 b = threadIdx.x; b < 2 * nb2(); b += BLOCK) hist[b] = 0;
-        parity = 0; has_prev = false;
-        __syncthreads();
-    }
-
-    __device__ __forceinline__ void write_prev()
-    {
-        const u64 *bs = base + (size_t)(parity ^ 1) * n_buckets;
-#pragma unroll
-        for (int g = 0; g < RUN; g++) {
-            if (pbkt[g] != 0xffffffffu) {
-                u64 pos = bs[pbkt[g]] + prank[g];
-                if (WIDE) {
-                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
-                    dst[0] = make_ulonglong2(pklo[g], pkhi[WIDE ? g : 0]);
-                    dst[1] = make_ulonglong2(pmeta[g], 0ULL);
-                } else {
-                    reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(pklo[g], pmeta[g]);
-                }
-            }
+        base = extra + n_buckets;
+        const u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
+        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
+            hist[b] = 0;
+            if (MODE == 1) base[b] = row[b];
         }
+        __syncthreads();
     }
 
     __device__ __forceinline__ void consume(const Occ (&o)[RUN], int nv)
     {
-        u32 *h = hist + (size_t)parity * nb2();
-        u32 bkt[RUN], rank[RUN];
 #pragma unroll
         for (int g = 0; g < RUN; g++) {
-            bkt[g] = 0xffffffffu; rank[g] = 0;
             if (g < nv) {
                 if ((o[g].klo | o[g].khi) == 0) {
                     if (MODE == 1) {   // the k-mer-0 side node is accumulated once, in the scatter pass
@@ -268,67 +246,84 @@ struct PartitionSink {
                     }
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                    bkt[g] = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
-                    rank[g] = atomicAdd(&h[bkt[g]], 1u);
+                    u32 bkt = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
+                    u32 rank = atomicAdd(&hist[bkt], 1u);
+                    if (MODE == 1) {
+                        u64 pos = (u64)base[bkt] + rank;
+                        u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+                        if (WIDE) {
+                            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
+                            dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
+                            dst[1] = make_ulonglong2(meta, 0ULL);
+                        } else {
+                            reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(o[g].klo, meta);
+                        }
+                    }
                 }
             }
         }
-        if (MODE == 0) return;
-        __syncthreads();                 // round k counted; round k-1's reservations are visible
-        if (has_prev) write_prev();
-        u64 *bs = base + (size_t)parity * n_buckets;
-        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
-            u32 c = h[b];
-            if (c) { bs[b] = atomicAdd(cursor + b, (u64)c); h[b] = 0; }
-        }
-#pragma unroll
-        for (int g = 0; g < RUN; g++) {
-            pklo[g] = o[g].klo; if (WIDE) pkhi[g] = o[g].khi;
-            pmeta[g] = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
-            pbkt[g] = bkt[g]; prank[g] = rank[g];
-        }
-        has_prev = true;
-        parity ^= 1;
     }
 
     __device__ __forceinline__ void finish()
     {
-        __syncthreads();
         if (MODE == 0) {
-            for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
-                u32 c = hist[b];
-                if (c) atomicAdd(counts + b, (u64)c);
-            }
-        } else if (has_prev) {
-            write_prev();
+            __syncthreads();
+            u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
+            for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) row[b] = hist[b];
         }
     }
 };
 
-// exclusive scan of the bucket counts (one CTA); offs[n] = total; cursor = copy of offs for the scatter pass
-__global__ void __launch_bounds__(1024) k_scan_buckets(const u64 *__restrict__ counts, u32 n, u64 *offs, u64 *cursor)
+// column-wise exclusive scan of M[n_chunks][n_buckets] (+ per-bucket bases), three small kernels:
+//   1: tile sums  ts[tile][b] = sum of M[c][b] over the tile's chunks            grid (tiles, ceil(nb/256))
+//   2: per bucket: exclusive scan of ts over tiles, bucket totals -> boffs (exclusive over buckets), one CTA
+//   3: M[c][b] <- boffs[b] + ts_excl[tile][b] + running sum inside the tile       grid like 1
+constexpr int PT_CHUNKS = 128;     // chunks per scan tile
+
+__global__ void __launch_bounds__(256) k_part_scan1(const u32 *__restrict__ matrix, u64 n_chunks, u32 nb, u64 *__restrict__ ts)
+{
+    const u32 b = blockIdx.y * 256 + threadIdx.x;
+    if (b >= nb) return;
+    const u64 c0 = (u64)blockIdx.x * PT_CHUNKS, c1 = c0 + PT_CHUNKS < n_chunks ? c0 + PT_CHUNKS : n_chunks;
+    u64 sum = 0;
+    for (u64 c = c0; c < c1; c++) sum += matrix[c * nb + b];
+    ts[(u64)blockIdx.x * nb + b] = sum;
+}
+
+__global__ void __launch_bounds__(1024) k_part_scan2(u64 *ts, u64 n_tiles, u32 nb, u64 *boffs)
 {
     __shared__ u64 wsum[32];
     __shared__ u64 carry;
     const int tid = threadIdx.x;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (u32 b0 = 0; b0 < n; b0 += 1024) {
-        u32 b = b0 + tid;
-        u64 v = b < n ? counts[b] : 0, inc = v;
+    for (u32 b0 = 0; b0 < nb; b0 += 1024) {
+        const u32 b = b0 + tid;
+        u64 tot = 0;
+        if (b < nb)
+            for (u64 tl = 0; tl < n_tiles; tl++) { u64 v = ts[tl * nb + b]; ts[tl * nb + b] = tot; tot += v; }   // exclusive over tiles
+        u64 inc = tot;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) { u64 x = __shfl_up_sync(0xffffffffu, inc, s); if ((tid & 31) >= s) inc += x; }
         if ((tid & 31) == 31) wsum[tid >> 5] = inc;
         __syncthreads();
         u64 wb = 0;
         for (int w = 0; w < (tid >> 5); w++) wb += wsum[w];
-        u64 ex = carry + wb + inc - v;
-        if (b < n) { offs[b] = ex; cursor[b] = ex; }
+        if (b < nb) boffs[b] = carry + wb + inc - tot;
         __syncthreads();
         if (tid == 1023) carry += wb + inc;
         __syncthreads();
     }
-    if (tid == 0) offs[n] = carry;
+    if (tid == 0) boffs[nb] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_part_scan3(u32 *matrix, u64 n_chunks, u32 nb, const u64 *__restrict__ ts, const u64 *__restrict__ boffs)
+{
+    const u32 b = blockIdx.y * 256 + threadIdx.x;
+    if (b >= nb) return;
+    const u64 c0 = (u64)blockIdx.x * PT_CHUNKS, c1 = c0 + PT_CHUNKS < n_chunks ? c0 + PT_CHUNKS : n_chunks;
+    u64 run = boffs[b] + ts[(u64)blockIdx.x * nb + b];
+    for (u64 c = c0; c < c1; c++) { u32 v = matrix[c * nb + b]; matrix[c * nb + b] = (u32)run; run += v; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -484,7 +479,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sin
 // DRAM one sector at a time; instead every tile also streams its proportional share of the NEXT slice into
 // L2 with coalesced prefetches.
 constexpr int INS_BLOCK = 256;
-constexpr int INS_CTAS = 6;      // per SM -> 48 warps
+#ifndef DBG_INS_CTAS
+#define DBG_INS_CTAS 6
+#endif
+constexpr int INS_CTAS = DBG_INS_CTAS;      // per SM (x8 warps)
 
 template <bool WIDE, bool TRACK>
 __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
