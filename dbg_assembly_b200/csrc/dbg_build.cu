@@ -622,6 +622,29 @@ extern "C" int dbg_extract_tuples_device(dbg_ctx *c, const char *d_bases, const 
     return DBG_OK;
 }
 
+template <bool WIDE>
+static int partition_tuples(dbg_ctx *c, const void *d_src, uint64_t n, cudaStream_t s)
+{
+    const uint32_t nb = c->n_buckets;
+    const uint64_t n_rows = (n + TP_TILE - 1) / TP_TILE;
+    const uint64_t n_tiles = (n_rows + PT_CHUNKS - 1) / PT_CHUNKS;
+    size_t smem = 2 * (size_t)nb * sizeof(u32);
+    TableView t = view_of(c);
+    k_tuple_partition<WIDE, 0><<<(unsigned)n_rows, 256, smem, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, nullptr);
+    CU_TRY(cudaGetLastError());
+    dim3 g1((unsigned)n_tiles, (nb + 255) / 256);
+    k_part_scan1<<<g1, 256, 0, s>>>(c->d_matrix, n_rows, nb, c->d_tile_sums);
+    CU_TRY(cudaGetLastError());
+    k_part_scan2<<<1, 1024, 0, s>>>(c->d_tile_sums, n_tiles, nb, c->d_boffs);
+    CU_TRY(cudaGetLastError());
+    k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_rows, nb, c->d_tile_sums, c->d_boffs);
+    CU_TRY(cudaGetLastError());
+    k_tuple_partition<WIDE, 1><<<(unsigned)n_rows, 256, smem, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
+    CU_TRY(cudaGetLastError());
+    c->launches += 5;
+    return DBG_OK;
+}
+
 extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64_t n, void *stream)
 {
     if (!c || (!d_tuples && n)) return set_err(DBG_ERR_INVALID, "dbg_insert_tuples_device: NULL argument");
@@ -629,11 +652,28 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     if (n == 0) return DBG_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    // enough tuples per table slice: put them in slice order first, then insert through L2-resident slices
+    bool part = want_partition(c, n) && 2 * (size_t)c->n_buckets * sizeof(u32) <= 48 * 1024;
+    if (part && (ensure_tuples(c, n) != DBG_OK || ensure_matrix(c, (n + TP_TILE - 1) / TP_TILE) != DBG_OK)) part = false;
     EvPair ev;
     int rc = ev_begin(c, s, &ev);
     if (rc) return rc;
-    rc = insert_any(c, d_tuples, n, nullptr, s);
-    if (rc) return rc;
+    if (part) {
+        rc = c->wide ? partition_tuples<true>(c, d_tuples, n, s) : partition_tuples<false>(c, d_tuples, n, s);
+        if (rc) return rc;
+        EvPair ei;
+        rc = ev_begin(c, s, &ei);
+        if (rc) return rc;
+        ei.slot = 6;
+        rc = insert_any(c, c->d_tuples, n, nullptr, s, true);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(ei.b, s));
+        c->build_ev.push_back(ei);
+        c->part_blocks++;
+    } else {
+        rc = insert_any(c, d_tuples, n, nullptr, s);
+        if (rc) return rc;
+    }
     CU_TRY(cudaEventRecord(ev.b, s));
     c->build_ev.push_back(ev);
     return DBG_OK;

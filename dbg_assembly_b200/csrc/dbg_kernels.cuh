@@ -469,6 +469,47 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sin
 }
 
 // ---------------------------------------------------------------------------------------------------
+// owner side of the multi-GPU exchange: received tuples arrive in source order; the same exact, atomic-free
+// radix partition (count rows -> column scan -> scatter) puts them in table-slice order for the bucketed insert
+// ---------------------------------------------------------------------------------------------------
+constexpr int TP_TILE = 4096;     // tuples per CTA
+
+template <bool WIDE, int MODE>
+__global__ void __launch_bounds__(256) k_tuple_partition(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
+                                                         u32 *matrix, u64 *dst)
+{
+    extern __shared__ u32 tp_smem[];
+    u32 *hist = tp_smem, *base = tp_smem + nb;
+    u32 *row = matrix + (size_t)blockIdx.x * nb;
+    for (u32 b = threadIdx.x; b < nb; b += 256) { hist[b] = 0; if (MODE == 1) base[b] = row[b]; }
+    __syncthreads();
+    const u64 i0 = (u64)blockIdx.x * TP_TILE;
+    for (int r = 0; r < TP_TILE / 256; r++) {
+        const u64 i = i0 + (u64)r * 256 + threadIdx.x;
+        if (i >= n) break;
+        u64 klo, khi = 0, meta, z = 0;
+        if (WIDE) ld256_cs(reinterpret_cast<const ulonglong2 *>(src) + 2 * i, klo, khi, meta, z);
+        else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(src) + i); klo = x.x; meta = x.y; }
+        u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
+        u32 bkt = (u32)((mod_P(h, t.P, t.M) - t.lo) >> shift);
+        u32 rank = atomicAdd(&hist[bkt], 1u);
+        if (MODE == 1) {
+            u64 pos = (u64)base[bkt] + rank;
+            if (WIDE) {
+                ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + 2 * pos;
+                d[0] = make_ulonglong2(klo, khi); d[1] = make_ulonglong2(meta, 0ULL);
+            } else {
+                reinterpret_cast<ulonglong2 *>(dst)[pos] = make_ulonglong2(klo, meta);
+            }
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (u32 b = threadIdx.x; b < nb; b += 256) row[b] = hist[b];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // owner side: insert tuples (partitioned build and multi-GPU exchange)
 // ---------------------------------------------------------------------------------------------------
 // Persistent CTAs; CTA c takes tiles c, c+grid, ... of 256 tuples, ONE tuple per thread per tile: the kernel is
@@ -480,7 +521,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sin
 // L2 with coalesced prefetches.
 constexpr int INS_BLOCK = 256;
 #ifndef DBG_INS_CTAS
-#define DBG_INS_CTAS 6
+#define DBG_INS_CTAS 8
 #endif
 constexpr int INS_CTAS = DBG_INS_CTAS;      // per SM (x8 warps)
 
