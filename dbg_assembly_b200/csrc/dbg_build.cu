@@ -135,7 +135,7 @@ struct dbg_ctx {
     int part_mode;                 // 0 never, 1 always, 2 auto
     int part_shift;                // bucket = local slot >> part_shift
     uint32_t n_buckets;
-    u64 *d_boffs, *d_tuples, *d_tile_sums;
+    u64 *d_boffs, *d_roffs, *d_tuples, *d_tile_sums;   // d_roffs: owner-rank offsets of the exchange (65 entries)
     u32 *d_matrix;
     uint64_t cap_tuples, cap_matrix, part_blocks;
     // finalize / export
@@ -203,7 +203,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
-    cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
+    cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_roffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -287,6 +287,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_boffs, ((size_t)c->n_buckets + 1) * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_roffs, 65 * sizeof(u64)));
     return clear_table(c);
 }
 
@@ -374,7 +375,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
 {
     const uint32_t nb = c->n_buckets;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
-    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.n_buckets = nb;
+    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.div = 0; cs.div_M = 0; cs.n_buckets = nb;
     cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
     a.count_stats = 0;
     int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
@@ -387,7 +388,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_boffs);
     CU_TRY(cudaGetLastError());
     c->launches += 3;
-    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.n_buckets = nb;
+    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.n_buckets = nb;
     ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
     rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
@@ -403,6 +404,34 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     return DBG_OK;
 }
 
+// multi-GPU: extract this rank's occurrences and pack them by OWNER rank (exact, atomic-free, same machinery)
+template <bool WIDE>
+static int run_rank_partition(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, void *d_tuples, u64 *d_counts, cudaStream_t s)
+{
+    const uint32_t nb = (uint32_t)n_parts;
+    const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
+    const uint64_t div = (c->P + n_parts - 1) / n_parts;
+    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = 0; cs.div = div; cs.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div);
+    cs.n_buckets = nb; cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
+    a.count_stats = 0;
+    int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
+    if (rc) return rc;
+    dim3 g1((unsigned)n_tiles, (nb + 255) / 256);
+    k_part_scan1<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums);
+    CU_TRY(cudaGetLastError());
+    k_part_scan2<<<1, 1024, 0, s>>>(c->d_tile_sums, n_tiles, nb, c->d_roffs);
+    CU_TRY(cudaGetLastError());
+    k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_roffs);
+    CU_TRY(cudaGetLastError());
+    k_offsets_to_counts<<<1, 64, 0, s>>>(c->d_roffs, nb, d_counts);
+    CU_TRY(cudaGetLastError());
+    c->launches += 4;
+    PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = 0; ss.div = cs.div; ss.div_M = cs.div_M; ss.n_buckets = nb;
+    ss.matrix = c->d_matrix; ss.tuples = (u64 *)d_tuples; ss.hist = nullptr; ss.base = nullptr;
+    a.count_stats = 1;
+    return launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
+}
+
 static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
 {
     if (c->part_mode == 0) return false;
@@ -412,9 +441,10 @@ static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
     return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * build_node_bytes(c);
 }
 
-static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks)
+static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks, uint32_t nb = 0)
 {
-    uint64_t cells = n_chunks * (uint64_t)c->n_buckets;
+    if (nb == 0) nb = c->n_buckets;
+    uint64_t cells = n_chunks * (uint64_t)(nb > c->n_buckets ? nb : c->n_buckets);
     if (cells > (1ull << 28)) return DBG_ERR_NOMEM;          // > 1 GiB of offsets: not worth it, use the direct path
     if (cells <= c->cap_matrix) return DBG_OK;
     CU_TRY(cudaDeviceSynchronize());
@@ -422,7 +452,7 @@ static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks)
     c->d_matrix = nullptr; c->d_tile_sums = nullptr; c->cap_matrix = 0;
     uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
     if (cudaMalloc(&c->d_matrix, (cells + 16) * sizeof(u32)) != cudaSuccess) { cudaGetLastError(); return DBG_ERR_NOMEM; }
-    if (cudaMalloc(&c->d_tile_sums, (n_tiles + 1) * c->n_buckets * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); cudaFree(c->d_matrix); c->d_matrix = nullptr; return DBG_ERR_NOMEM; }
+    if (cudaMalloc(&c->d_tile_sums, (n_tiles + 1) * (uint64_t)(nb > c->n_buckets ? nb : c->n_buckets) * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); cudaFree(c->d_matrix); c->d_matrix = nullptr; return DBG_ERR_NOMEM; }
     c->cap_matrix = cells;
     return DBG_OK;
 }
@@ -458,6 +488,11 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     if (rc) return rc;
     bool part = n_parts == 0 && want_partition(c, total_bases);
     if (part && (ensure_tuples(c, total_bases) != DBG_OK || ensure_matrix(c, n_chunks) != DBG_OK)) part = false;
+    if (n_parts > 0) {
+        if (total_bases > bucket_stride) return set_err(DBG_ERR_BUFFER, "tuple capacity %llu < %llu (bases in the block)", (unsigned long long)bucket_stride, (unsigned long long)total_bases);
+        if (total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
+        if (ensure_matrix(c, n_chunks, (uint32_t)n_parts) != DBG_OK) return set_err(DBG_ERR_NOMEM, "partition offsets");
+    }
 
     EvPair ev;
     rc = ev_begin(c, s, &ev);
@@ -476,15 +511,8 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
         rc = c->wide ? run_partitioned<true>(c, a, n_chunks, total_bases, s) : run_partitioned<false>(c, a, n_chunks, total_bases, s);
         c->part_blocks++;
     } else if (n_parts > 0) {
-        if (c->wide) {
-            BucketSink<true> sk; sk.t = view_of(c); sk.shard_size = (c->P + n_parts - 1) / n_parts; sk.n_parts = n_parts;
-            sk.tuples = (u64 *)d_tuples; sk.bucket_stride = bucket_stride; sk.counts = d_counts;
-            rc = launch_build<true>(c, a, sk, n_chunks, s);
-        } else {
-            BucketSink<false> sk; sk.t = view_of(c); sk.shard_size = (c->P + n_parts - 1) / n_parts; sk.n_parts = n_parts;
-            sk.tuples = (u64 *)d_tuples; sk.bucket_stride = bucket_stride; sk.counts = d_counts;
-            rc = launch_build<false>(c, a, sk, n_chunks, s);
-        }
+        rc = c->wide ? run_rank_partition<true>(c, a, n_chunks, n_parts, d_tuples, d_counts, s)
+                     : run_rank_partition<false>(c, a, n_chunks, n_parts, d_tuples, d_counts, s);
     } else if (c->wide) {
         if (c->track) { InsertSink<true, true> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
         else { InsertSink<true, false> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
@@ -609,14 +637,13 @@ extern "C" int dbg_tuple_bytes(const dbg_ctx *c) { return c ? (c->wide ? 32 : 16
 
 extern "C" int dbg_extract_tuples_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
                                          uint64_t first_base, uint64_t total_bases, uint64_t first_read_index,
-                                         int32_t n_parts, void *d_tuples, uint64_t bucket_stride, uint64_t *d_counts, void *stream)
+                                         int32_t n_parts, void *d_tuples, uint64_t capacity, uint64_t *d_counts, void *stream)
 {
     if (!c || !d_tuples || !d_counts || n_parts < 1 || n_parts > 64) return set_err(DBG_ERR_INVALID, "dbg_extract_tuples_device: bad argument");
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    CU_TRY(cudaMemsetAsync(d_counts, 0, n_parts * sizeof(u64), s));
     int rc = build_device(c, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, first_read_index, s,
-                          n_parts, d_tuples, bucket_stride, (u64 *)d_counts);
+                          n_parts, d_tuples, capacity, (u64 *)d_counts);
     if (rc) return rc;
     c->reads_total += n_reads;
     return DBG_OK;

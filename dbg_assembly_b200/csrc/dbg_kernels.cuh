@@ -143,65 +143,7 @@ struct InsertSink {
     }
 };
 
-// tuples for the exchange: 16 B (narrow) {kmer, ord<<8 | rb<<4 | lb}, 32 B (wide) {lo, hi, meta, 0}
-template <bool WIDE>
-struct BucketSink {
-    static constexpr int RUN = G;
-    TableView t;            // P, M, polyA, counters (nodes unused)
-    u64 shard_size;         // ceil(P / n_parts)
-    int n_parts;
-    u64 *tuples;            // bucket b starts at b * bucket_stride tuples
-    u64 bucket_stride;
-    u64 *counts;            // n_parts
-
-    __device__ __forceinline__ void init(u32 *) {}
-    __device__ __forceinline__ void finish() {}
-
-    __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
-    {
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            // warp-aggregated append: all lanes take part in the ballots
-            int part = -1;
-            if (g < nv) {
-                if ((o[g].klo | o[g].khi) == 0) {
-                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
-                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
-                } else {
-                    u64 h = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                    u64 home = mod_P(h, t.P, t.M);
-                    part = 0;
-                    for (int q = 1; q < n_parts; q++) part += (home >= (u64)q * shard_size);
-                }
-            }
-            const u32 active = 0xffffffffu;   // consume() is called by every thread of the CTA
-            for (int q = 0; q < n_parts; q++) {
-                u32 m = __ballot_sync(active, part == q);
-                if (m == 0) continue;
-                int leader = __ffs(m) - 1;
-                u64 base = 0;
-                if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counts + q, (u64)__popc(m));
-                base = __shfl_sync(active, base, leader);
-                if (part == q) {
-                    u64 pos = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
-                    if (pos < bucket_stride) {
-                        u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
-                        if (WIDE) {
-                            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * ((u64)q * bucket_stride + pos);
-                            dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
-                            dst[1] = make_ulonglong2(meta, 0ULL);
-                        } else {
-                            reinterpret_cast<ulonglong2 *>(tuples)[(u64)q * bucket_stride + pos] = make_ulonglong2(o[g].klo, meta);
-                        }
-                    } else {
-                        atomicExch(t.counters + CNT_ERROR, 2ULL);
-                    }
-                }
-            }
-        }
-    }
-};
-
+// tuples (partitioned build and multi-GPU exchange): 16 B (narrow) {kmer, ord<<8 | rb<<4 | lb}, 32 B (wide) {lo, hi, meta, 0}
 // Radix partition by home-slot range (bucket = home >> shift), exact and atomic-free in global memory:
 //   pass 1 (MODE 0)  every chunk CTA histograms its occurrences per bucket in shared memory and stores the row
 //                    M[chunk][bucket];
@@ -215,7 +157,8 @@ template <bool WIDE, int MODE>
 struct PartitionSink {
     static constexpr int RUN = G;
     TableView t;
-    int shift;
+    int shift;         // bucket = (home - lo) >> shift          (table slices), or, when div != 0,
+    u64 div, div_M;    // bucket = home / div                    (owner ranks of the multi-GPU exchange)
     u32 n_buckets;
     u32 *matrix;       // [n_chunks][n_buckets]: counts after pass 1, write offsets after the scan
     u64 *tuples;
@@ -246,7 +189,10 @@ struct PartitionSink {
                     }
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                    u32 bkt = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
+                    u64 home = mod_P(hh, t.P, t.M);
+                    u32 bkt;
+                    if (div) { bkt = (u32)__umul64hi(home, div_M); if ((u64)(bkt + 1) * div <= home) bkt++; }
+                    else bkt = (u32)((home - t.lo) >> shift);
                     u32 rank = atomicAdd(&hist[bkt], 1u);
                     if (MODE == 1) {
                         u64 pos = (u64)base[bkt] + rank;
@@ -279,6 +225,12 @@ struct PartitionSink {
 //   2: per bucket: exclusive scan of ts over tiles, bucket totals -> boffs (exclusive over buckets), one CTA
 //   3: M[c][b] <- boffs[b] + ts_excl[tile][b] + running sum inside the tile       grid like 1
 constexpr int PT_CHUNKS = 128;     // chunks per scan tile
+
+__global__ void k_offsets_to_counts(const u64 *__restrict__ offs, u32 n, u64 *counts)
+{
+    u32 i = threadIdx.x;
+    if (i < n) counts[i] = offs[i + 1] - offs[i];
+}
 
 __global__ void __launch_bounds__(256) k_part_scan1(const u32 *__restrict__ matrix, u64 n_chunks, u32 nb, u64 *__restrict__ ts)
 {

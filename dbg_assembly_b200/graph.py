@@ -109,10 +109,10 @@ class DBGBuilder:
                                                   int(total_bases), idx, stream), "dbg_submit_reads_device")
 
     def extract_tuples_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index,
-                              n_parts, d_tuples_ptr, bucket_stride, d_counts_ptr, stream=None):
+                              n_parts, d_tuples_ptr, capacity, d_counts_ptr, stream=None):
         capi.check(self.L.dbg_extract_tuples_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base),
                                                     int(total_bases), int(first_read_index), int(n_parts), d_tuples_ptr,
-                                                    int(bucket_stride), d_counts_ptr, stream), "dbg_extract_tuples_device")
+                                                    int(capacity), d_counts_ptr, stream), "dbg_extract_tuples_device")
 
     def insert_tuples_device(self, d_tuples_ptr, n, stream=None):
         capi.check(self.L.dbg_insert_tuples_device(self.h, d_tuples_ptr, int(n), stream), "dbg_insert_tuples_device")

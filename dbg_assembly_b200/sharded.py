@@ -73,7 +73,7 @@ class ShardedBuilder:
     """The per-rank driver.  `reads` are this rank's own contiguous block of the global read sequence."""
 
     def __init__(self, K, max_read_len, init_slots, load_factor=0.7, device=0, track_order=True, group=None,
-                 slack=1.25):
+                 slack=None):
         from .graph import DBGBuilder
         self.ex = Exchange(group)
         self.n, self.rank = self.ex.world, self.ex.rank
@@ -81,36 +81,37 @@ class ShardedBuilder:
                             track_order=track_order, shard_rank=self.rank, shard_count=self.n)
         self.device = torch.device("cuda", device)
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
-        self.slack = slack
         self._send = self._counts = None
         self.exchange_bytes = 0
 
     def close(self):
         self.b.close()
 
-    def _buffers(self, n_occ_upper):
-        stride = int(n_occ_upper / self.n * self.slack) + 4096
-        need = self.n * stride * self.width
+    def _buffers(self, capacity):
+        need = capacity * self.width
         if self._send is None or self._send.numel() < need:
             self._send = torch.empty(need, dtype=torch.int64, device=self.device)
             self._counts = torch.zeros(self.n, dtype=torch.int64, device=self.device)
-        return stride
 
     def add_reads_device(self, d_bases: torch.Tensor, d_offs: torch.Tensor, n_reads, first_base, total_bases,
-                         first_read_index, n_occ_upper):
-        """one block of this rank's reads, device resident.  n_occ_upper bounds its occurrence count."""
+                         first_read_index, n_occ_upper=None):
+        """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
+        total_bases bounds the tuple count)"""
         from .graph import torch_stream_handle
         stream = torch_stream_handle(self.device)
-        stride = self._buffers(n_occ_upper)
+        cap = int(total_bases)
+        self._buffers(cap)
+        # tuples come back packed by owner rank: sizes in _counts, offsets = their prefix sums
         self.b.extract_tuples_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
-                                     self.n, self._send.data_ptr(), stride, self._counts.data_ptr(), stream=stream)
+                                     self.n, self._send.data_ptr(), cap, self._counts.data_ptr(), stream=stream)
         recv_counts = self.ex.exchange_counts(self._counts)
         sc = self._counts.cpu().tolist()
         rc = recv_counts.cpu().tolist()
-        if max(sc) > stride:
-            raise RuntimeError(f"tuple bucket overflow ({max(sc)} > {stride}): raise slack")
-        view = self._send.view(self.n, stride, self.width)
-        buckets = [view[q, : sc[q]] for q in range(self.n)]
+        view = self._send[: sum(sc) * self.width].view(-1, self.width)
+        buckets, off = [], 0
+        for q in range(self.n):
+            buckets.append(view[off:off + sc[q]])
+            off += sc[q]
         recv, total = self.ex.exchange_payload(buckets, rc, self.width, self._send)
         self.exchange_bytes += (sum(sc) - sc[self.rank]) * self.width * 8
         self.b.insert_tuples_device(recv.data_ptr(), total, stream=stream)

@@ -109,12 +109,13 @@ int  dbg_submit_reads_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *
 
 /* ---- multi-GPU building blocks (owner-computes split of thread_updatekmers, DBGgraph.cpp:148) ---- */
 /* 16-B occurrence tuple (K <= 31): kmer, meta = ordinal<<8 | right<<4 | left ; wide tuples add kmer_hi
- * (24 B, padded to 32).  Extract all occurrences of a device-resident block, bucketed by owner shard
- * (owner = (hash % P) / ceil(P/n_parts)), into d_tuples (capacity cap tuples, laid out bucket after
- * bucket at bucket_stride tuples); d_counts[n_parts] receives the bucket sizes. */
+ * (24 B, padded to 32).  Extract all occurrences of a device-resident block into d_tuples, PACKED by owner
+ * shard (owner = (hash % P) / ceil(P/n_parts)): the tuples of owner 0 first, then owner 1, ...;
+ * d_counts[n_parts] receives the sizes (offsets = their prefix sums).  `capacity` (in tuples) must be at
+ * least total_bases (an occurrence starts at a distinct base), else DBG_ERR_BUFFER. */
 int  dbg_extract_tuples_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
                                uint64_t first_base, uint64_t total_bases, uint64_t first_read_index,
-                               int32_t n_parts, void *d_tuples, uint64_t bucket_stride,
+                               int32_t n_parts, void *d_tuples, uint64_t capacity,
                                uint64_t *d_counts, void *stream);
 /* Insert n tuples (all owned by this context's shard) produced by dbg_extract_tuples_device. */
 int  dbg_insert_tuples_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, void *stream);

@@ -344,41 +344,51 @@ def test_sharded_tuple_path_single_gpu(dbg, oracle_mod):
     n_occ = o.occurrences
     for n_parts in (2, 3):
         shards = [dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req, shard_rank=r, shard_count=n_parts) for r in range(n_parts)]
-        stride = n_occ + 16
-        tuples = torch.empty(n_parts * stride * 2, dtype=torch.int64, device="cuda")
+        cap = int(offs[-1])
+        tuples = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
         counts = torch.zeros(n_parts, dtype=torch.int64, device="cuda")
         # every rank extracts its own half of the reads (here: one extractor context does both halves)
         half = len(reads) // 2
         polyA = np.zeros(8, dtype=np.uint64)
-        got = []
         for (r0, r1) in ((0, half), (half, len(reads))):
             ex = shards[0]
             ex.extract_tuples_device(db.data_ptr(), do.data_ptr() + 8 * r0, r1 - r0, int(offs[r0]), int(offs[r1] - offs[r0]), r0,
-                                     n_parts, tuples.data_ptr(), stride, counts.data_ptr())
+                                     n_parts, tuples.data_ptr(), cap, counts.data_ptr())
             torch.cuda.synchronize()
             c = counts.cpu().numpy()
-            for q in range(n_parts):
-                shards[q].insert_tuples_device(tuples.data_ptr() + 16 * q * stride, int(c[q]))
+            off = 0
+            for q in range(n_parts):          # tuples are packed by owner: offsets = prefix sums of the counts
+                shards[q].insert_tuples_device(tuples.data_ptr() + 16 * off, int(c[q]))
+                off += int(c[q])
             torch.cuda.synchronize()
         polyA += shards[0].get_polyA_counts()
         total_nodes = 0
-        ks, ls, rs = [], [], []
+        merged = {"kmer": [], "l": [], "r": []}
         for q, s in enumerate(shards):
             st = s.finalize()
             total_nodes += st["count"]
+            d = s.dump_shard()
+            assert len(d["kmer"]) == st["count"]
+            homes = np.array([dbg.capi.hash_code(int(k)) % o.size for k in d["kmer"][:500].tolist()], dtype=np.int64)
+            assert ((homes // ((o.size + n_parts - 1) // n_parts)) == q).all()
+            for k in merged:
+                merged[k].append(d[k])
             s.close()
-        # node contents are checked through the unsharded path fed by the same tuples
         assert total_nodes == o.count - 1            # shards do not carry the k-mer-0 node
+        nzm = e["kmer"] != 0
+        so = np.argsort(np.concatenate(merged["kmer"])); eo = np.argsort(e["kmer"][nzm])
+        for k in ("kmer", "l", "r"):
+            assert np.array_equal(np.concatenate(merged[k])[so], e[k][nzm][eo]), (n_parts, k)
         exp_l = np.minimum(polyA[:4], 255); exp_r = np.minimum(polyA[4:], 255)
         zero = e["kmer"] == 0
         assert int(e["l"][zero][0]) == int(exp_l[0]) << 24 | int(exp_l[1]) << 16 | int(exp_l[2]) << 8 | int(exp_l[3])
         assert int(e["r"][zero][0]) == int(exp_r[0]) << 24 | int(exp_r[1]) << 16 | int(exp_r[2]) << 8 | int(exp_r[3])
     # tuples of ALL occurrences into one unsharded context == the fused path == the oracle (layout too)
     with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ex, dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ins:
-        stride = n_occ + 16
-        tuples = torch.empty(stride * 2, dtype=torch.int64, device="cuda")
+        cap = int(offs[-1])
+        tuples = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
         counts = torch.zeros(1, dtype=torch.int64, device="cuda")
-        ex.extract_tuples_device(db.data_ptr(), do.data_ptr(), len(reads), 0, int(offs[-1]), 0, 1, tuples.data_ptr(), stride, counts.data_ptr())
+        ex.extract_tuples_device(db.data_ptr(), do.data_ptr(), len(reads), 0, int(offs[-1]), 0, 1, tuples.data_ptr(), cap, counts.data_ptr())
         torch.cuda.synchronize()
         ins.insert_tuples_device(tuples.data_ptr(), int(counts.item()))
         ins.set_polyA_counts(ex.get_polyA_counts())
