@@ -56,6 +56,8 @@ SYMBOLS = [
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
     "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
+    "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
+    "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
 ]
 
 _lib = None
@@ -105,6 +107,16 @@ def load(build_if_missing: bool = True):
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),
         "dbg_synth_reads_device": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp, i32, vp]),
         "dbg_measure_random_rmw": (C.c_int, [i32, u64, u64, i32, C.POINTER(C.c_float)]),
+        "kfreq_create": (C.c_int, [C.POINTER(vp), i32, i32, i32, i32]),
+        "kfreq_destroy": (None, [vp]),
+        "kfreq_submit_reads": (C.c_int, [vp, vp, vp, u64]),
+        "kfreq_submit_reads_device": (C.c_int, [vp, vp, vp, u64, u64, u64]),
+        "kfreq_finalize": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "kfreq_index_range": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "kfreq_histogram": (C.c_int, [vp, vp]),
+        "kfreq_export": (C.c_int, [vp, i32, i32, vp]),
+        "kfreq_write_cz": (C.c_int, [vp, C.c_char_p, i32, i32]),
+        "kfreq_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -51,7 +51,7 @@ struct BuildArgs {
 // ---------------------------------------------------------------------------------------------------
 // chunk index: chunk_first[c] = first read whose start offset lies in chunk >= c
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, u64 abase, u64 n_chunks,
+static __global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, u64 abase, u64 n_chunks,
                               u64 *__restrict__ chunk_first)
 {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,13 +226,13 @@ struct PartitionSink {
 //   3: M[c][b] <- boffs[b] + ts_excl[tile][b] + running sum inside the tile       grid like 1
 constexpr int PT_CHUNKS = 128;     // chunks per scan tile
 
-__global__ void k_offsets_to_counts(const u64 *__restrict__ offs, u32 n, u64 *counts)
+static __global__ void k_offsets_to_counts(const u64 *__restrict__ offs, u32 n, u64 *counts)
 {
     u32 i = threadIdx.x;
     if (i < n) counts[i] = offs[i + 1] - offs[i];
 }
 
-__global__ void __launch_bounds__(256) k_part_scan1(const u32 *__restrict__ matrix, u64 n_chunks, u32 nb, u64 *__restrict__ ts)
+static __global__ void __launch_bounds__(256) k_part_scan1(const u32 *__restrict__ matrix, u64 n_chunks, u32 nb, u64 *__restrict__ ts)
 {
     const u32 b = blockIdx.y * 256 + threadIdx.x;
     if (b >= nb) return;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) k_part_scan1(const u32 *__restrict__ matr
     ts[(u64)blockIdx.x * nb + b] = sum;
 }
 
-__global__ void __launch_bounds__(1024) k_part_scan2(u64 *ts, u64 n_tiles, u32 nb, u64 *boffs)
+static __global__ void __launch_bounds__(1024) k_part_scan2(u64 *ts, u64 n_tiles, u32 nb, u64 *boffs)
 {
     __shared__ u64 wsum[32];
     __shared__ u64 carry;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(1024) k_part_scan2(u64 *ts, u64 n_tiles, u32 n
     if (tid == 0) boffs[nb] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_part_scan3(u32 *matrix, u64 n_chunks, u32 nb, const u64 *__restrict__ ts, const u64 *__restrict__ boffs)
+static __global__ void __launch_bounds__(256) k_part_scan3(u32 *matrix, u64 n_chunks, u32 nb, const u64 *__restrict__ ts, const u64 *__restrict__ boffs)
 {
     const u32 b = blockIdx.y * 256 + threadIdx.x;
     if (b >= nb) return;
@@ -849,7 +849,7 @@ __device__ __forceinline__ void classify(u32 link, int cutoff, u32 &num, u32 &ba
 }
 
 // pass 1: klink, del_flag, depth histogram, per-tile counts of tips / branches / survivors / filled
-__global__ void __launch_bounds__(256) k_links_classify(const void *__restrict__ img, const u32 *__restrict__ nul32, u64 P, int wide,
+static __global__ void __launch_bounds__(256) k_links_classify(const void *__restrict__ img, const u32 *__restrict__ nul32, u64 P, int wide,
                                                         int cutoff, unsigned short *klink, u32 *del32,
                                                         u64 *depth_hist, u64 *stats3, u32 *tile_counts /* 4 per tile */)
 {
@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(256) k_links_classify(const void *__restrict__
 }
 
 // exclusive scan of tile_counts (4 interleaved streams) by one CTA; totals[4] out
-__global__ void __launch_bounds__(1024) k_scan_tiles(const u32 *__restrict__ tile_counts, u64 n_tiles, u64 *tile_offs, u64 *totals)
+static __global__ void __launch_bounds__(1024) k_scan_tiles(const u32 *__restrict__ tile_counts, u64 n_tiles, u64 *tile_offs, u64 *totals)
 {
     __shared__ u64 wsum[32][4];
     __shared__ u64 carry[4];
@@ -982,7 +982,7 @@ __device__ __forceinline__ void tile_rank(const bool (&flag)[TILE / 256], u32 (&
 }
 
 // pass 2: index-ordered tip and branch lists (contig.cpp:175-180 push_back order = slot order)
-__global__ void __launch_bounds__(256) k_links_lists(const unsigned short *__restrict__ klink, const u32 *__restrict__ nul32, u64 P,
+static __global__ void __launch_bounds__(256) k_links_lists(const unsigned short *__restrict__ klink, const u32 *__restrict__ nul32, u64 P,
                                                      const u64 *__restrict__ tile_offs, u64 *tips, u64 cap_tips,
                                                      u64 *branches, u64 cap_br)
 {
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(256) k_links_lists(const unsigned short *__res
 }
 
 // pass 2': slot-ordered dump of the surviving (or all filled) nodes
-__global__ void __launch_bounds__(256) k_compact_nodes(const void *__restrict__ img, const u32 *__restrict__ nul32,
+static __global__ void __launch_bounds__(256) k_compact_nodes(const void *__restrict__ img, const u32 *__restrict__ nul32,
                                                        const u32 *__restrict__ del32, u64 P, int wide, int which /*2 surv, 3 filled*/,
                                                        const u64 *__restrict__ tile_offs, u64 cap, u64 *slots, u64 *klo_out,
                                                        u64 *khi_out, u32 *l_out, u32 *r_out)

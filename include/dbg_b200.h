@@ -183,6 +183,29 @@ int  dbg_synth_reads_host(const dbg_synth_params *p, uint64_t first_read, uint64
 int  dbg_synth_reads_device(const dbg_synth_params *p, uint64_t first_read, uint64_t n_reads, char *d_out,
                             int32_t device, void *stream);
 
+/* ---- K-mer frequency table for correct_error ---------------------------------
+ * What the external `kmerfreq` program writes and correct_error loads (correct_error/main_parallel_senior.cpp:
+ * 273-408 1-bit form, correct_error/main.cpp:161-220 8-bit form): canonical k-mer counts in a direct-index table
+ * (K <= 17), written as <prefix>.kmer.freq.cz (zlib blocks of 8 Mi k-mers), .cz.len and .kmer.freq.stat.
+ * PARITY UNPINNED: kmerfreq itself is not in the reference tree; the format contract is the loaders'. */
+typedef struct kfreq_ctx kfreq_ctx;
+/* block_rank/block_count: this context owns a contiguous run of whole .cz blocks (multi-GPU); 0/1 = everything */
+int  kfreq_create(kfreq_ctx **ctx, int32_t K, int32_t device, int32_t block_rank, int32_t block_count);
+void kfreq_destroy(kfreq_ctx *ctx);
+int  kfreq_submit_reads(kfreq_ctx *ctx, const char *bases, const uint64_t *offs, uint64_t n_reads);
+int  kfreq_submit_reads_device(kfreq_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
+                               uint64_t first_base, uint64_t total_bases);
+int  kfreq_finalize(kfreq_ctx *ctx, uint64_t *n_occurrences, uint64_t *n_reads);
+int  kfreq_index_range(kfreq_ctx *ctx, uint64_t *lo, uint64_t *hi);
+/* hist[f] = species seen f times (f = 65535: that often or more), over the owned index range */
+int  kfreq_histogram(kfreq_ctx *ctx, uint64_t hist[65536]);
+/* raw image of the owned range into host memory: bits=1 -> (hi-lo)/8 bytes, bit 7-idx%8 of byte idx/8 set iff
+ * count > cutoff; bits=8 -> one byte min(255,count) per k-mer */
+int  kfreq_export(kfreq_ctx *ctx, int32_t bits, int32_t cutoff, uint8_t *out);
+/* <prefix>.kmer.freq.cz, <prefix>.kmer.freq.cz.len, and (when the context owns all of 4^K) <prefix>.kmer.freq.stat */
+int  kfreq_write_cz(kfreq_ctx *ctx, const char *prefix, int32_t bits, int32_t cutoff);
+const char *kfreq_last_error(void);
+
 /* ---- roofline denominators measured on the spot (bench.py) --------------------------------------- */
 /* uniformly random 32-B sector read-modify-writes over `bytes` of device memory, `n_ops` operations;
  * returns milliseconds (CUDA events).  mode 0: 32-B load + store, 1: 32-B load + 64-bit atomicCAS,

@@ -435,3 +435,29 @@ void orc_calculate_kmer_links(const orc_set *s, int freq_cutoff, uint8_t *klink,
     *n_tips = nt; *n_branches = nb;
     stats[0] = total; stats[1] = deleted; stats[2] = linear;
 }
+
+/* ---------------------------------------------------------------- a-14 / a-15: K-mer frequency table -----------
+ * PARITY UNPINNED: the producer (`kmerfreq`, fanagislab/kmerfreq, unpinned) is not in the reference tree.  This
+ * restates what its consumers and artefacts imply: canonical k-mer of EVERY read position (N counts
+ * as A, correct_error/seqKmer.cpp alphabet[]), direct index = the canonical 2K-bit value.  The in-tree mini builder
+ * construct_ref_kmer_table (correct_error/simulate_lowfreq_kmer.cpp:189-260) walks positions the same way. */
+void orc_kfreq_count(const char *bases, const uint64_t *offs, uint64_t n_reads, int K, uint32_t *counts)
+{
+    uint64_t mask = (1ULL << (2 * K)) - 1;
+    for (uint64_t i = 0; i < n_reads; i++) {
+        const char *rd = bases + offs[i];
+        uint64_t len = offs[i + 1] - offs[i];
+        if (len < (uint64_t)K) continue;
+        uint64_t kbit = 0, rc = 0;
+        for (uint64_t j = 0; j + K <= len; j++) {
+            if (j == 0) { kbit = orc_seq2bit(rd, K); rc = orc_rev_com_kbit(kbit, K); }
+            else {
+                uint64_t b = (uint64_t)orc_base_code((unsigned char)rd[j + K - 1]);
+                kbit = ((kbit << 2) | b) & mask;
+                rc = (rc >> 2) | ((3 - b) << (2 * (K - 1)));
+            }
+            uint64_t km = kbit <= rc ? kbit : rc;
+            if (counts[km] != 0xFFFFFFFFu) counts[km]++;
+        }
+    }
+}

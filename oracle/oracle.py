@@ -64,8 +64,64 @@ def lib():
     L.orc_dump.restype = u64; L.orc_dump.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.orc_calculate_kmer_links.restype = None
     L.orc_calculate_kmer_links.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    L.orc_kfreq_count.restype = None
+    L.orc_kfreq_count.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_int, C.c_void_p]
     _lib = L
     return L
+
+
+def kfreq_count(bases, offs, K):
+    """canonical K-mer counts of every read position, direct-index u32 table of 4^K entries"""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    if bases.size == 0:
+        bases = np.zeros(1, dtype=np.uint8)
+    counts = np.zeros(1 << (2 * K), dtype=np.uint32)
+    lib().orc_kfreq_count(bases.ctypes.data, offs.ctypes.data, len(offs) - 1, K, counts.ctypes.data)
+    return counts
+
+
+def load_cz_1bit(prefix, K):
+    """What correct_error's loader does with a 1-bit .cz (main_parallel_senior.cpp:334-408): inflate block i to
+    KmerFreq + i * 1 MiB, then set the reverse-complement bit of every set canonical entry.  -> bit array (uint8 0/1)"""
+    import zlib
+    total = 1 << (2 * K)
+    table = np.zeros(total // 8 if total >= 8 else 1, dtype=np.uint8)
+    lens = [int(x) for x in open(prefix + ".kmer.freq.cz.len").read().split()]
+    raw = open(prefix + ".kmer.freq.cz", "rb").read()
+    pos = 0
+    for i, ln in enumerate(lens):
+        blk = zlib.decompress(raw[pos:pos + ln]); pos += ln
+        a = np.frombuffer(blk, dtype=np.uint8)
+        table[i * (1 << 20): i * (1 << 20) + len(a)] = a
+    assert pos == len(raw)
+    bits = np.unpackbits(table)[:total]              # MSB first == get_freq (seqKmer.cpp:102-106)
+    idx = np.nonzero(bits)[0].astype(np.uint64)
+    L = lib()
+    rc = np.array([L.orc_rev_com_kbit(int(i), K) for i in idx.tolist()], dtype=np.uint64)
+    out = bits.copy()
+    out[rc[idx <= rc].astype(np.int64)] = 1          # thread_setrevcompkmer: only for i <= rc(i)
+    return out, bits
+
+
+def load_cz_8bit(prefix, K, low_freq_cutoff):
+    """correct_error/main.cpp:161-220: bytes > cutoff set the bit of the k-mer and of its reverse complement"""
+    import zlib
+    total = 1 << (2 * K)
+    lens = [int(x) for x in open(prefix + ".kmer.freq.cz.len").read().split()]
+    raw = open(prefix + ".kmer.freq.cz", "rb").read()
+    vals = np.zeros(total, dtype=np.uint8)
+    pos = 0
+    for i, ln in enumerate(lens):
+        a = np.frombuffer(zlib.decompress(raw[pos:pos + ln]), dtype=np.uint8); pos += ln
+        vals[i * (8 << 20): i * (8 << 20) + len(a)] = a
+    bits = np.zeros(total, dtype=np.uint8)
+    hi = np.nonzero(vals > low_freq_cutoff)[0]
+    bits[hi] = 1
+    L = lib()
+    for i in hi.tolist():
+        bits[L.orc_rev_com_kbit(int(i), K)] = 1
+    return bits, vals
 
 
 NODE16 = np.dtype([("kmer", "<u8"), ("l", "<u4"), ("r", "<u4")])
