@@ -179,8 +179,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's version banner goes to stdout when NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("DBG_BENCH_NCCL_DEBUG", "WARN")
+        # keep stdout to the one JSON line: NCCL writes its version banner / debug lines to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload(args.workload, world, args.scale)
