@@ -749,7 +749,6 @@ static int read_counters(dbg_ctx *c, u64 *cnt)
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost));
     if (cnt[CNT_ERROR] == 1) return set_err(DBG_ERR_TABLE_FULL, "probe ran off the shard (%llu slots + margin): table too full", (unsigned long long)(c->shard_hi - c->shard_lo));
-    if (cnt[CNT_ERROR] == 2) return set_err(DBG_ERR_BUFFER, "tuple bucket overflow: raise bucket_stride");
     return DBG_OK;
 }
 

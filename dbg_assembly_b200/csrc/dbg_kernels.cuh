@@ -1,18 +1,21 @@
 // dbg_kernels.cuh -- the sm_100a kernels of the De Bruijn graph build.
 //
-//   k_chunk_first   : reads -> fixed-size base chunks (one CTA per chunk later)
-//   k_build<..>     : FUSED  stage ASCII -> 2-bit pack in shared memory -> canonical k-mer + neighbour
-//                     bases per occurrence -> sink.  Sinks: InsertSink (hash insert/update, single GPU
-//                     and the owner side of multi-GPU) and BucketSink (tuples bucketed by owner shard
-//                     for the all-to-all).
-//   k_insert_tuples : owner side of the exchange
-//   k_layout_*      : rebuild the reference's slot layout (first-occurrence priority linear probing)
-//   k_links_* / k_compact_* : calculate_kmer_links + ordered stream compaction
+//   k_chunk_first       : reads -> fixed-size base chunks (one CTA per chunk later)
+//   k_build<..>         : FUSED  stage ASCII -> 2-bit pack in shared memory -> canonical k-mer + neighbour
+//                         bases per occurrence -> sink.  Sinks: InsertSink (direct hash insert),
+//                         PartitionSink<0/1> (exact radix partition by table slice or by owner rank),
+//                         FreqSink (kfreq.cu: direct-index k-mer counts).
+//   k_part_scan1/2/3    : column scan of the per-chunk bucket counts -> exact write offsets
+//   k_tuple_partition   : the same partition over received tuples (owner side of the multi-GPU exchange)
+//   k_insert_tuples     : bucket-ordered hash insert through L2-resident table slices
+//   k_layout_*          : rebuild the reference's slot layout (first-occurrence priority linear probing)
+//   k_links_* / k_compact_* / k_dump_shard : calculate_kmer_links + ordered stream compaction, shard dump
 //
 // Reference semantics: DBGgraph.cpp:38-213 (parse + update), kmerSet.cpp:253-273 (poly-A node),
 // contig.cpp:107-205 (link pass).  Nothing here is a translation of the pthread code: the reference
 // materialises (kmer,left,right) per block and lets T threads rescan it; here one CTA owns a chunk of
-// bases, keeps it packed in shared memory and pushes occurrences straight into the HBM table.
+// bases, keeps it packed in shared memory and pushes occurrences straight into the HBM table or into
+// slice-ordered tuples.
 #pragma once
 #include "dbg_core.cuh"
 
