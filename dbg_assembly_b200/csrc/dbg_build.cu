@@ -436,9 +436,10 @@ static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
 {
     if (c->part_mode == 0) return false;
     if (c->part_mode == 1) return true;
-    // auto: streaming the table slice through L2 once per block (2 x table bytes) plus 2 x 16..32 B of tuple
-    // traffic must beat one random 64-B sector round trip per occurrence at ~1/5 of the streaming rate
-    return c->n_buckets >= 2 && (double)occ_upper * 144.0 > (double)c->n_local * build_node_bytes(c);
+    // auto (measured on C2, profiles/README.md): the partitioned path costs ~47 ps per occurrence plus one
+    // streaming pass over the table per block (~0.4 ps per table byte), the direct path ~55 ps per occurrence
+    // whatever the table size -> partition when the block has more than about table_bytes / 20 occurrences
+    return c->n_buckets >= 2 && (double)occ_upper * 20.0 > (double)c->n_local * build_node_bytes(c);
 }
 
 static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks, uint32_t nb = 0)

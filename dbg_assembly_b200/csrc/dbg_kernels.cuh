@@ -202,10 +202,10 @@ struct PartitionSink {
                         u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
                         if (WIDE) {
                             ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
-                            dst[0] = make_ulonglong2(o[g].klo, o[g].khi);
-                            dst[1] = make_ulonglong2(meta, 0ULL);
+                            __stcg(dst, make_ulonglong2(o[g].klo, o[g].khi));
+                            __stcg(dst + 1, make_ulonglong2(meta, 0ULL));
                         } else {
-                            reinterpret_cast<ulonglong2 *>(tuples)[pos] = make_ulonglong2(o[g].klo, meta);
+                            __stcg(reinterpret_cast<ulonglong2 *>(tuples) + pos, make_ulonglong2(o[g].klo, meta));
                         }
                     }
                 }
@@ -489,7 +489,15 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
     u32 n_new = 0, n_conf = 0;
     u32 b = 0;                  // current bucket of this CTA's tile (monotone)
     u64 b0 = 0, b1 = 0;
-    if (boffs) { b0 = __ldg(boffs); b1 = __ldg(boffs + 1); }
+    float ratio = 0.f;
+    if (boffs) {
+        b0 = __ldg(boffs); b1 = __ldg(boffs + 1);
+        if (n_buckets > 1 && b1 > b0) {
+            u64 slice_n = (u64)1 << shift;
+            if (2 * slice_n > t.n_local) slice_n = t.n_local > slice_n ? t.n_local - slice_n : 0;
+            ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);
+        }
+    }
     __shared__ u64 s_tile;
     // tiles are handed out by a global counter, so at any moment the resident CTAs hold the NEXT gridDim tiles of
     // the bucket-ordered stream: the window of table slices they touch cannot drift apart (static round-robin
@@ -507,18 +515,27 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
             else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + i); klo = x.x; meta = x.y; }
         }
         if (boffs) {
-            while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
-            if (b + 1 < n_buckets && b1 > b0) {
-                const u64 slice_lo = (u64)(b + 1) << shift;
-                u64 slice_n = (u64)1 << shift;
-                if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
-                const u64 lines = slice_n * sizeof(NodeT<WIDE>) / 128;                 // 128-B L2 lines in the next slice
-                const u64 span = b1 - b0;
-                const u64 t0 = tile - b0, t1 = (t0 + INS_BLOCK < span) ? t0 + INS_BLOCK : span;
-                const u64 l0 = lines * t0 / span, l1 = lines * t1 / span;      // lines <= 2^17: no overflow
-                const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + slice_lo);
-                for (u64 l = l0 + threadIdx.x; l < l1; l += INS_BLOCK)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
+            if (tile >= b1 && b + 1 < n_buckets) {
+                // entered a new bucket: its tuple span and the lines-per-tuple ratio of the NEXT slice (rare path)
+                while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
+                ratio = 0.f;
+                if (b + 1 < n_buckets && b1 > b0) {
+                    const u64 slice_lo = (u64)(b + 1) << shift;
+                    u64 slice_n = (u64)1 << shift;
+                    if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
+                    ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);   // 128-B L2 lines per tuple
+                }
+            }
+            if (ratio > 0.f) {
+                // this tile's proportional share of the next slice (approximate shares are fine: overlaps and small
+                // gaps only cost a few redundant or late lines)
+                const float t0 = (float)(tile - b0);
+                const u64 l0 = (u64)(t0 * ratio), l1 = (u64)((t0 + (float)INS_BLOCK) * ratio) + 1;
+                const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + ((u64)(b + 1) << shift));
+                const u64 lmax = (((u64)1 << shift) * sizeof(NodeT<WIDE>)) / 128;
+                for (u64 l = l0 + threadIdx.x; l < l1 && l < lmax; l += INS_BLOCK)
+                    if (((u64)(b + 1) << shift) + l * (128 / sizeof(NodeT<WIDE>)) < t.n_local)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
             }
         }
         if (i < n)
