@@ -14,6 +14,7 @@
 // Differences a user can observe: the "conflict:" statistic counts GPU probe steps, "-t" only affects the
 // host traversal, and "-e" (enlarge) is not emulated: if the node count passes max_cutoff a warning is
 // printed (the reference would have enlarged and produced a different slot order; contents are the same).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -117,9 +118,15 @@ static void parse_one_reads_file_b200(dbg_ctx *ctx, Block &b, string &reads_file
     currentFile.close();
 }
 
+static double wall_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void build_debruijn_graph(vector<string> &reads_files)
 {
     time_start = clock();
+    const double w0 = wall_now();
 
     // contig.h:127-130 needs the head mask (DBGgraph.cpp:371)
     KmerHeadMaskVal = pow_integer(2, KmerSize * 2) - 1;
@@ -157,6 +164,7 @@ void build_debruijn_graph(vector<string> &reads_files)
     if ((rc = dbg_host_alloc(&p, (b.cap_reads + 1) * sizeof(uint64_t)))) die("dbg_host_alloc", rc);
     b.offs = (uint64_t *)p;
 
+    const double w1 = wall_now();
     cerr << "\nparse input reads files: " << endl;
     for (size_t i = 0; i < reads_files.size(); i++) {
         cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
@@ -171,6 +179,7 @@ void build_debruijn_graph(vector<string> &reads_files)
     }
 
     // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
+    const double w2 = wall_now();
     dbg_stats st;
     if ((rc = dbg_finalize(ctx, &st))) die("dbg_finalize", rc);
     if (st.count - 1 > st.max_cutoff)
@@ -190,7 +199,11 @@ void build_debruijn_graph(vector<string> &reads_files)
     kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
     kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
     if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
+    const double w3 = wall_now();
     if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
+    const double w4 = wall_now();
+    cerr << "libdbgb200 wall clock (s): init " << w1 - w0 << ", read files + submit " << w2 - w1 << ", finalize (GPU build + layout) "
+         << w3 - w2 << ", export kmerset " << w4 - w3 << endl;
 
     dbg_host_free(b.bases);
     dbg_host_free(b.offs);
