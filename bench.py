@@ -178,9 +178,12 @@ def run_b200(args):
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep stdout to the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1 behind python's back, so
+    # fd 1 is pointed at stderr for the whole run and the result goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its version banner / debug lines to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload(args.workload, world, args.scale)
@@ -367,11 +370,13 @@ def run_b200(args):
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
 
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    os.close(real_stdout)
     return 0
 
 
