@@ -15,6 +15,7 @@
 // host traversal, and "-e" (enlarge) is not emulated: if the node count passes max_cutoff a warning is
 // printed (the reference would have enlarged and produced a different slot order; contents are the same).
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -150,6 +151,14 @@ void build_debruijn_graph(vector<string> &reads_files)
     dbg_ctx *ctx = NULL;
     int rc = dbg_create(&ctx, &prm);
     if (rc) die("dbg_create", rc);
+    // the KmerSet the traversal consumes (kmerSet.h:88-99): allocated page-locked, in the background while the
+    // reads are being parsed, so that the export is one PCIe-rate copy instead of a page-faulting pageable one
+    const uint64_t P_slots = prm.init_slots < 3 ? 3 : dbg_find_next_prime(prm.init_slots);   // kmerSet.cpp:102-103
+    KmerNode *pinned_array = NULL;
+    std::thread alloc_thread([&]() {
+        void *q = NULL;
+        if (dbg_host_alloc(&q, P_slots * sizeof(KmerNode)) == DBG_OK) pinned_array = (KmerNode *)q;
+    });
     cerr << "Hash initialization array size:  " << initHashSize << " G" << endl;
     cerr << "The initialization memory used:  " << initHashSize * 16 << " G" << endl;
     time_end = clock();
@@ -195,7 +204,8 @@ void build_debruijn_graph(vector<string> &reads_files)
     kset->load_factor = st.load_factor;
     kset->max = st.max_cutoff;
     kset->iter_ptr = 0;
-    kset->array = (KmerNode *)malloc(kset->size * kset->e_size);
+    alloc_thread.join();
+    kset->array = (pinned_array && P_slots == kset->size) ? pinned_array : (KmerNode *)malloc(kset->size * kset->e_size);
     kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
     kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
     if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
