@@ -351,7 +351,7 @@ template <bool WIDE, bool TRACK>
 static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed)
 {
     if (n_upper == 0) return DBG_OK;
-    uint64_t tiles = (n_upper + INS_BLOCK - 1) / INS_BLOCK;
+    uint64_t tiles = (n_upper + INS_TILE - 1) / INS_TILE;
     uint64_t persistent = (uint64_t)c->n_sms * INS_CTAS;
     unsigned grid = (unsigned)(tiles < persistent ? tiles : persistent);
     CU_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(u64), s));      // tile counter

@@ -475,6 +475,11 @@ __global__ void __launch_bounds__(256) k_tuple_partition(const u64 *__restrict__
 // DRAM one sector at a time; instead every tile also streams its proportional share of the NEXT slice into
 // L2 with coalesced prefetches.
 constexpr int INS_BLOCK = 256;
+#ifndef DBG_INS_ROUNDS
+#define DBG_INS_ROUNDS 2
+#endif
+constexpr int INS_ROUNDS = DBG_INS_ROUNDS;            // tuples per thread per tile
+constexpr int INS_TILE = INS_BLOCK * INS_ROUNDS;
 #ifndef DBG_INS_CTAS
 #define DBG_INS_CTAS 8
 #endif
@@ -498,21 +503,28 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
             ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);
         }
     }
-    __shared__ u64 s_tile;
+    __shared__ u64 s_tile[2];
     // tiles are handed out by a global counter, so at any moment the resident CTAs hold the NEXT gridDim tiles of
     // the bucket-ordered stream: the window of table slices they touch cannot drift apart (static round-robin
-    // let fast CTAs run buckets ahead and the slices fell out of L2)
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ULL);
+    // let fast CTAs run buckets ahead and the slices fell out of L2).  The counter is read one tile ahead (its
+    // round trip hides behind the current tile) and published through a ping-pong slot: one barrier per tile.
+    u64 next_tile = 0;
+    if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+    for (u32 par = 0;; par ^= 1) {
+        if (threadIdx.x == 0) s_tile[par] = next_tile;
         __syncthreads();
-        const u64 tile = s_tile * INS_BLOCK;
-        __syncthreads();
+        const u64 tile = s_tile[par] * INS_TILE;
         if (tile >= n) break;
-        const u64 i = tile + threadIdx.x;
-        u64 klo = 0, khi = 0, meta = 0;
-        if (i < n) {
-            if (WIDE) { u64 z; ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * i, klo, khi, meta, z); }   // read once: evict first
-            else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + i); klo = x.x; meta = x.y; }
+        if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+        u64 klo[INS_ROUNDS], khi[INS_ROUNDS], meta[INS_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < INS_ROUNDS; r++) {
+            const u64 i = tile + (u64)r * INS_BLOCK + threadIdx.x;
+            klo[r] = 0; khi[r] = 0; meta[r] = 0;
+            if (i < n) {
+                if (WIDE) { u64 z; ld256_cs(reinterpret_cast<const ulonglong2 *>(tuples) + 2 * i, klo[r], khi[r], meta[r], z); }   // read once: evict first
+                else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + i); klo[r] = x.x; meta[r] = x.y; }
+            }
         }
         if (boffs) {
             if (tile >= b1 && b + 1 < n_buckets) {
@@ -530,7 +542,7 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
                 // this tile's proportional share of the next slice (approximate shares are fine: overlaps and small
                 // gaps only cost a few redundant or late lines)
                 const float t0 = (float)(tile - b0);
-                const u64 l0 = (u64)(t0 * ratio), l1 = (u64)((t0 + (float)INS_BLOCK) * ratio) + 1;
+                const u64 l0 = (u64)(t0 * ratio), l1 = (u64)((t0 + (float)INS_TILE) * ratio) + 1;
                 const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + ((u64)(b + 1) << shift));
                 const u64 lmax = (((u64)1 << shift) * sizeof(NodeT<WIDE>)) / 128;
                 for (u64 l = l0 + threadIdx.x; l < l1 && l < lmax; l += INS_BLOCK)
@@ -538,8 +550,10 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
             }
         }
-        if (i < n)
-            insert_one<WIDE, TRACK>(t, klo, khi, (u32)(meta & 15), (u32)((meta >> 4) & 15), meta >> 8, n_new, n_conf);
+#pragma unroll
+        for (int r = 0; r < INS_ROUNDS; r++)
+            if ((klo[r] | khi[r]) != 0)      // tuples never carry the k-mer-0 key, so 0 = past the end
+                insert_one<WIDE, TRACK>(t, klo[r], khi[r], (u32)(meta[r] & 15), (u32)((meta[r] >> 4) & 15), meta[r] >> 8, n_new, n_conf);
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) { n_new += __shfl_xor_sync(0xffffffffu, n_new, s); n_conf += __shfl_xor_sync(0xffffffffu, n_conf, s); }
