@@ -222,7 +222,9 @@ def run_b200(args):
         timings = b.timings
     else:
         from dbg_assembly_b200.sharded import ShardedBuilder
-        sb = ShardedBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True)
+        sb = ShardedBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True,
+                            exchange=args.exchange)
+        extra["exchange"] = sb.exchange
         sb.b.set_stream(stream)
 
         def step():
@@ -390,6 +392,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; numbers at scale != 1 are not the metric)")
     ap.add_argument("--init-g", type=float, default=None, help="override the table size -i (experiments only)")
     ap.add_argument("--ref-sample-reads", type=int, default=400_000)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU: 'peer' = scatter kernel stores tuples into the owners' buffers over NVLink (fused), 'nccl' = pack + send/recv")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     args = ap.parse_args()

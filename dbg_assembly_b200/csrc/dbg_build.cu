@@ -376,7 +376,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     const uint32_t nb = c->n_buckets;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
     PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.div = 0; cs.div_M = 0; cs.n_buckets = nb;
-    cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
+    cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.dst_ptrs = nullptr; cs.dst_base = nullptr; cs.roffs = nullptr; cs.hist = nullptr; cs.base = nullptr;
     a.count_stats = 0;
     int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
     if (rc) return rc;
@@ -389,7 +389,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     CU_TRY(cudaGetLastError());
     c->launches += 3;
     PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.n_buckets = nb;
-    ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.hist = nullptr; ss.base = nullptr;
+    ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.dst_ptrs = nullptr; ss.dst_base = nullptr; ss.roffs = nullptr; ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
     rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
     if (rc) return rc;
@@ -404,15 +404,24 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     return DBG_OK;
 }
 
-// multi-GPU: extract this rank's occurrences and pack them by OWNER rank (exact, atomic-free, same machinery)
+// multi-GPU: extract this rank's occurrences and pack them by OWNER rank (exact, atomic-free, same machinery).
+// phase 1 = count + scan (-> per-owner sizes in d_counts), phase 2 = scatter; phase 2 either packs locally
+// (d_tuples) or stores straight into the owners' receive buffers over NVLink peer mappings (fused exchange).
 template <bool WIDE>
-static int run_rank_partition(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, void *d_tuples, u64 *d_counts, cudaStream_t s)
+static void fill_rank_sink(dbg_ctx *c, PartitionSink<WIDE, 0> &cs, int n_parts)
+{
+    const uint64_t div = (c->P + n_parts - 1) / n_parts;
+    cs.t = view_of(c); cs.shift = 0; cs.div = div; cs.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div);
+    cs.n_buckets = (uint32_t)n_parts; cs.matrix = c->d_matrix; cs.tuples = nullptr;
+    cs.dst_ptrs = nullptr; cs.dst_base = nullptr; cs.roffs = nullptr; cs.hist = nullptr; cs.base = nullptr;
+}
+
+template <bool WIDE>
+static int run_rank_count(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, u64 *d_counts, cudaStream_t s)
 {
     const uint32_t nb = (uint32_t)n_parts;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
-    const uint64_t div = (c->P + n_parts - 1) / n_parts;
-    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = 0; cs.div = div; cs.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div);
-    cs.n_buckets = nb; cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.hist = nullptr; cs.base = nullptr;
+    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts);
     a.count_stats = 0;
     int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
     if (rc) return rc;
@@ -426,10 +435,27 @@ static int run_rank_partition(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_
     k_offsets_to_counts<<<1, 64, 0, s>>>(c->d_roffs, nb, d_counts);
     CU_TRY(cudaGetLastError());
     c->launches += 4;
-    PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = 0; ss.div = cs.div; ss.div_M = cs.div_M; ss.n_buckets = nb;
-    ss.matrix = c->d_matrix; ss.tuples = (u64 *)d_tuples; ss.hist = nullptr; ss.base = nullptr;
+    return DBG_OK;
+}
+
+template <bool WIDE>
+static int run_rank_scatter(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, void *d_tuples, u64 *const *d_dst_ptrs,
+                            const u64 *d_dst_base, cudaStream_t s)
+{
+    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts);
+    PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = 0; ss.div = cs.div; ss.div_M = cs.div_M; ss.n_buckets = cs.n_buckets;
+    ss.matrix = c->d_matrix; ss.tuples = (u64 *)d_tuples; ss.dst_ptrs = d_dst_ptrs; ss.dst_base = d_dst_base; ss.roffs = c->d_roffs;
+    ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
-    return launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
+    return launch_build<WIDE>(c, a, ss, n_chunks, s, (uint32_t)n_parts);
+}
+
+template <bool WIDE>
+static int run_rank_partition(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, void *d_tuples, u64 *d_counts, cudaStream_t s)
+{
+    int rc = run_rank_count<WIDE>(c, a, n_chunks, n_parts, d_counts, s);
+    if (rc) return rc;
+    return run_rank_scatter<WIDE>(c, a, n_chunks, n_parts, d_tuples, nullptr, nullptr, s);
 }
 
 static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
@@ -647,6 +673,104 @@ extern "C" int dbg_extract_tuples_device(dbg_ctx *c, const char *d_bases, const 
                           n_parts, d_tuples, capacity, (u64 *)d_counts);
     if (rc) return rc;
     c->reads_total += n_reads;
+    return DBG_OK;
+}
+
+// ---- fused exchange over NVLink peer memory ---------------------------------------------------------
+static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_offs, uint64_t n_reads, uint64_t first_base,
+                      uint64_t total_bases, uint64_t read_index0, int n_parts, u64 *d_counts, u64 *const *d_dst_ptrs,
+                      const u64 *d_dst_base, cudaStream_t s)
+{
+    if (n_parts < 1 || n_parts > 64) return set_err(DBG_ERR_INVALID, "n_parts outside 1..64");
+    if (n_reads == 0 || total_bases == 0) {
+        if (phase == 1) CU_TRY(cudaMemsetAsync(d_counts, 0, n_parts * sizeof(u64), s));
+        return DBG_OK;
+    }
+    uint64_t abase = first_base & ~15ull;
+    if (((uintptr_t)(d_bases + abase) & 15) != 0) return set_err(DBG_ERR_INVALID, "device base buffer must be 16-byte aligned");
+    uint64_t n_chunks = (first_base + total_bases - abase + CB - 1) / CB;
+    if (n_chunks > 0x7fffffffull || total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
+    int rc = ensure_chunks(c, n_chunks);
+    if (rc) return rc;
+    if (ensure_matrix(c, n_chunks, (uint32_t)n_parts) != DBG_OK) return set_err(DBG_ERR_NOMEM, "partition offsets");
+    EvPair ev;
+    rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    BuildArgs a;
+    a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
+    a.chunk_first = c->d_chunk_first; a.read_index0 = read_index0; a.K = c->prm.K; a.R = c->prm.max_read_len;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
+    if (phase == 1) {
+        unsigned gb = (unsigned)((n_reads + 1 + 255) / 256);
+        k_chunk_first<<<gb, 256, 0, s>>>(d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        rc = c->wide ? run_rank_count<true>(c, a, n_chunks, n_parts, d_counts, s) : run_rank_count<false>(c, a, n_chunks, n_parts, d_counts, s);
+    } else {
+        rc = c->wide ? run_rank_scatter<true>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s)
+                     : run_rank_scatter<false>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s);
+        c->reads_total += n_reads;
+    }
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+extern "C" int dbg_exchange_count_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                         uint64_t total_bases, int32_t n_parts, uint64_t *d_counts, void *stream)
+{
+    if (!c || !d_counts) return set_err(DBG_ERR_INVALID, "dbg_exchange_count_device: NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    return rank_phase(c, 1, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, 0, n_parts, (u64 *)d_counts, nullptr, nullptr,
+                      stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int dbg_exchange_scatter_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                           uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
+                                           const uint64_t *d_dst_base, void *stream)
+{
+    if (!c || !d_dst_ptrs || !d_dst_base) return set_err(DBG_ERR_INVALID, "dbg_exchange_scatter_device: NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    return rank_phase(c, 2, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, first_read_index, n_parts, nullptr,
+                      (u64 *const *)d_dst_ptrs, (const u64 *)d_dst_base, stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int dbg_peer_alloc(dbg_ctx *c, uint64_t bytes, void **d_ptr, uint8_t handle[64])
+{
+    if (!c || !d_ptr || !handle) return set_err(DBG_ERR_INVALID, "dbg_peer_alloc: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMalloc(d_ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle, &h, 64);
+    return DBG_OK;
+}
+
+extern "C" int dbg_peer_open(dbg_ctx *c, const uint8_t handle[64], void **d_ptr)
+{
+    if (!c || !d_ptr || !handle) return set_err(DBG_ERR_INVALID, "dbg_peer_open: NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DBG_OK;
+}
+
+extern "C" int dbg_peer_close(dbg_ctx *c, void *d_ptr)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    if (d_ptr) CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return DBG_OK;
+}
+
+extern "C" int dbg_peer_free(dbg_ctx *c, void *d_ptr)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    CU_TRY(cudaSetDevice(c->device));
+    if (d_ptr) CU_TRY(cudaFree(d_ptr));
     return DBG_OK;
 }
 

@@ -165,6 +165,11 @@ struct PartitionSink {
     u32 n_buckets;
     u32 *matrix;       // [n_chunks][n_buckets]: counts after pass 1, write offsets after the scan
     u64 *tuples;
+    // fused exchange (multi-GPU): bucket q's tuples are stored straight into rank q's receive buffer over
+    // NVLink peer mappings, at dst_base[q] + (this rank's running offset for q); NULL = local packed output
+    u64 *const *dst_ptrs;
+    const u64 *dst_base;   // first tuple index reserved for this rank in each peer's buffer
+    const u64 *roffs;      // this rank's packed start of each bucket (subtracted from the matrix offsets)
     u32 *hist;         // shared: n_buckets running counts of this chunk
     u32 *base;         // shared: n_buckets write offsets of this chunk (MODE 1)
 
@@ -175,7 +180,7 @@ struct PartitionSink {
         const u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
         for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) {
             hist[b] = 0;
-            if (MODE == 1) base[b] = row[b];
+            if (MODE == 1) base[b] = dst_ptrs ? (u32)((u64)row[b] - roffs[b] + dst_base[b]) : row[b];
         }
         __syncthreads();
     }
@@ -200,6 +205,7 @@ struct PartitionSink {
                     if (MODE == 1) {
                         u64 pos = (u64)base[bkt] + rank;
                         u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+                        u64 *tuples = dst_ptrs ? dst_ptrs[bkt] : this->tuples;      // peer (or own) receive buffer
                         if (WIDE) {
                             ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tuples) + 2 * pos;
                             __stcg(dst, make_ulonglong2(o[g].klo, o[g].khi));

@@ -114,6 +114,36 @@ class DBGBuilder:
                                                     int(total_bases), int(first_read_index), int(n_parts), d_tuples_ptr,
                                                     int(capacity), d_counts_ptr, stream), "dbg_extract_tuples_device")
 
+    # ---- fused exchange over peer memory ----
+    def peer_alloc(self, nbytes):
+        """-> (device pointer, 64-byte IPC handle) of a cudaMalloc'ed receive buffer on this context's device"""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        capi.check(self.L.dbg_peer_alloc(self.h, int(nbytes), C.byref(ptr), handle), "dbg_peer_alloc")
+        return ptr.value, bytes(handle)
+
+    def peer_open(self, handle: bytes):
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        capi.check(self.L.dbg_peer_open(self.h, buf, C.byref(ptr)), "dbg_peer_open")
+        return ptr.value
+
+    def peer_close(self, ptr):
+        capi.check(self.L.dbg_peer_close(self.h, ptr), "dbg_peer_close")
+
+    def peer_free(self, ptr):
+        capi.check(self.L.dbg_peer_free(self.h, ptr), "dbg_peer_free")
+
+    def exchange_count_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, n_parts, d_counts_ptr, stream=None):
+        capi.check(self.L.dbg_exchange_count_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
+                                                    int(n_parts), d_counts_ptr, stream), "dbg_exchange_count_device")
+
+    def exchange_scatter_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index, n_parts,
+                                d_dst_ptrs_ptr, d_dst_base_ptr, stream=None):
+        capi.check(self.L.dbg_exchange_scatter_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
+                                                      int(first_read_index), int(n_parts), d_dst_ptrs_ptr, d_dst_base_ptr, stream),
+                   "dbg_exchange_scatter_device")
+
     def insert_tuples_device(self, d_tuples_ptr, n, stream=None):
         capi.check(self.L.dbg_insert_tuples_device(self.h, d_tuples_ptr, int(n), stream), "dbg_insert_tuples_device")
 

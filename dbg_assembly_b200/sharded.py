@@ -73,7 +73,7 @@ class ShardedBuilder:
     """The per-rank driver.  `reads` are this rank's own contiguous block of the global read sequence."""
 
     def __init__(self, K, max_read_len, init_slots, load_factor=0.7, device=0, track_order=True, group=None,
-                 slack=None):
+                 slack=None, exchange="peer"):
         from .graph import DBGBuilder
         self.ex = Exchange(group)
         self.n, self.rank = self.ex.world, self.ex.rank
@@ -83,9 +83,75 @@ class ShardedBuilder:
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
         self._send = self._counts = None
         self.exchange_bytes = 0
+        # "peer": the scatter pass stores tuples straight into the owners' receive buffers over NVLink peer
+        # mappings (exchange fused into the kernel); "nccl": pack locally, then grouped send/recv
+        self.exchange = exchange if self.n > 1 else "nccl"
+        self._recv_ptr = None
+        self._recv_cap = 0
+        self._peer_ptrs = None
 
     def close(self):
+        self._release_peers()
         self.b.close()
+
+    # ---- peer receive buffers ----
+    def _release_peers(self):
+        if self._peer_ptrs is not None:
+            for q, p in enumerate(self._peer_ptrs):
+                if q != self.rank and p:
+                    self.b.peer_close(p)
+            self._peer_ptrs = None
+        if self._recv_ptr:
+            self.b.peer_free(self._recv_ptr)
+            self._recv_ptr = None
+            self._recv_cap = 0
+
+    def _ensure_peers(self, cap_tuples):
+        """(re)allocate the receive buffers so that every rank can take cap_tuples; collective"""
+        want = torch.tensor([int(cap_tuples)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=self.ex.group)
+        cap = int(want.item())
+        if cap <= self._recv_cap:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.ex.group)
+        self._release_peers()
+        cap = int(cap * 1.25) + 4096
+        self._recv_ptr, handle = self.b.peer_alloc(cap * self.width * 8)
+        self._recv_cap = cap
+        handles = [None] * self.n
+        dist.all_gather_object(handles, handle, group=self.ex.group)
+        self._peer_ptrs = [self._recv_ptr if q == self.rank else self.b.peer_open(handles[q]) for q in range(self.n)]
+        self._d_ptrs = torch.tensor(self._peer_ptrs, dtype=torch.int64, device=self.device)
+        dist.barrier(group=self.ex.group)
+
+    def _add_reads_peer(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index):
+        from .graph import torch_stream_handle
+        stream = torch_stream_handle(self.device)
+        if self._counts is None:
+            self._counts = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        # pass 1: how many tuples this block has for every owner
+        self.b.exchange_count_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, self.n,
+                                     self._counts.data_ptr(), stream=stream)
+        allc = torch.empty(self.n * self.n, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allc, self._counts, group=self.ex.group)
+        allc = allc.view(self.n, self.n)                       # [source rank][owner]
+        base = allc[: self.rank].sum(dim=0)                    # tuples of lower ranks ahead of mine, per owner
+        recv_total = int(allc[:, self.rank].sum().item())
+        self._ensure_peers(recv_total)
+        d_base = base.contiguous()
+        # everybody is done with the previous content of the receive buffers before anybody overwrites them
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.ex.group)
+        # pass 2: regenerate the occurrences and store every tuple into its owner's buffer over NVLink
+        self.b.exchange_scatter_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
+                                       self.n, self._d_ptrs.data_ptr(), d_base.data_ptr(), stream=stream)
+        torch.cuda.synchronize(self.device)                    # my stores have landed ...
+        dist.barrier(group=self.ex.group)                      # ... and so have everybody else's
+        sc = self._counts.cpu().tolist()
+        self.exchange_bytes += (sum(sc) - sc[self.rank]) * self.width * 8
+        self.b.insert_tuples_device(self._recv_ptr, recv_total, stream=stream)
+        return recv_total
 
     def _buffers(self, capacity):
         need = capacity * self.width
@@ -97,6 +163,8 @@ class ShardedBuilder:
                          first_read_index, n_occ_upper=None):
         """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
         total_bases bounds the tuple count)"""
+        if self.exchange == "peer":
+            return self._add_reads_peer(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
         from .graph import torch_stream_handle
         stream = torch_stream_handle(self.device)
         cap = int(total_bases)

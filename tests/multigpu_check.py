@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reads", type=int, default=200_000)
     ap.add_argument("--K", type=int, default=31)
     ap.add_argument("--slots", type=int, default=12_000_000)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     a = ap.parse_args()
     import dbg_assembly_b200 as dbg
     from dbg_assembly_b200 import synth
@@ -41,7 +42,7 @@ def main():
     synth.reads_device(p, first, per, d_bases.data_ptr(), device=local)
     d_offs = torch.arange(per + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
-    sb = ShardedBuilder(K=a.K, max_read_len=L, init_slots=a.slots, device=local)
+    sb = ShardedBuilder(K=a.K, max_read_len=L, init_slots=a.slots, device=local, exchange=a.exchange)
     from dbg_assembly_b200.graph import torch_stream_handle
     sb.b.set_stream(torch_stream_handle(dev))
     # two blocks per rank, to exercise repeated exchanges
@@ -99,7 +100,7 @@ def main():
             ok, msg = False, str(ex)
         print(json.dumps({"multigpu_check": "ok" if ok else "FAILED", "n_gpus": world, "K": a.K, "reads": per * world,
                           "nodes": int(len(kk)) + 1, "occurrences": st["global_occurrences"], "detail": msg,
-                          "exchange_bytes_rank0": sb.exchange_bytes}))
+                          "exchange_bytes_rank0": sb.exchange_bytes, "exchange": sb.exchange}))
         o.close()
     dist.barrier()
     sb.close()
