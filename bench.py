@@ -392,7 +392,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; numbers at scale != 1 are not the metric)")
     ap.add_argument("--init-g", type=float, default=None, help="override the table size -i (experiments only)")
     ap.add_argument("--ref-sample-reads", type=int, default=400_000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_sliced", "nccl"],
                     help="multi-GPU: 'peer' = scatter kernel stores tuples into the owners' buffers over NVLink (fused), 'nccl' = pack + send/recv")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-micro", action="store_true")

@@ -53,7 +53,7 @@ SYMBOLS = [
     "dbg_find_next_prime", "dbg_hash_code", "dbg_hash_code_wide", "dbg_strerror", "dbg_last_error",
     "dbg_device_count", "dbg_host_alloc", "dbg_host_free", "dbg_create", "dbg_destroy", "dbg_submit_reads",
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
-    "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device",
+    "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device", "dbg_insert_sliced_device", "dbg_partition_info",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
     "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
@@ -95,8 +95,10 @@ def load(build_if_missing: bool = True):
         "dbg_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "dbg_peer_close": (C.c_int, [vp, vp]),
         "dbg_peer_free": (C.c_int, [vp, vp]),
-        "dbg_exchange_count_device": (C.c_int, [vp, vp, vp, u64, u64, u64, i32, vp, vp]),
-        "dbg_exchange_scatter_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, i32, vp, vp, vp]),
+        "dbg_exchange_count_device": (C.c_int, [vp, vp, vp, u64, u64, u64, i32, i32, vp, vp]),
+        "dbg_exchange_scatter_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, i32, i32, vp, vp, vp]),
+        "dbg_insert_sliced_device": (C.c_int, [vp, vp, u64, vp, vp]),
+        "dbg_partition_info": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(i32)]),
         "dbg_tuple_bytes": (C.c_int, [vp]),
         "dbg_get_polyA_counts": (C.c_int, [vp, vp]),
         "dbg_set_polyA_counts": (C.c_int, [vp, vp]),

@@ -276,8 +276,13 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     // prefetched and the tuple stream fit the 126 MB L2 with room to spare
     c->part_shift = c->wide ? 18 : 19;
     if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
-    while (((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift) > 4096) c->part_shift++;
-    c->n_buckets = (uint32_t)((c->n_local + (1ull << c->part_shift) - 1) >> c->part_shift);
+    // slice geometry from the (rank-independent) shard size, so that every rank of a sharded build agrees on it
+    // (the last shard may be smaller: its trailing slices just stay empty)
+    {
+        const uint64_t uni = c->shard_size + MARGIN_SLOTS;
+        while (((uni + (1ull << c->part_shift) - 1) >> c->part_shift) > 4096) c->part_shift++;
+        c->n_buckets = (uint32_t)((uni + (1ull << c->part_shift) - 1) >> c->part_shift);
+    }
     *out = c;   // from here on the caller can dbg_destroy() after a failure
 
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -287,7 +292,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_boffs, ((size_t)c->n_buckets + 1) * sizeof(u64)));
-    CU_TRY(cudaMalloc(&c->d_roffs, 65 * sizeof(u64)));
+    CU_TRY(cudaMalloc(&c->d_roffs, (64 * 1024 + 1) * sizeof(u64)));     // owner (x slice) offsets of the exchange
     return clear_table(c);
 }
 
@@ -375,7 +380,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
 {
     const uint32_t nb = c->n_buckets;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
-    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.div = 0; cs.div_M = 0; cs.n_buckets = nb;
+    PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.div = 0; cs.div_M = 0; cs.nb_local = 0; cs.n_buckets = nb;
     cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.dst_ptrs = nullptr; cs.dst_base = nullptr; cs.roffs = nullptr; cs.hist = nullptr; cs.base = nullptr;
     a.count_stats = 0;
     int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
@@ -388,7 +393,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_boffs);
     CU_TRY(cudaGetLastError());
     c->launches += 3;
-    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.n_buckets = nb;
+    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.nb_local = 0; ss.n_buckets = nb;
     ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.dst_ptrs = nullptr; ss.dst_base = nullptr; ss.roffs = nullptr; ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
     rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
@@ -408,20 +413,21 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
 // phase 1 = count + scan (-> per-owner sizes in d_counts), phase 2 = scatter; phase 2 either packs locally
 // (d_tuples) or stores straight into the owners' receive buffers over NVLink peer mappings (fused exchange).
 template <bool WIDE>
-static void fill_rank_sink(dbg_ctx *c, PartitionSink<WIDE, 0> &cs, int n_parts)
+static void fill_rank_sink(dbg_ctx *c, PartitionSink<WIDE, 0> &cs, int n_parts, uint32_t nb_local = 0)
 {
     const uint64_t div = (c->P + n_parts - 1) / n_parts;
-    cs.t = view_of(c); cs.shift = 0; cs.div = div; cs.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div);
-    cs.n_buckets = (uint32_t)n_parts; cs.matrix = c->d_matrix; cs.tuples = nullptr;
+    cs.t = view_of(c); cs.shift = nb_local ? c->part_shift : 0; cs.div = div; cs.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div);
+    cs.nb_local = nb_local;
+    cs.n_buckets = nb_local ? (uint32_t)n_parts * nb_local : (uint32_t)n_parts; cs.matrix = c->d_matrix; cs.tuples = nullptr;
     cs.dst_ptrs = nullptr; cs.dst_base = nullptr; cs.roffs = nullptr; cs.hist = nullptr; cs.base = nullptr;
 }
 
 template <bool WIDE>
-static int run_rank_count(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, u64 *d_counts, cudaStream_t s)
+static int run_rank_count(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, u64 *d_counts, cudaStream_t s, uint32_t nb_local = 0)
 {
-    const uint32_t nb = (uint32_t)n_parts;
+    const uint32_t nb = nb_local ? (uint32_t)n_parts * nb_local : (uint32_t)n_parts;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
-    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts);
+    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts, nb_local);
     a.count_stats = 0;
     int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
     if (rc) return rc;
@@ -432,7 +438,7 @@ static int run_rank_count(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_part
     CU_TRY(cudaGetLastError());
     k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_roffs);
     CU_TRY(cudaGetLastError());
-    k_offsets_to_counts<<<1, 64, 0, s>>>(c->d_roffs, nb, d_counts);
+    k_offsets_to_counts<<<(nb + 255) / 256, 256, 0, s>>>(c->d_roffs, nb, d_counts);
     CU_TRY(cudaGetLastError());
     c->launches += 4;
     return DBG_OK;
@@ -440,14 +446,14 @@ static int run_rank_count(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_part
 
 template <bool WIDE>
 static int run_rank_scatter(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_parts, void *d_tuples, u64 *const *d_dst_ptrs,
-                            const u64 *d_dst_base, cudaStream_t s)
+                            const u64 *d_dst_base, cudaStream_t s, uint32_t nb_local = 0)
 {
-    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts);
-    PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = 0; ss.div = cs.div; ss.div_M = cs.div_M; ss.n_buckets = cs.n_buckets;
+    PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts, nb_local);
+    PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = cs.shift; ss.div = cs.div; ss.div_M = cs.div_M; ss.nb_local = cs.nb_local; ss.n_buckets = cs.n_buckets;
     ss.matrix = c->d_matrix; ss.tuples = (u64 *)d_tuples; ss.dst_ptrs = d_dst_ptrs; ss.dst_base = d_dst_base; ss.roffs = c->d_roffs;
     ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
-    return launch_build<WIDE>(c, a, ss, n_chunks, s, (uint32_t)n_parts);
+    return launch_build<WIDE>(c, a, ss, n_chunks, s, ss.n_buckets);
 }
 
 template <bool WIDE>
@@ -678,12 +684,16 @@ extern "C" int dbg_extract_tuples_device(dbg_ctx *c, const char *d_bases, const 
 
 // ---- fused exchange over NVLink peer memory ---------------------------------------------------------
 static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_offs, uint64_t n_reads, uint64_t first_base,
-                      uint64_t total_bases, uint64_t read_index0, int n_parts, u64 *d_counts, u64 *const *d_dst_ptrs,
+                      uint64_t total_bases, uint64_t read_index0, int n_parts, int by_slice, u64 *d_counts, u64 *const *d_dst_ptrs,
                       const u64 *d_dst_base, cudaStream_t s)
 {
     if (n_parts < 1 || n_parts > 64) return set_err(DBG_ERR_INVALID, "n_parts outside 1..64");
+    // by_slice: buckets = (owner, 16-MB table slice of the owner); every shard has the same slice count as this one
+    const uint32_t nb_local = by_slice ? c->n_buckets : 0;
+    const uint32_t nb_total = nb_local ? (uint32_t)n_parts * nb_local : (uint32_t)n_parts;
+    if (nb_total > 64 * 1024 || 2 * (size_t)nb_total * sizeof(u32) > 160 * 1024) return set_err(DBG_ERR_INVALID, "too many exchange buckets (%u)", nb_total);
     if (n_reads == 0 || total_bases == 0) {
-        if (phase == 1) CU_TRY(cudaMemsetAsync(d_counts, 0, n_parts * sizeof(u64), s));
+        if (phase == 1) CU_TRY(cudaMemsetAsync(d_counts, 0, nb_total * sizeof(u64), s));
         return DBG_OK;
     }
     uint64_t abase = first_base & ~15ull;
@@ -692,7 +702,7 @@ static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_o
     if (n_chunks > 0x7fffffffull || total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
     int rc = ensure_chunks(c, n_chunks);
     if (rc) return rc;
-    if (ensure_matrix(c, n_chunks, (uint32_t)n_parts) != DBG_OK) return set_err(DBG_ERR_NOMEM, "partition offsets");
+    if (ensure_matrix(c, n_chunks, nb_total) != DBG_OK) return set_err(DBG_ERR_NOMEM, "partition offsets");
     EvPair ev;
     rc = ev_begin(c, s, &ev);
     if (rc) return rc;
@@ -705,10 +715,10 @@ static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_o
         k_chunk_first<<<gb, 256, 0, s>>>(d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
         CU_TRY(cudaGetLastError());
         c->launches++;
-        rc = c->wide ? run_rank_count<true>(c, a, n_chunks, n_parts, d_counts, s) : run_rank_count<false>(c, a, n_chunks, n_parts, d_counts, s);
+        rc = c->wide ? run_rank_count<true>(c, a, n_chunks, n_parts, d_counts, s, nb_local) : run_rank_count<false>(c, a, n_chunks, n_parts, d_counts, s, nb_local);
     } else {
-        rc = c->wide ? run_rank_scatter<true>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s)
-                     : run_rank_scatter<false>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s);
+        rc = c->wide ? run_rank_scatter<true>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s, nb_local)
+                     : run_rank_scatter<false>(c, a, n_chunks, n_parts, nullptr, d_dst_ptrs, d_dst_base, s, nb_local);
         c->reads_total += n_reads;
     }
     if (rc) return rc;
@@ -718,21 +728,21 @@ static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_o
 }
 
 extern "C" int dbg_exchange_count_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
-                                         uint64_t total_bases, int32_t n_parts, uint64_t *d_counts, void *stream)
+                                         uint64_t total_bases, int32_t n_parts, int32_t by_slice, uint64_t *d_counts, void *stream)
 {
     if (!c || !d_counts) return set_err(DBG_ERR_INVALID, "dbg_exchange_count_device: NULL argument");
     CU_TRY(cudaSetDevice(c->device));
-    return rank_phase(c, 1, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, 0, n_parts, (u64 *)d_counts, nullptr, nullptr,
+    return rank_phase(c, 1, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, 0, n_parts, by_slice, (u64 *)d_counts, nullptr, nullptr,
                       stream ? (cudaStream_t)stream : c->stream);
 }
 
 extern "C" int dbg_exchange_scatter_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
-                                           uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
-                                           const uint64_t *d_dst_base, void *stream)
+                                           uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, int32_t by_slice,
+                                           void *const *d_dst_ptrs, const uint64_t *d_dst_base, void *stream)
 {
     if (!c || !d_dst_ptrs || !d_dst_base) return set_err(DBG_ERR_INVALID, "dbg_exchange_scatter_device: NULL argument");
     CU_TRY(cudaSetDevice(c->device));
-    return rank_phase(c, 2, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, first_read_index, n_parts, nullptr,
+    return rank_phase(c, 2, d_bases, (const u64 *)d_offs, n_reads, first_base, total_bases, first_read_index, n_parts, by_slice, nullptr,
                       (u64 *const *)d_dst_ptrs, (const u64 *)d_dst_base, stream ? (cudaStream_t)stream : c->stream);
 }
 
@@ -828,6 +838,36 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     }
     CU_TRY(cudaEventRecord(ev.b, s));
     c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+// tuples already in this shard's slice order (fused exchange with by_slice=1): d_slice_offs[n_slices+1] = start of
+// every slice's tuples; goes straight to the bucketed insert through L2-resident slices
+extern "C" int dbg_insert_sliced_device(dbg_ctx *c, const void *d_tuples, uint64_t n, const uint64_t *d_slice_offs, void *stream)
+{
+    if (!c || (!d_tuples && n) || !d_slice_offs) return set_err(DBG_ERR_INVALID, "dbg_insert_sliced_device: NULL argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
+    if (n == 0) return DBG_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemcpyAsync(c->d_boffs, d_slice_offs, ((size_t)c->n_buckets + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    EvPair ev;
+    int rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    ev.slot = 6;
+    rc = insert_any(c, d_tuples, n, nullptr, s, true);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    c->part_blocks++;
+    return DBG_OK;
+}
+
+extern "C" int dbg_partition_info(const dbg_ctx *c, uint32_t *n_slices, int32_t *slice_shift)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    if (n_slices) *n_slices = c->n_buckets;
+    if (slice_shift) *slice_shift = c->part_shift;
     return DBG_OK;
 }
 

@@ -161,7 +161,8 @@ struct PartitionSink {
     static constexpr int RUN = G;
     TableView t;
     int shift;         // bucket = (home - lo) >> shift          (table slices), or, when div != 0,
-    u64 div, div_M;    // bucket = home / div                    (owner ranks of the multi-GPU exchange)
+    u64 div, div_M;    // bucket = home / div                    (owner ranks of the multi-GPU exchange), or, when
+    u32 nb_local;      // nb_local != 0: owner * nb_local + ((home - owner*div) >> shift)   (owner AND its table slice)
     u32 n_buckets;
     u32 *matrix;       // [n_chunks][n_buckets]: counts after pass 1, write offsets after the scan
     u64 *tuples;
@@ -199,8 +200,10 @@ struct PartitionSink {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
                     u64 home = mod_P(hh, t.P, t.M);
                     u32 bkt;
-                    if (div) { bkt = (u32)__umul64hi(home, div_M); if ((u64)(bkt + 1) * div <= home) bkt++; }
-                    else bkt = (u32)((home - t.lo) >> shift);
+                    if (div) {
+                        bkt = (u32)__umul64hi(home, div_M); if ((u64)(bkt + 1) * div <= home) bkt++;
+                        if (nb_local) bkt = bkt * nb_local + (u32)((home - (u64)bkt * div) >> shift);
+                    } else bkt = (u32)((home - t.lo) >> shift);
                     u32 rank = atomicAdd(&hist[bkt], 1u);
                     if (MODE == 1) {
                         u64 pos = (u64)base[bkt] + rank;
@@ -503,9 +506,9 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
     float ratio = 0.f;
     if (boffs) {
         b0 = __ldg(boffs); b1 = __ldg(boffs + 1);
-        if (n_buckets > 1 && b1 > b0) {
+        if (n_buckets > 1 && b1 > b0 && ((u64)1 << shift) < t.n_local) {
             u64 slice_n = (u64)1 << shift;
-            if (2 * slice_n > t.n_local) slice_n = t.n_local > slice_n ? t.n_local - slice_n : 0;
+            if (2 * slice_n > t.n_local) slice_n = t.n_local - slice_n;
             ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);
         }
     }
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
                 // entered a new bucket: its tuple span and the lines-per-tuple ratio of the NEXT slice (rare path)
                 while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
                 ratio = 0.f;
-                if (b + 1 < n_buckets && b1 > b0) {
+                if (b + 1 < n_buckets && b1 > b0 && ((u64)(b + 1) << shift) < t.n_local) {
                     const u64 slice_lo = (u64)(b + 1) << shift;
                     u64 slice_n = (u64)1 << shift;
                     if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;

@@ -134,15 +134,24 @@ class DBGBuilder:
     def peer_free(self, ptr):
         capi.check(self.L.dbg_peer_free(self.h, ptr), "dbg_peer_free")
 
-    def exchange_count_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, n_parts, d_counts_ptr, stream=None):
+    def exchange_count_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, n_parts, d_counts_ptr, by_slice=False,
+                              stream=None):
         capi.check(self.L.dbg_exchange_count_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
-                                                    int(n_parts), d_counts_ptr, stream), "dbg_exchange_count_device")
+                                                    int(n_parts), int(bool(by_slice)), d_counts_ptr, stream), "dbg_exchange_count_device")
 
     def exchange_scatter_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index, n_parts,
-                                d_dst_ptrs_ptr, d_dst_base_ptr, stream=None):
+                                d_dst_ptrs_ptr, d_dst_base_ptr, by_slice=False, stream=None):
         capi.check(self.L.dbg_exchange_scatter_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
-                                                      int(first_read_index), int(n_parts), d_dst_ptrs_ptr, d_dst_base_ptr, stream),
-                   "dbg_exchange_scatter_device")
+                                                      int(first_read_index), int(n_parts), int(bool(by_slice)), d_dst_ptrs_ptr,
+                                                      d_dst_base_ptr, stream), "dbg_exchange_scatter_device")
+
+    def insert_sliced_device(self, d_tuples_ptr, n, d_slice_offs_ptr, stream=None):
+        capi.check(self.L.dbg_insert_sliced_device(self.h, d_tuples_ptr, int(n), d_slice_offs_ptr, stream), "dbg_insert_sliced_device")
+
+    def partition_info(self):
+        n, sh = C.c_uint32(0), C.c_int32(0)
+        capi.check(self.L.dbg_partition_info(self.h, C.byref(n), C.byref(sh)), "dbg_partition_info")
+        return n.value, sh.value
 
     def insert_tuples_device(self, d_tuples_ptr, n, stream=None):
         capi.check(self.L.dbg_insert_tuples_device(self.h, d_tuples_ptr, int(n), stream), "dbg_insert_tuples_device")

@@ -126,31 +126,47 @@ class ShardedBuilder:
         dist.barrier(group=self.ex.group)
 
     def _add_reads_peer(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index):
+        """fused exchange.  "peer": exchange buckets = owners; stores of one CTA go to n streams, so NVLink sees long
+        contiguous runs, and the owner re-partitions what it received by table slice.  "peer_sliced": buckets =
+        (owner, slice): the receive buffer arrives in slice order and goes straight to the bucketed insert, but the
+        16-B stores scatter over n * n_slices streams (measured slower over NVLink: short packets)."""
         from .graph import torch_stream_handle
         stream = torch_stream_handle(self.device)
-        if self._counts is None:
-            self._counts = torch.zeros(self.n, dtype=torch.int64, device=self.device)
-        # pass 1: how many tuples this block has for every owner
-        self.b.exchange_count_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, self.n,
-                                     self._counts.data_ptr(), stream=stream)
-        allc = torch.empty(self.n * self.n, dtype=torch.int64, device=self.device)
+        n, dev = self.n, self.device
+        sliced = self.exchange == "peer_sliced"
+        nbl = self.b.partition_info()[0] if sliced else 1      # table slices per shard (same on every rank)
+        nbt = n * nbl                                          # exchange buckets, owner-major
+        if self._counts is None or self._counts.numel() != nbt:
+            self._counts = torch.zeros(nbt, dtype=torch.int64, device=dev)
+        # pass 1: how many tuples this block has for every bucket
+        self.b.exchange_count_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, n,
+                                     self._counts.data_ptr(), by_slice=sliced, stream=stream)
+        allc = torch.empty(n * nbt, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, self._counts, group=self.ex.group)
-        allc = allc.view(self.n, self.n)                       # [source rank][owner]
-        base = allc[: self.rank].sum(dim=0)                    # tuples of lower ranks ahead of mine, per owner
-        recv_total = int(allc[:, self.rank].sum().item())
+        allc = allc.view(n, nbt)                                   # [source rank][bucket]
+        col = allc.sum(dim=0).view(n, nbl)                         # tuples per (owner, slice) over all sources
+        start = (torch.cumsum(col, dim=1) - col)                   # start of every slice inside its owner's buffer
+        d_base = (start.reshape(-1) + allc[: self.rank].sum(dim=0)).contiguous()   # + tuples of lower ranks for that bucket
+        recv_total = int(col[self.rank].sum().item())
         self._ensure_peers(recv_total)
-        d_base = base.contiguous()
+        d_ptrs = self._d_ptrs.repeat_interleave(nbl).contiguous() if sliced else self._d_ptrs
         # everybody is done with the previous content of the receive buffers before anybody overwrites them
-        torch.cuda.synchronize(self.device)
+        torch.cuda.synchronize(dev)
         dist.barrier(group=self.ex.group)
         # pass 2: regenerate the occurrences and store every tuple into its owner's buffer over NVLink
         self.b.exchange_scatter_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
-                                       self.n, self._d_ptrs.data_ptr(), d_base.data_ptr(), stream=stream)
-        torch.cuda.synchronize(self.device)                    # my stores have landed ...
-        dist.barrier(group=self.ex.group)                      # ... and so have everybody else's
-        sc = self._counts.cpu().tolist()
-        self.exchange_bytes += (sum(sc) - sc[self.rank]) * self.width * 8
-        self.b.insert_tuples_device(self._recv_ptr, recv_total, stream=stream)
+                                       n, d_ptrs.data_ptr(), d_base.data_ptr(), by_slice=sliced, stream=stream)
+        torch.cuda.synchronize(dev)                                # my stores have landed ...
+        dist.barrier(group=self.ex.group)                          # ... and so have everybody else's
+        mine = self._counts.view(n, nbl).sum(dim=1).cpu().tolist()
+        self.exchange_bytes += (sum(mine) - mine[self.rank]) * self.width * 8
+        if sliced:
+            slice_offs = torch.cat([start[self.rank], col[self.rank].sum().reshape(1)]).contiguous()
+            self.b.insert_sliced_device(self._recv_ptr, recv_total, slice_offs.data_ptr(), stream=stream)
+            self._keep = (slice_offs, d_ptrs, d_base)
+        else:
+            self.b.insert_tuples_device(self._recv_ptr, recv_total, stream=stream)
+            self._keep = (d_ptrs, d_base)
         return recv_total
 
     def _buffers(self, capacity):
@@ -163,7 +179,7 @@ class ShardedBuilder:
                          first_read_index, n_occ_upper=None):
         """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
         total_bases bounds the tuple count)"""
-        if self.exchange == "peer":
+        if self.exchange in ("peer", "peer_sliced"):
             return self._add_reads_peer(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
         from .graph import torch_stream_handle
         stream = torch_stream_handle(self.device)

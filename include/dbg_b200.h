@@ -120,19 +120,27 @@ int  dbg_extract_tuples_device(dbg_ctx *ctx, const char *d_bases, const uint64_t
 /* FUSED exchange over NVLink peer memory (one process per GPU): instead of packing tuples locally and handing them to
  * a collective, the scatter pass stores every tuple straight into its OWNER's receive buffer.
  *   dbg_peer_alloc / dbg_peer_open : a cudaMalloc'ed receive buffer + its 64-byte cudaIpcMemHandle; peers open it
- *   dbg_exchange_count_device      : pass 1 (count + scan); d_counts[n_parts] = tuples this block has for each owner
- *   (caller all-gathers the counts and derives, for every owner q, dst_base[q] = sum of the counts of lower ranks)
- *   dbg_exchange_scatter_device    : pass 2 on the SAME block; tuple for owner q -> d_dst_ptrs[q][dst_base[q] + k]
- * The caller synchronises (stream sync + barrier) before the owners insert. */
+ *   dbg_exchange_count_device      : pass 1 (count + scan); d_counts[b] = tuples this block has for exchange bucket b.
+ *                                    by_slice = 0: one bucket per owner (n_parts buckets);
+ *                                    by_slice = 1: one bucket per (owner, 16-MB table slice of the owner):
+ *                                    n_parts * n_slices buckets (dbg_partition_info), owner-major
+ *   (caller all-gathers the counts and derives dst_base[b] = start of bucket b inside its owner's buffer + the
+ *    counts of lower ranks for b)
+ *   dbg_exchange_scatter_device    : pass 2 on the SAME block; tuple of bucket b -> d_dst_ptrs[b][dst_base[b] + k]
+ * The caller synchronises (stream sync + barrier) before the owners insert: dbg_insert_tuples_device for by_slice=0
+ * (re-partitions by slice first), dbg_insert_sliced_device for by_slice=1 (the buffer already is in slice order). */
 int  dbg_peer_alloc(dbg_ctx *ctx, uint64_t bytes, void **d_ptr, uint8_t handle[64]);
 int  dbg_peer_open(dbg_ctx *ctx, const uint8_t handle[64], void **d_ptr);
 int  dbg_peer_close(dbg_ctx *ctx, void *d_ptr);
 int  dbg_peer_free(dbg_ctx *ctx, void *d_ptr);
 int  dbg_exchange_count_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
-                               uint64_t first_base, uint64_t total_bases, int32_t n_parts, uint64_t *d_counts, void *stream);
+                               uint64_t first_base, uint64_t total_bases, int32_t n_parts, int32_t by_slice,
+                               uint64_t *d_counts, void *stream);
 int  dbg_exchange_scatter_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
                                  uint64_t first_base, uint64_t total_bases, uint64_t first_read_index, int32_t n_parts,
-                                 void *const *d_dst_ptrs, const uint64_t *d_dst_base, void *stream);
+                                 int32_t by_slice, void *const *d_dst_ptrs, const uint64_t *d_dst_base, void *stream);
+int  dbg_insert_sliced_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, const uint64_t *d_slice_offs, void *stream);
+int  dbg_partition_info(const dbg_ctx *ctx, uint32_t *n_slices, int32_t *slice_shift);
 /* Insert n tuples (all owned by this context's shard) produced by dbg_extract_tuples_device. */
 int  dbg_insert_tuples_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, void *stream);
 int  dbg_tuple_bytes(const dbg_ctx *ctx);               /* 16 or 32 */

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--reads", type=int, default=200_000)
     ap.add_argument("--K", type=int, default=31)
     ap.add_argument("--slots", type=int, default=12_000_000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_sliced", "nccl"])
     a = ap.parse_args()
     import dbg_assembly_b200 as dbg
     from dbg_assembly_b200 import synth
