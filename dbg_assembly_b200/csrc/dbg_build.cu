@@ -145,6 +145,7 @@ struct dbg_ctx {
     LayoutInfo *d_layout_info;
     LayoutRegion *d_regions;
     int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
+    int peer_unstaged;             // env DBG_B200_PEER_UNSTAGED=1: fused exchange stores tuples one by one (experiments)
     uint32_t layout_regions;
     void *d_out;
     u32 *d_nul32;
@@ -268,6 +269,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
     if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->peer_unstaged = getenv("DBG_B200_PEER_UNSTAGED") ? atoi(getenv("DBG_B200_PEER_UNSTAGED")) : 0;
     c->layout_mode = 0;
     if (const char *e = getenv("DBG_B200_LAYOUT")) c->layout_mode = strcmp(e, "global") == 0 ? 1 : 0;
     c->part_mode = 2;
@@ -323,11 +325,11 @@ extern "C" int dbg_reset(dbg_ctx *c)
 // build: launch helpers
 // ---------------------------------------------------------------------------------------------------
 static uint32_t stage_words_for(int R) { return (uint32_t)(((CB + ((R + 15) / 16) * 16) / 16 + 8 + 1) & ~1); }   // even: keeps sink smem 8-B aligned
-static size_t build_smem(uint32_t stage_words, uint32_t n_buckets)
+static size_t build_smem(uint32_t stage_words, uint32_t n_buckets, size_t extra_bytes = 0)
 {
     size_t words = (size_t)stage_words + MAXR + MAXR + 2;
     if (n_buckets) words += 2 * (size_t)n_buckets;   // hist + base (u32 each)
-    return words * sizeof(u32);
+    return words * sizeof(u32) + extra_bytes;
 }
 
 static int ensure_chunks(dbg_ctx *c, uint64_t n_chunks)
@@ -342,9 +344,10 @@ static int ensure_chunks(dbg_ctx *c, uint64_t n_chunks)
 }
 
 template <bool WIDE, class Sink>
-static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_chunks, cudaStream_t s, uint32_t n_buckets = 0)
+static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_chunks, cudaStream_t s, uint32_t n_buckets = 0,
+                        size_t extra_bytes = 0)
 {
-    size_t smem = build_smem(a.stage_words, n_buckets);
+    size_t smem = build_smem(a.stage_words, n_buckets, extra_bytes);
     if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_build<WIDE, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_build<WIDE, Sink><<<(unsigned)n_chunks, BLOCK, smem, s>>>(a, sink);
     CU_TRY(cudaGetLastError());
@@ -449,6 +452,13 @@ static int run_rank_scatter(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, int n_pa
                             const u64 *d_dst_base, cudaStream_t s, uint32_t nb_local = 0)
 {
     PartitionSink<WIDE, 0> cs; fill_rank_sink<WIDE>(c, cs, n_parts, nb_local);
+    if (d_dst_ptrs && nb_local == 0 && n_parts <= 32 && !c->peer_unstaged) {
+        // fused exchange, owner buckets: sort each round by owner in shared memory, copy out in contiguous runs
+        PeerStagedSink<WIDE> ps; ps.t = cs.t; ps.div = cs.div; ps.div_M = cs.div_M; ps.n_buckets = cs.n_buckets; ps.matrix = c->d_matrix;
+        ps.dst_ptrs = d_dst_ptrs; ps.dst_base = d_dst_base; ps.roffs = c->d_roffs; ps.cnt = nullptr; ps.base = nullptr; ps.stage = nullptr; ps.parity = 0;
+        a.count_stats = 1;
+        return launch_build<WIDE>(c, a, ps, n_chunks, s, 0, PeerStagedSink<WIDE>::smem_bytes());
+    }
     PartitionSink<WIDE, 1> ss; ss.t = cs.t; ss.shift = cs.shift; ss.div = cs.div; ss.div_M = cs.div_M; ss.nb_local = cs.nb_local; ss.n_buckets = cs.n_buckets;
     ss.matrix = c->d_matrix; ss.tuples = (u64 *)d_tuples; ss.dst_ptrs = d_dst_ptrs; ss.dst_base = d_dst_base; ss.roffs = c->d_roffs;
     ss.hist = nullptr; ss.base = nullptr;

@@ -232,6 +232,98 @@ struct PartitionSink {
     }
 };
 
+// Scatter pass of the FUSED multi-GPU exchange, owner buckets only (n_buckets = ranks <= 32).  Every round of
+// BLOCK*G occurrences is first sorted by owner in shared memory, then copied out with adjacent lanes writing
+// adjacent 16-B tuples: each owner receives contiguous runs (hundreds of bytes) instead of isolated 16-B stores,
+// which is what NVLink wants (a store per tuple straight from the generator reached only a fraction of the link
+// rate: every 16-B store became its own packet).
+template <bool WIDE>
+struct PeerStagedSink {
+    static constexpr int RUN = G;
+    static constexpr int TW = WIDE ? 4 : 2;            // u64 words per tuple
+    TableView t;
+    u64 div, div_M;
+    u32 n_buckets;
+    u32 *matrix;            // [n_chunks][n_buckets] write offsets (after the scan)
+    u64 *const *dst_ptrs;   // owner receive buffers (peer mappings)
+    const u64 *dst_base;    // first tuple index reserved for this rank in each owner's buffer
+    const u64 *roffs;       // this rank's packed start of each bucket (subtracted from the matrix offsets)
+    u32 *cnt;               // shared [2][32] round counts (ping-pong)
+    u32 *base;              // shared [32] running write offset per owner
+    u64 *stage;             // shared [BLOCK*G] tuples
+    u32 parity;
+
+    static __host__ __device__ size_t smem_bytes() { return (size_t)(3 * 32) * sizeof(u32) + (size_t)BLOCK * G * TW * sizeof(u64); }
+
+    __device__ __forceinline__ void init(u32 *extra)
+    {
+        cnt = extra; base = extra + 64;
+        stage = reinterpret_cast<u64 *>(extra + 96);
+        const u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
+        if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+        if (threadIdx.x < n_buckets) base[threadIdx.x] = (u32)((u64)row[threadIdx.x] - roffs[threadIdx.x] + dst_base[threadIdx.x]);
+        parity = 0;
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void consume(const Occ (&o)[RUN], int nv)
+    {
+        u32 *c = cnt + 32 * parity;
+        u32 bkt[RUN], rank[RUN];
+#pragma unroll
+        for (int g = 0; g < RUN; g++) {
+            bkt[g] = 0xffffffffu; rank[g] = 0;
+            if (g < nv) {
+                if ((o[g].klo | o[g].khi) == 0) {     // the k-mer-0 side node is accumulated here, once
+                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
+                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                } else {
+                    u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                    u64 home = mod_P(hh, t.P, t.M);
+                    u32 b = (u32)__umul64hi(home, div_M); if ((u64)(b + 1) * div <= home) b++;
+                    bkt[g] = b;
+                    rank[g] = atomicAdd(&c[b], 1u);
+                }
+            }
+        }
+        __syncthreads();                                   // round counted
+        u32 eoff[RUN] = {};                                // exclusive prefix of the round's counts at my owners
+        u32 total = 0;
+        for (u32 b = 0; b < n_buckets; b++) {
+#pragma unroll
+            for (int g = 0; g < RUN; g++) if (bkt[g] == b) eoff[g] = total;
+            total += c[b];
+        }
+#pragma unroll
+        for (int g = 0; g < RUN; g++) {
+            if (bkt[g] != 0xffffffffu) {
+                const u32 e = eoff[g] + rank[g];
+                u64 meta = (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb;
+                if (WIDE) { stage[4 * e] = o[g].klo; stage[4 * e + 1] = o[g].khi; stage[4 * e + 2] = meta; stage[4 * e + 3] = 0; }
+                else { stage[2 * e] = o[g].klo; stage[2 * e + 1] = meta; }
+            }
+        }
+        __syncthreads();                                   // round sorted by owner in shared memory
+        for (u32 e = threadIdx.x; e < total; e += BLOCK) {
+            u32 b = 0, lo = 0;
+            for (; b + 1 < n_buckets; b++) { const u32 cq = c[b]; if (e < lo + cq) break; lo += cq; }
+            const u64 pos = (u64)base[b] + (e - lo);
+            if (WIDE) {
+                ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(dst_ptrs[b]) + 2 * pos;
+                __stcg(dst, make_ulonglong2(stage[4 * e], stage[4 * e + 1]));
+                __stcg(dst + 1, make_ulonglong2(stage[4 * e + 2], 0ULL));
+            } else {
+                __stcg(reinterpret_cast<ulonglong2 *>(dst_ptrs[b]) + pos, make_ulonglong2(stage[2 * e], stage[2 * e + 1]));
+            }
+        }
+        __syncthreads();                                   // copied out: stage, base and this round's counts are free
+        if (threadIdx.x < n_buckets) { base[threadIdx.x] += c[threadIdx.x]; c[threadIdx.x] = 0; }
+        parity ^= 1;                                       // next round counts in the other slot while these reset
+    }
+
+    __device__ __forceinline__ void finish() {}
+};
+
 // column-wise exclusive scan of M[n_chunks][n_buckets] (+ per-bucket bases), three small kernels:
 //   1: tile sums  ts[tile][b] = sum of M[c][b] over the tile's chunks            grid (tiles, ceil(nb/256))
 //   2: per bucket: exclusive scan of ts over tiles, bucket totals -> boffs (exclusive over buckets), one CTA
