@@ -145,6 +145,7 @@ struct dbg_ctx {
     LayoutInfo *d_layout_info;
     LayoutRegion *d_regions;
     int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
+    int stage_cap;                 // env DBG_B200_STAGE_CAP: batch size of the staged scatter (-1 default, 0 off)
     int peer_unstaged;             // env DBG_B200_PEER_UNSTAGED=1: fused exchange stores tuples one by one (experiments)
     uint32_t layout_regions;
     void *d_out;
@@ -269,6 +270,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
     if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->stage_cap = getenv("DBG_B200_STAGE_CAP") ? atoi(getenv("DBG_B200_STAGE_CAP")) : -1;
     c->peer_unstaged = getenv("DBG_B200_PEER_UNSTAGED") ? atoi(getenv("DBG_B200_PEER_UNSTAGED")) : 0;
     c->layout_mode = 0;
     if (const char *e = getenv("DBG_B200_LAYOUT")) c->layout_mode = strcmp(e, "global") == 0 ? 1 : 0;
@@ -327,7 +329,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
 static uint32_t stage_words_for(int R) { return (uint32_t)(((CB + ((R + 15) / 16) * 16) / 16 + 8 + 1) & ~1); }   // even: keeps sink smem 8-B aligned
 static size_t build_smem(uint32_t stage_words, uint32_t n_buckets, size_t extra_bytes = 0)
 {
-    size_t words = (size_t)stage_words + MAXR + MAXR + 2;
+    size_t words = (size_t)stage_words + MAXR + MAXR + 2 + 3;   // + 16-byte alignment of the sink's part
     if (n_buckets) words += 2 * (size_t)n_buckets;   // hist + base (u32 each)
     return words * sizeof(u32) + extra_bytes;
 }
@@ -377,6 +379,21 @@ static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const 
     return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed);
 }
 
+// batch capacity (tuples) of the shared-memory staging of the scatter passes; 0 = store tuples one by one
+// (env DBG_B200_STAGE_CAP, experiments).  Must hold one round of BLOCK*G occurrences and index with 16 bits.
+static uint32_t stage_cap(const dbg_ctx *c, bool wide)
+{
+    uint32_t cap = c->stage_cap >= 0 ? (uint32_t)c->stage_cap : 2048u;
+    if (cap == 0) return 0;
+    if (cap < (uint32_t)BLOCK * G) cap = BLOCK * G;
+    if (cap > 32768) cap = 32768;
+    const size_t tb = wide ? 32 : 16;
+    // keep two CTAs per SM resident next to the build kernel's own shared memory
+    while (cap > (uint32_t)BLOCK * G && cap * tb + cap * 6 + (size_t)c->n_buckets * 12 > 98 * 1024) cap /= 2;
+    if (cap * tb + cap * 6 + (size_t)c->n_buckets * 12 > 150 * 1024) return 0;
+    return cap;
+}
+
 // radix-partitioned build of one device-resident block (see PartitionSink): count, scan, scatter, insert
 template <bool WIDE>
 static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t occ_upper, cudaStream_t s)
@@ -396,10 +413,18 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums, c->d_boffs);
     CU_TRY(cudaGetLastError());
     c->launches += 3;
-    PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.nb_local = 0; ss.n_buckets = nb;
-    ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.dst_ptrs = nullptr; ss.dst_base = nullptr; ss.roffs = nullptr; ss.hist = nullptr; ss.base = nullptr;
     a.count_stats = 1;
-    rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
+    const uint32_t cap = stage_cap(c, WIDE);
+    if (cap) {
+        // scatter through shared-memory batches copied out in bucket order (whole-sector runs)
+        StagedScatterSink<WIDE> st; st.t = view_of(c); st.shift = c->part_shift; st.n_buckets = nb; st.cap = cap;
+        st.matrix = c->d_matrix; st.tuples = c->d_tuples; st.filled = 0;
+        rc = launch_build<WIDE>(c, a, st, n_chunks, s, 0, StageBuf<WIDE>::bytes(cap, nb));
+    } else {
+        PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.nb_local = 0; ss.n_buckets = nb;
+        ss.matrix = c->d_matrix; ss.tuples = c->d_tuples; ss.dst_ptrs = nullptr; ss.dst_base = nullptr; ss.roffs = nullptr; ss.hist = nullptr; ss.base = nullptr;
+        rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
+    }
     if (rc) return rc;
     EvPair ev;                       // the insert kernel alone (ms[6]): the roofline's dominant kernel
     rc = ev_begin(c, s, &ev);
@@ -811,7 +836,14 @@ static int partition_tuples(dbg_ctx *c, const void *d_src, uint64_t n, cudaStrea
     CU_TRY(cudaGetLastError());
     k_part_scan3<<<g1, 256, 0, s>>>(c->d_matrix, n_rows, nb, c->d_tile_sums, c->d_boffs);
     CU_TRY(cudaGetLastError());
-    k_tuple_partition<WIDE, 1><<<(unsigned)n_rows, 256, smem, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
+    const size_t st_bytes = StageBuf<WIDE>::bytes(TP_TILE, nb);
+    if (c->stage_cap != 0 && st_bytes <= 200 * 1024) {
+        if (st_bytes > 48 * 1024)
+            CU_TRY(cudaFuncSetAttribute(k_tuple_scatter_staged<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
+        k_tuple_scatter_staged<WIDE><<<(unsigned)n_rows, 256, st_bytes, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
+    } else {
+        k_tuple_partition<WIDE, 1><<<(unsigned)n_rows, 256, smem, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
+    }
     CU_TRY(cudaGetLastError());
     c->launches += 5;
     return DBG_OK;

@@ -73,15 +73,28 @@ static __global__ void k_chunk_first(const u64 *__restrict__ offs, u64 n_reads, 
 // 256-bit request, claim an empty slot with a CAS (the only atomic with a return value, and only for NEW
 // keys), count with one fire-and-forget vector RED, keep the earliest ordinal with a RED.max.
 template <bool WIDE, bool TRACK>
+__device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p, NodeRegs n, u64 klo, u64 khi, u32 lb, u32 rb, u64 ord,
+                                             u32 &n_new, u32 &n_conf);
+
+template <bool WIDE, bool TRACK>
 __device__ __forceinline__ void insert_one(const TableView &t, u64 klo, u64 khi, u32 lb, u32 rb, u64 ord, u32 &n_new, u32 &n_conf)
 {
     typedef NodeT<WIDE> Nd;
     u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
     Nd *p = static_cast<Nd *>(t.nodes) + (mod_P(h, t.P, t.M) - t.lo);
+    NodeRegs n;
+    load_node(p, n);
+    insert_probe<WIDE, TRACK>(t, p, n, klo, khi, lb, rb, ord, n_new, n_conf);
+}
+
+// the probe loop, entered with the home slot's node already loaded (callers may have several loads in flight)
+template <bool WIDE, bool TRACK>
+__device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p, NodeRegs n, u64 klo, u64 khi, u32 lb, u32 rb, u64 ord,
+                                             u32 &n_new, u32 &n_conf)
+{
+    typedef NodeT<WIDE> Nd;
     Nd *const p_end = static_cast<Nd *>(t.nodes) + t.n_local;
     for (;;) {
-        NodeRegs n;
-        load_node(p, n);
         if ((n.klo | n.khi) == 0) {
             if (WIDE) {
                 u64 olo, ohi;
@@ -107,12 +120,14 @@ __device__ __forceinline__ void insert_one(const TableView &t, u64 klo, u64 khi,
         n_conf++;                                       // occupied by another key: next slot (DBGgraph.cpp:201-204)
         p++;
         if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); return; }
+        load_node(p, n);
     }
 }
 
 template <bool WIDE, bool TRACK>
 struct InsertSink {
     static constexpr int RUN = G;
+    static constexpr int MIN_BLOCKS = MIN_CTAS;
     TableView t;
     u32 n_new, n_conf;     // per-thread, reduced at kernel end
 
@@ -159,6 +174,7 @@ struct InsertSink {
 template <bool WIDE, int MODE>
 struct PartitionSink {
     static constexpr int RUN = G;
+    static constexpr int MIN_BLOCKS = MIN_CTAS;
     TableView t;
     int shift;         // bucket = (home - lo) >> shift          (table slices), or, when div != 0,
     u64 div, div_M;    // bucket = home / div                    (owner ranks of the multi-GPU exchange), or, when
@@ -232,6 +248,151 @@ struct PartitionSink {
     }
 };
 
+// Shared-memory staging for the scatter passes: tuples are appended to a batch in shared memory (with their bucket
+// and their rank inside the batch's bucket), and when the batch is full it is copied out IN BUCKET ORDER, adjacent
+// lanes writing adjacent tuples.  A bucket then receives runs of several tuples (whole 32-B sectors) per batch
+// instead of isolated 16-B half-sector stores -- the scattered-store transaction rate, not bandwidth, bounds the
+// scatter (profiles/README.md).
+template <bool WIDE>
+struct StageBuf {
+    static constexpr int TW = WIDE ? 4 : 2;   // u64 words per tuple
+    u64 *tup;            // [cap * TW]
+    unsigned short *bk;  // [cap] bucket of entry e
+    unsigned short *rk;  // [cap] rank of entry e inside its bucket (this batch)
+    unsigned short *idx; // [cap] entry at sorted position i
+    u32 *bh;             // [nb] batch counts
+    u32 *boff;           // [nb] exclusive scan of bh
+    u32 *base;           // [nb] running global write offset of this CTA per bucket
+    u32 *misc;           // [0] cursor, [1..8] warp totals
+    u32 cap, nb;
+
+    static __host__ __device__ size_t bytes(u32 cap, u32 nb)
+    {
+        return (size_t)cap * TW * 8 + (size_t)cap * 3 * 2 + (size_t)nb * 3 * 4 + 16 * 4;
+    }
+    __device__ __forceinline__ void carve(void *mem, u32 cap_, u32 nb_)
+    {
+        cap = cap_; nb = nb_;
+        tup = reinterpret_cast<u64 *>(mem);
+        bh = reinterpret_cast<u32 *>(tup + (size_t)cap * TW);
+        boff = bh + nb; base = boff + nb; misc = base + nb;
+        bk = reinterpret_cast<unsigned short *>(misc + 16);
+        rk = bk + cap; idx = rk + cap;
+    }
+    // all threads of the CTA; a __syncthreads() must separate the last append from this call; ends with one
+    __device__ __forceinline__ void flush(u64 *dst)
+    {
+        const u32 t = threadIdx.x, nthr = blockDim.x;
+        const u32 n = misc[0];
+        // exclusive scan of bh (nb <= 4096): a contiguous segment per thread, warp scan, warp totals
+        const u32 seg = (nb + nthr - 1) / nthr;
+        const u32 b0 = t * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
+        u32 sum = 0;
+        for (u32 b = b0; b < b1; b++) sum += bh[b];
+        u32 incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, d); if ((t & 31) >= (u32)d) incl += v; }
+        if ((t & 31) == 31) misc[1 + (t >> 5)] = incl;
+        __syncthreads();
+        u32 run = incl - sum;
+        for (u32 w = 0; w < (t >> 5); w++) run += misc[1 + w];
+        for (u32 b = b0; b < b1; b++) { boff[b] = run; run += bh[b]; }
+        __syncthreads();
+        for (u32 e = t; e < n; e += nthr) idx[boff[bk[e]] + rk[e]] = (unsigned short)e;
+        __syncthreads();
+        for (u32 i = t; i < n; i += nthr) {
+            const u32 e = idx[i], b = bk[e];
+            const u64 pos = (u64)base[b] + (i - boff[b]);
+            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(tup);
+            if (WIDE) {
+                ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + 2 * pos;
+                __stcg(d, q[2 * e]);
+                __stcg(d + 1, q[2 * e + 1]);
+            } else {
+                __stcg(reinterpret_cast<ulonglong2 *>(dst) + pos, q[e]);
+            }
+        }
+        __syncthreads();
+        for (u32 b = t; b < nb; b += nthr) { base[b] += bh[b]; bh[b] = 0; }
+        if (t == 0) misc[0] = 0;
+        __syncthreads();
+    }
+    // append one tuple at entry e (reserved by the caller)
+    __device__ __forceinline__ void put(u32 e, u32 b, u64 klo, u64 khi, u64 meta)
+    {
+        ulonglong2 *q = reinterpret_cast<ulonglong2 *>(tup);          // tup is 16-B aligned: one 128-bit store per half
+        if (WIDE) { q[2 * e] = make_ulonglong2(klo, khi); q[2 * e + 1] = make_ulonglong2(meta, 0ULL); }
+        else q[e] = make_ulonglong2(klo, meta);
+        bk[e] = (unsigned short)b;
+        rk[e] = (unsigned short)atomicAdd(&bh[b], 1u);
+    }
+};
+
+// scatter pass of the single-GPU partitioned build through the staging above (slice buckets)
+template <bool WIDE>
+struct StagedScatterSink {
+    static constexpr int RUN = G;
+    static constexpr int MIN_BLOCKS = 3;           // <= 85 registers: three CTAs per SM next to a 2048-tuple batch
+    TableView t;
+    int shift;
+    u32 n_buckets, cap;
+    u32 *matrix;
+    u64 *tuples;
+    StageBuf<WIDE> sb;
+    u32 filled;
+
+    __device__ __forceinline__ void init(u32 *extra)
+    {
+        filled = 0;
+        sb.carve(extra, cap, n_buckets);
+        const u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
+        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) { sb.bh[b] = 0; sb.base[b] = row[b]; }
+        if (threadIdx.x == 0) sb.misc[0] = 0;
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void consume(const Occ (&o)[RUN], int nv)
+    {
+        // `filled` is a block-uniform upper bound of the batch cursor kept in registers (never read the shared
+        // cursor to decide: a fast warp may already have bumped it for this round)
+        if (filled + BLOCK * RUN > sb.cap) { __syncthreads(); sb.flush(tuples); filled = 0; }
+        filled += BLOCK * RUN;
+        u32 bkt[RUN];
+        u32 mine = 0;
+#pragma unroll
+        for (int g = 0; g < RUN; g++) {
+            bkt[g] = 0xffffffffu;
+            if (g < nv) {
+                if ((o[g].klo | o[g].khi) == 0) {
+                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
+                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                } else {
+                    u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
+                    bkt[g] = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
+                    mine++;
+                }
+            }
+        }
+        // reserve entries: warp-aggregated bump of the batch cursor
+        u32 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, d); if ((threadIdx.x & 31) >= (u32)d) incl += v; }
+        u32 wbase = 0;
+        if ((threadIdx.x & 31) == 31 && incl) wbase = atomicAdd(&sb.misc[0], incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        u32 e = wbase + incl - mine;
+#pragma unroll
+        for (int g = 0; g < RUN; g++)
+            if (bkt[g] != 0xffffffffu) sb.put(e++, bkt[g], o[g].klo, o[g].khi, (o[g].ord << 8) | (o[g].rb << 4) | o[g].lb);
+    }
+
+    __device__ __forceinline__ void finish()
+    {
+        __syncthreads();
+        sb.flush(tuples);
+    }
+};
+
 // Scatter pass of the FUSED multi-GPU exchange, owner buckets only (n_buckets = ranks <= 32).  Every round of
 // BLOCK*G occurrences is first sorted by owner in shared memory, then copied out with adjacent lanes writing
 // adjacent 16-B tuples: each owner receives contiguous runs (hundreds of bytes) instead of isolated 16-B stores,
@@ -240,6 +401,7 @@ struct PartitionSink {
 template <bool WIDE>
 struct PeerStagedSink {
     static constexpr int RUN = G;
+    static constexpr int MIN_BLOCKS = MIN_CTAS;
     static constexpr int TW = WIDE ? 4 : 2;            // u64 words per tuple
     TableView t;
     u64 div, div_M;
@@ -386,13 +548,14 @@ static __global__ void __launch_bounds__(256) k_part_scan3(u32 *matrix, u64 n_ch
 // the fused build kernel: one CTA per chunk of CB bases
 // ---------------------------------------------------------------------------------------------------
 template <bool WIDE, class Sink>
-__global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sink)
+__global__ void __launch_bounds__(BLOCK, Sink::MIN_BLOCKS) k_build(BuildArgs a, Sink sink)
 {
     extern __shared__ u32 smem[];
     u32 *pk = smem;                          // a.stage_words
     u32 *rstart = pk + a.stage_words;        // MAXR
     u32 *rpre = rstart + MAXR;               // MAXR + 1
-    u32 *extra = rpre + MAXR + 2;            // sink-private shared memory (8-byte aligned)
+    u32 *extra = rpre + MAXR + 2;            // sink-private shared memory, 16-byte aligned
+    extra += (4 - ((a.stage_words + 2 * MAXR + 2) & 3)) & 3;
     __shared__ u32 warp_tot[BLOCK / 32];
 
     const int tid = threadIdx.x;
@@ -529,6 +692,32 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) k_build(BuildArgs a, Sink sin
 // radix partition (count rows -> column scan -> scatter) puts them in table-slice order for the bucketed insert
 // ---------------------------------------------------------------------------------------------------
 constexpr int TP_TILE = 4096;     // tuples per CTA
+
+// scatter pass of the tuple partition through the shared-memory staging (one batch = the CTA's tile of TP_TILE tuples)
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_tuple_scatter_staged(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
+                                                              const u32 *__restrict__ matrix, u64 *dst)
+{
+    extern __shared__ u32 tp_smem[];
+    StageBuf<WIDE> sb;
+    sb.carve(tp_smem, TP_TILE, nb);
+    const u32 *row = matrix + (size_t)blockIdx.x * nb;
+    for (u32 b = threadIdx.x; b < nb; b += 256) { sb.bh[b] = 0; sb.base[b] = row[b]; }
+    const u64 i0 = (u64)blockIdx.x * TP_TILE;
+    const u32 cnt = (u32)((n - i0) < (u64)TP_TILE ? (n - i0) : (u64)TP_TILE);
+    if (threadIdx.x == 0) sb.misc[0] = cnt;
+    __syncthreads();
+    for (u32 e = threadIdx.x; e < cnt; e += 256) {
+        const u64 i = i0 + e;
+        u64 klo, khi = 0, meta, z = 0;
+        if (WIDE) ld256_cs(reinterpret_cast<const ulonglong2 *>(src) + 2 * i, klo, khi, meta, z);
+        else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(src) + i); klo = x.x; meta = x.y; }
+        u64 h = WIDE ? hash_code_wide(klo, khi) : hash_code(klo);
+        sb.put(e, (u32)((mod_P(h, t.P, t.M) - t.lo) >> shift), klo, khi, meta);
+    }
+    __syncthreads();
+    sb.flush(dst);
+}
 
 template <bool WIDE, int MODE>
 __global__ void __launch_bounds__(256) k_tuple_partition(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
@@ -806,7 +995,7 @@ __device__ __forceinline__ void cluster_bounds(const u32 *W, int k, bool prev_oc
 }
 
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+__global__ void __launch_bounds__(LT, 8) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
                                                         LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
 {
     // the tile's nodes, loaded coalesced and digested in parallel: key, ordinal, packed link words, home slot;

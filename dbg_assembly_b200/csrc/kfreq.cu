@@ -56,6 +56,7 @@ static const uint64_t KF_BLOCK = 8ull * 1024 * 1024;      // k-mers per .cz bloc
 // ---------------------------------------------------------------------------------------------------
 struct FreqSink {
     static constexpr int RUN = G;
+    static constexpr int MIN_BLOCKS = MIN_CTAS;
     TableView t;           // counters only
     u32 *table;
     u64 lo, hi;            // owned index range [lo, hi)
