@@ -55,7 +55,7 @@ SYMBOLS = [
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
     "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device", "dbg_insert_sliced_device", "dbg_partition_info",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
-    "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count",
+    "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count", "dbg_path_counts",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
     "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
@@ -111,6 +111,7 @@ def load(build_if_missing: bool = True):
         "dbg_device_image": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "dbg_get_timings": (C.c_int, [vp, vp]),
         "dbg_launch_count": (u64, [vp]),
+        "dbg_path_counts": (C.c_int, [vp, vp]),
         "dbg_reset": (C.c_int, [vp]),
         "dbg_set_stream": (C.c_int, [vp, vp]),
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),

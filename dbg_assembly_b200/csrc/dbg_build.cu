@@ -145,6 +145,12 @@ struct dbg_ctx {
     LayoutInfo *d_layout_info;
     LayoutRegion *d_regions;
     int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
+    int optimistic;                // env DBG_B200_OPTIMISTIC (default 1): single-pass partition with fixed bucket regions first
+    int opt_capb;                  // env DBG_B200_OPT_CAPB: force the region size (tests: provoke the overflow fallback)
+    u32 *d_fill = nullptr;         // [n_buckets] tuples per bucket + [n_buckets] overflow flag
+    u64 *d_snap = nullptr;         // counters + polyA before an optimistic scatter (restored on overflow)
+    u32 *h_flag = nullptr;         // pinned
+    uint64_t path_counts[4] = {0, 0, 0, 0};   // blocks: direct, partitioned exact, partitioned optimistic, overflow fallbacks
     int stage_cap;                 // env DBG_B200_STAGE_CAP: batch size of the staged scatter (-1 default, 0 off)
     int peer_unstaged;             // env DBG_B200_PEER_UNSTAGED=1: fused exchange stores tuples one by one (experiments)
     uint32_t layout_regions;
@@ -208,6 +214,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_roffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    cudaFree(c->d_fill); cudaFree(c->d_snap); if (c->h_flag) cudaFreeHost(c->h_flag);
     delete c;
 }
 
@@ -270,6 +277,8 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
     if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->optimistic = getenv("DBG_B200_OPTIMISTIC") ? atoi(getenv("DBG_B200_OPTIMISTIC")) : 1;
+    c->opt_capb = getenv("DBG_B200_OPT_CAPB") ? atoi(getenv("DBG_B200_OPT_CAPB")) : 0;
     c->stage_cap = getenv("DBG_B200_STAGE_CAP") ? atoi(getenv("DBG_B200_STAGE_CAP")) : -1;
     c->peer_unstaged = getenv("DBG_B200_PEER_UNSTAGED") ? atoi(getenv("DBG_B200_PEER_UNSTAGED")) : 0;
     c->layout_mode = 0;
@@ -318,6 +327,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
     c->build_ev.clear();
     c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
     c->batch_reads = 0; c->batch_bases = 0; c->part_blocks = 0;
+    for (int i = 0; i < 4; i++) c->path_counts[i] = 0;
     c->links_cutoff = INT32_MIN;
     for (int i = 1; i < 8; i++) c->ms[i] = 0;
     return clear_table(c);
@@ -358,7 +368,7 @@ static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_ch
 }
 
 template <bool WIDE, bool TRACK>
-static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed)
+static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed, const u32 *d_fill)
 {
     if (n_upper == 0) return DBG_OK;
     uint64_t tiles = (n_upper + INS_TILE - 1) / INS_TILE;
@@ -367,16 +377,17 @@ static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, con
     CU_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(u64), s));      // tile counter
     k_insert_tuples<WIDE, TRACK><<<grid, INS_BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, view_of(c),
                                                             bucketed ? c->d_boffs : nullptr, c->n_buckets, c->part_shift,
-                                                            c->d_counters + 7);
+                                                            c->d_counters + 7, d_fill);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return DBG_OK;
 }
 
-static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed = false)
+static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed = false,
+                      const u32 *d_fill = nullptr)
 {
-    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s, bucketed) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s, bucketed);
-    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed);
+    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill);
+    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill);
 }
 
 // batch capacity (tuples) of the shared-memory staging of the scatter passes; 0 = store tuples one by one
@@ -400,10 +411,54 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
 {
     const uint32_t nb = c->n_buckets;
     const uint64_t n_tiles = (n_chunks + PT_CHUNKS - 1) / PT_CHUNKS;
+    int rc = DBG_OK;
+    // ---- optimistic single pass: every bucket gets a fixed region of the tuple buffer (the buffer holds one tuple
+    // per BASE, occurrences are fewer, and hash%P spreads them evenly); batches reserve their runs with atomics.
+    // No counting pass, no scan.  Skewed input (a bucket region overflows) falls back to the exact partition.
+    const uint32_t cap0 = stage_cap(c, WIDE);
+    uint64_t capb64 = (c->opt_capb > 0 ? (uint64_t)c->opt_capb : c->cap_tuples / nb) / INS_TILE * INS_TILE;   // regions start on insert tiles
+    if (c->optimistic && cap0 && capb64 >= INS_TILE && capb64 * nb <= c->cap_tuples && capb64 * nb < (1ull << 32)) {
+        const uint32_t capb = (uint32_t)capb64;
+        if (!c->d_fill) {
+            CU_TRY(cudaMalloc(&c->d_fill, ((size_t)4096 + 1) * sizeof(u32)));
+            CU_TRY(cudaMalloc(&c->d_snap, (CNT_N + 8) * sizeof(u64)));
+            CU_TRY(cudaMallocHost(&c->h_flag, sizeof(u32)));
+        }
+        CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaMemsetAsync(c->d_fill, 0, ((size_t)nb + 1) * sizeof(u32), s));
+        StagedScatterSink<WIDE, true> st; st.t = view_of(c); st.shift = c->part_shift; st.n_buckets = nb; st.cap = cap0;
+        st.matrix = nullptr; st.tuples = c->d_tuples; st.fill = c->d_fill; st.capb = capb; st.flag = c->d_fill + nb; st.filled = 0;
+        a.count_stats = 1;
+        rc = launch_build<WIDE>(c, a, st, n_chunks, s, 0, StageBuf<WIDE>::bytes(cap0, nb));
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(c->h_flag, c->d_fill + nb, sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        if (*c->h_flag == 0) {
+            k_opt_finish<WIDE><<<nb, 256, 0, s>>>(c->d_tuples, c->d_fill, capb, nb, c->d_boffs, (u32)INS_TILE);
+            CU_TRY(cudaGetLastError());
+            c->launches++;
+            c->path_counts[2]++;
+            EvPair ev;
+            rc = ev_begin(c, s, &ev);
+            if (rc) return rc;
+            ev.slot = 6;
+            rc = insert_any(c, c->d_tuples, (uint64_t)capb * nb, nullptr, s, true, c->d_fill);
+            if (rc) return rc;
+            CU_TRY(cudaEventRecord(ev.b, s));
+            c->build_ev.push_back(ev);
+            return DBG_OK;
+        }
+        // overflow: nothing was inserted; undo the side counters of the scatter and redo the block exactly
+        CU_TRY(cudaMemcpyAsync(c->d_counters, c->d_snap, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->d_polyA, c->d_snap + CNT_N, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        c->path_counts[3]++;
+    }
+    c->path_counts[1]++;
     PartitionSink<WIDE, 0> cs; cs.t = view_of(c); cs.shift = c->part_shift; cs.div = 0; cs.div_M = 0; cs.nb_local = 0; cs.n_buckets = nb;
     cs.matrix = c->d_matrix; cs.tuples = nullptr; cs.dst_ptrs = nullptr; cs.dst_base = nullptr; cs.roffs = nullptr; cs.hist = nullptr; cs.base = nullptr;
     a.count_stats = 0;
-    int rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
+    rc = launch_build<WIDE>(c, a, cs, n_chunks, s, nb);
     if (rc) return rc;
     dim3 g1((unsigned)n_tiles, (nb + 255) / 256);
     k_part_scan1<<<g1, 256, 0, s>>>(c->d_matrix, n_chunks, nb, c->d_tile_sums);
@@ -418,7 +473,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
     if (cap) {
         // scatter through shared-memory batches copied out in bucket order (whole-sector runs)
         StagedScatterSink<WIDE> st; st.t = view_of(c); st.shift = c->part_shift; st.n_buckets = nb; st.cap = cap;
-        st.matrix = c->d_matrix; st.tuples = c->d_tuples; st.filled = 0;
+        st.matrix = c->d_matrix; st.tuples = c->d_tuples; st.fill = nullptr; st.capb = 0; st.flag = nullptr; st.filled = 0;
         rc = launch_build<WIDE>(c, a, st, n_chunks, s, 0, StageBuf<WIDE>::bytes(cap, nb));
     } else {
         PartitionSink<WIDE, 1> ss; ss.t = view_of(c); ss.shift = c->part_shift; ss.div = 0; ss.div_M = 0; ss.nb_local = 0; ss.n_buckets = nb;
@@ -582,9 +637,11 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
         rc = c->wide ? run_rank_partition<true>(c, a, n_chunks, n_parts, d_tuples, d_counts, s)
                      : run_rank_partition<false>(c, a, n_chunks, n_parts, d_tuples, d_counts, s);
     } else if (c->wide) {
+        c->path_counts[0]++;
         if (c->track) { InsertSink<true, true> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
         else { InsertSink<true, false> sk; sk.t = view_of(c); rc = launch_build<true>(c, a, sk, n_chunks, s); }
     } else {
+        c->path_counts[0]++;
         if (c->track) { InsertSink<false, true> sk; sk.t = view_of(c); rc = launch_build<false>(c, a, sk, n_chunks, s); }
         else { InsertSink<false, false> sk; sk.t = view_of(c); rc = launch_build<false>(c, a, sk, n_chunks, s); }
     }
@@ -1004,7 +1061,7 @@ static int run_layout(dbg_ctx *c)
         CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
         k_layout_wrapscan<WIDE><<<1, 32, 0, c->stream>>>(nodes, c->n_local, c->P, c->d_layout_info, c->d_regions, SCRATCH_CAP);
         CU_TRY(cudaGetLastError());
-        k_layout_clusters<WIDE, TRACK><<<c->n_sms * 8, LT, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
                                                                              c->d_regions, SCRATCH_CAP);
         CU_TRY(cudaGetLastError());
         k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
@@ -1263,6 +1320,13 @@ extern "C" int dbg_get_timings(dbg_ctx *c, float ms[8])
 }
 
 extern "C" uint64_t dbg_launch_count(const dbg_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int dbg_path_counts(const dbg_ctx *c, uint64_t counts[4])
+{
+    if (!c || !counts) return set_err(DBG_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 4; i++) counts[i] = c->path_counts[i];
+    return DBG_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // roofline denominator

@@ -279,11 +279,38 @@ struct StageBuf {
         bk = reinterpret_cast<unsigned short *>(misc + 16);
         rk = bk + cap; idx = rk + cap;
     }
-    // all threads of the CTA; a __syncthreads() must separate the last append from this call; ends with one
-    __device__ __forceinline__ void flush(u64 *dst)
+    // all threads of the CTA; a __syncthreads() must separate the last append from this call; ends with one.
+    // OPT (optimistic single-pass partition): no precomputed offsets; every bucket has a fixed region of `capb`
+    // tuples and the batch reserves its run with one atomicAdd per touched bucket on fill[]; a bucket that would
+    // overflow raises *flag and its tuples are dropped (the host then redoes the block with the exact two-pass
+    // partition).
+    template <bool OPT = false>
+    __device__ __forceinline__ void flush(u64 *dst, u32 *fill = nullptr, u32 capb = 0, u32 *flag = nullptr)
     {
         const u32 t = threadIdx.x, nthr = blockDim.x;
         const u32 n = misc[0];
+        // OPT: reserve this batch's run in every touched bucket's region.  The atomics are issued first and their
+        // results are picked up after the scan below, so the round trips hide behind it (nb <= 4 * nthr; larger
+        // bucket counts take the results at once, chunk by chunk)
+        u32 rr[4] = {0, 0, 0, 0};
+        if (OPT) {
+            for (u32 c0 = 0; c0 < nb; c0 += 4 * nthr) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const u32 b = c0 + j * nthr + t;
+                    const u32 cnt = b < nb ? bh[b] : 0u;
+                    rr[j] = cnt ? atomicAdd(&fill[b], cnt) : 0u;
+                }
+                if (nb > 4 * nthr) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const u32 b = c0 + j * nthr + t;
+                        const u32 cnt = b < nb ? bh[b] : 0u;
+                        if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = b * capb + rr[j]; }
+                    }
+                }
+            }
+        }
         // exclusive scan of bh (nb <= 4096): a contiguous segment per thread, warp scan, warp totals
         const u32 seg = (nb + nthr - 1) / nthr;
         const u32 b0 = t * seg, b1 = (b0 + seg < nb) ? b0 + seg : nb;
@@ -297,11 +324,20 @@ struct StageBuf {
         u32 run = incl - sum;
         for (u32 w = 0; w < (t >> 5); w++) run += misc[1 + w];
         for (u32 b = b0; b < b1; b++) { boff[b] = run; run += bh[b]; }
+        if (OPT && nb <= 4 * nthr) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u32 b = j * nthr + t;
+                const u32 cnt = b < nb ? bh[b] : 0u;
+                if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = b * capb + rr[j]; }
+            }
+        }
         __syncthreads();
         for (u32 e = t; e < n; e += nthr) idx[boff[bk[e]] + rk[e]] = (unsigned short)e;
         __syncthreads();
         for (u32 i = t; i < n; i += nthr) {
             const u32 e = idx[i], b = bk[e];
+            if (OPT && base[b] == 0xffffffffu) continue;
             const u64 pos = (u64)base[b] + (i - boff[b]);
             const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(tup);
             if (WIDE) {
@@ -313,7 +349,7 @@ struct StageBuf {
             }
         }
         __syncthreads();
-        for (u32 b = t; b < nb; b += nthr) { base[b] += bh[b]; bh[b] = 0; }
+        for (u32 b = t; b < nb; b += nthr) { if (!OPT) base[b] += bh[b]; bh[b] = 0; }
         if (t == 0) misc[0] = 0;
         __syncthreads();
     }
@@ -329,15 +365,18 @@ struct StageBuf {
 };
 
 // scatter pass of the single-GPU partitioned build through the staging above (slice buckets)
-template <bool WIDE>
+template <bool WIDE, bool OPT = false>
 struct StagedScatterSink {
     static constexpr int RUN = G;
     static constexpr int MIN_BLOCKS = 3;           // <= 85 registers: three CTAs per SM next to a 2048-tuple batch
     TableView t;
     int shift;
     u32 n_buckets, cap;
-    u32 *matrix;
+    u32 *matrix;       // exact: [n_chunks][n_buckets] write offsets
     u64 *tuples;
+    u32 *fill;         // OPT: tuples stored so far per bucket (global)
+    u32 capb;          // OPT: region size per bucket
+    u32 *flag;         // OPT: overflow
     StageBuf<WIDE> sb;
     u32 filled;
 
@@ -345,8 +384,8 @@ struct StagedScatterSink {
     {
         filled = 0;
         sb.carve(extra, cap, n_buckets);
-        const u32 *row = matrix + (size_t)blockIdx.x * n_buckets;
-        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) { sb.bh[b] = 0; sb.base[b] = row[b]; }
+        const u32 *row = OPT ? nullptr : matrix + (size_t)blockIdx.x * n_buckets;
+        for (u32 b = threadIdx.x; b < n_buckets; b += BLOCK) { sb.bh[b] = 0; sb.base[b] = OPT ? 0u : row[b]; }
         if (threadIdx.x == 0) sb.misc[0] = 0;
         __syncthreads();
     }
@@ -355,7 +394,7 @@ struct StagedScatterSink {
     {
         // `filled` is a block-uniform upper bound of the batch cursor kept in registers (never read the shared
         // cursor to decide: a fast warp may already have bumped it for this round)
-        if (filled + BLOCK * RUN > sb.cap) { __syncthreads(); sb.flush(tuples); filled = 0; }
+        if (filled + BLOCK * RUN > sb.cap) { __syncthreads(); sb.template flush<OPT>(tuples, fill, capb, flag); filled = 0; }
         filled += BLOCK * RUN;
         u32 bkt[RUN];
         u32 mine = 0;
@@ -389,7 +428,7 @@ struct StagedScatterSink {
     __device__ __forceinline__ void finish()
     {
         __syncthreads();
-        sb.flush(tuples);
+        sb.template flush<OPT>(tuples, fill, capb, flag);
     }
 };
 
@@ -693,6 +732,26 @@ __global__ void __launch_bounds__(BLOCK, Sink::MIN_BLOCKS) k_build(BuildArgs a, 
 // ---------------------------------------------------------------------------------------------------
 constexpr int TP_TILE = 4096;     // tuples per CTA
 
+// after an optimistic scatter that did not overflow: bucket b occupies [b*capb, b*capb + fill[b]); publish the
+// strided bucket offsets the insert kernel walks and zero the keys behind the last tuple of every region (the insert
+// kernel skips tuples whose key is 0: tuples never carry the k-mer-0 key)
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_opt_finish(u64 *tuples, const u32 *__restrict__ fill, u32 capb, u32 nb, u64 *boffs, u32 tile)
+{
+    const u32 b = blockIdx.x;
+    if (threadIdx.x == 0) { boffs[b] = (u64)b * capb; if (b == nb - 1) boffs[nb] = (u64)nb * capb; }
+    const u32 f = fill[b];
+    ulonglong2 *t = reinterpret_cast<ulonglong2 *>(tuples);
+    // capb is a multiple of the insert tile, so regions start on tile boundaries; the insert kernel skips the tiles
+    // that lie entirely in the unused tail, only the partly used tile needs its tail zeroed
+    const u32 z_end = min(capb, (f + tile - 1) / tile * tile);
+    for (u32 i = f + threadIdx.x; i < z_end; i += 256) {
+        const u64 pos = (u64)b * capb + i;
+        if (WIDE) t[2 * pos] = make_ulonglong2(0ULL, 0ULL);
+        else t[pos] = make_ulonglong2(0ULL, 0ULL);
+    }
+}
+
 // scatter pass of the tuple partition through the shared-memory staging (one batch = the CTA's tile of TP_TILE tuples)
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_tuple_scatter_staged(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
@@ -778,20 +837,26 @@ constexpr int INS_CTAS = DBG_INS_CTAS;      // per SM (x8 warps)
 template <bool WIDE, bool TRACK>
 __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
                                                                        TableView t, const u64 *__restrict__ boffs, u32 n_buckets, int shift,
-                                                                       u64 *tile_counter)
+                                                                       u64 *tile_counter, const u32 *__restrict__ fill)
 {
     if (n_ptr) n = *n_ptr;      // exact count produced on the device (partitioned build): no host round trip
     u32 n_new = 0, n_conf = 0;
     u32 b = 0;                  // current bucket of this CTA's tile (monotone)
-    u64 b0 = 0, b1 = 0;
+    u64 b0 = 0, b1 = 0;         // the bucket's region in the tuple stream
+    u64 used = 0;               // tuples actually stored in it (== b1 - b0 unless the regions are fixed-size: `fill`)
     float ratio = 0.f;
+    // lines of the NEXT table slice per tuple of the current bucket: every tile prefetches its share
+    auto next_slice_ratio = [&]() -> float {
+        if (!(b + 1 < n_buckets && used > 0 && ((u64)(b + 1) << shift) < t.n_local)) return 0.f;
+        const u64 slice_lo = (u64)(b + 1) << shift;
+        u64 slice_n = (u64)1 << shift;
+        if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
+        return (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)used;      // 128-B L2 lines per tuple
+    };
     if (boffs) {
         b0 = __ldg(boffs); b1 = __ldg(boffs + 1);
-        if (n_buckets > 1 && b1 > b0 && ((u64)1 << shift) < t.n_local) {
-            u64 slice_n = (u64)1 << shift;
-            if (2 * slice_n > t.n_local) slice_n = t.n_local - slice_n;
-            ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);
-        }
+        used = fill ? (u64)__ldg(fill) : b1 - b0;
+        ratio = next_slice_ratio();
     }
     __shared__ u64 s_tile[2];
     // tiles are handed out by a global counter, so at any moment the resident CTAs hold the NEXT gridDim tiles of
@@ -806,6 +871,13 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
         const u64 tile = s_tile[par] * INS_TILE;
         if (tile >= n) break;
         if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+        if (boffs && tile >= b1 && b + 1 < n_buckets) {
+            // entered a new bucket (rare path): its region, its tuple count, the prefetch ratio of the next slice
+            while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
+            used = fill ? (u64)__ldg(fill + b) : b1 - b0;
+            ratio = next_slice_ratio();
+        }
+        if (fill && tile - b0 >= used) continue;        // fixed-size regions: this tile lies in the unused tail (block-uniform)
         u64 klo[INS_ROUNDS], khi[INS_ROUNDS], meta[INS_ROUNDS];
 #pragma unroll
         for (int r = 0; r < INS_ROUNDS; r++) {
@@ -816,29 +888,16 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
                 else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(tuples) + i); klo[r] = x.x; meta[r] = x.y; }
             }
         }
-        if (boffs) {
-            if (tile >= b1 && b + 1 < n_buckets) {
-                // entered a new bucket: its tuple span and the lines-per-tuple ratio of the NEXT slice (rare path)
-                while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
-                ratio = 0.f;
-                if (b + 1 < n_buckets && b1 > b0 && ((u64)(b + 1) << shift) < t.n_local) {
-                    const u64 slice_lo = (u64)(b + 1) << shift;
-                    u64 slice_n = (u64)1 << shift;
-                    if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
-                    ratio = (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)(b1 - b0);   // 128-B L2 lines per tuple
-                }
-            }
-            if (ratio > 0.f) {
-                // this tile's proportional share of the next slice (approximate shares are fine: overlaps and small
-                // gaps only cost a few redundant or late lines)
-                const float t0 = (float)(tile - b0);
-                const u64 l0 = (u64)(t0 * ratio), l1 = (u64)((t0 + (float)INS_TILE) * ratio) + 1;
-                const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + ((u64)(b + 1) << shift));
-                const u64 lmax = (((u64)1 << shift) * sizeof(NodeT<WIDE>)) / 128;
-                for (u64 l = l0 + threadIdx.x; l < l1 && l < lmax; l += INS_BLOCK)
-                    if (((u64)(b + 1) << shift) + l * (128 / sizeof(NodeT<WIDE>)) < t.n_local)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
-            }
+        if (ratio > 0.f) {
+            // this tile's proportional share of the next slice (approximate shares are fine: overlaps and small
+            // gaps only cost a few redundant or late lines)
+            const float t0 = (float)(tile - b0);
+            const u64 l0 = (u64)(t0 * ratio), l1 = (u64)((t0 + (float)INS_TILE) * ratio) + 1;
+            const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + ((u64)(b + 1) << shift));
+            const u64 lmax = (((u64)1 << shift) * sizeof(NodeT<WIDE>)) / 128;
+            for (u64 l = l0 + threadIdx.x; l < l1 && l < lmax; l += INS_BLOCK)
+                if (((u64)(b + 1) << shift) + l * (128 / sizeof(NodeT<WIDE>)) < t.n_local)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
         }
 #pragma unroll
         for (int r = 0; r < INS_ROUNDS; r++)
@@ -967,7 +1026,10 @@ __global__ void k_layout_wrapscan(const NodeT<WIDE> *__restrict__ nodes, u64 n_l
     *info = li;
 }
 
-constexpr int LT = 256;     // slots per layout tile (one CTA round)
+#ifndef DBG_LT
+#define DBG_LT 256
+#endif
+constexpr int LT = DBG_LT;  // slots per layout tile (one CTA round) = threads per CTA
 constexpr int LH = 64;      // halo: the longest cluster handled in shared memory
 constexpr int LW = (LT + LH) / 32;
 
@@ -995,7 +1057,7 @@ __device__ __forceinline__ void cluster_bounds(const u32 *W, int k, bool prev_oc
 }
 
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(LT, 8) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+__global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
                                                         LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
 {
     // the tile's nodes, loaded coalesced and digested in parallel: key, ordinal, packed link words, home slot;

@@ -250,6 +250,12 @@ class DBGBuilder:
     def launches(self):
         return int(self.L.dbg_launch_count(self.h))
 
+    def path_counts(self):
+        """read blocks per build path: direct, exact partition, optimistic partition, optimistic overflows (redone exactly)"""
+        c = np.zeros(4, dtype=np.uint64)
+        capi.check(self.L.dbg_path_counts(self.h, c.ctypes.data), "dbg_path_counts")
+        return dict(direct=int(c[0]), exact=int(c[1]), optimistic=int(c[2]), overflows=int(c[3]))
+
 
 # ---------------------------------------------------------------------------------------------------
 # reference-shaped interface

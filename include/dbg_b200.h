@@ -186,6 +186,10 @@ int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
 int  dbg_get_timings(dbg_ctx *ctx, float ms[8]);
 /* number of kernel launches issued by this context so far */
 uint64_t dbg_launch_count(const dbg_ctx *ctx);
+/* how many read blocks went through which build path so far: [0] fused direct insert, [1] exact two-pass
+ * partition (count, scan, scatter), [2] optimistic single-pass partition (fixed bucket regions), [3] optimistic
+ * attempts that overflowed a region and were redone exactly (also counted in [1]) */
+int  dbg_path_counts(const dbg_ctx *ctx, uint64_t counts[4]);
 /* re-zero the table and counters so the context can build again (bench steps) */
 int  dbg_reset(dbg_ctx *ctx);
 /* run all of this context's kernels, memsets and copies on a caller-owned cudaStream_t (e.g. torch's

@@ -417,6 +417,55 @@ def test_medium_synthetic_matches_oracle(dbg, oracle_mod):
     o.close()
 
 
+@pytest.mark.parametrize("variant", ["optimistic", "overflow_fallback", "exact", "unstaged"])
+def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatch, variant):
+    """the partitioned build's variants on the medium C2-shaped case: the optimistic single-pass partition (fixed bucket
+    regions), its overflow fallback (regions forced too small, so every block is redone by the exact two-pass
+    partition -- and the side counters must not be double counted), the exact partition alone, and the scatter
+    that stores tuples one by one; all bit-identical to the oracle, layout included"""
+    if build_path != "partitioned":
+        pytest.skip("partitioned path only")
+    for k in ("DBG_B200_PART_SHIFT", "DBG_B200_BATCH_BASES", "DBG_B200_BATCH_READS"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("DBG_B200_PART_SHIFT", "14")
+    if variant == "overflow_fallback":
+        monkeypatch.setenv("DBG_B200_OPT_CAPB", "1000")
+    elif variant == "exact":
+        monkeypatch.setenv("DBG_B200_OPTIMISTIC", "0")
+    elif variant == "unstaged":
+        monkeypatch.setenv("DBG_B200_STAGE_CAP", "0")
+    from dbg_assembly_b200 import synth
+    p = synth.make_params(seed=12, genome_len=300_000, read_len=150, insert=500, err=0.01, n_rate=0.002)
+    n = 120_000
+    hb, ho = synth.reads_host(p, 0, n)
+    # poly-A reads: the k-mer-0 side counters are bumped by the scatter pass, which the fallback must undo
+    extra = [b"A" * 150] * 40
+    eb = np.frombuffer(b"".join(extra), dtype=np.uint8)
+    hb = np.concatenate([hb, eb]); ho = np.concatenate([ho, ho[-1] + 150 * np.arange(1, len(extra) + 1, dtype=ho.dtype)])
+    init_slots = 12_000_000
+    o = oracle_build(oracle_mod, [(hb, ho)], 31, 150, init_slots)
+    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=init_slots, load_factor=0.7) as b:
+        half = (n // 2)
+        b.submit(hb, ho[: half + 1])
+        b.submit(hb, ho[half:])
+        st = b.finalize()
+        arr, nul = b.export_kmerset()
+        pc = b.path_counts()
+    assert pc["direct"] == 0
+    if variant == "optimistic":
+        assert pc["optimistic"] >= 1 and pc["overflows"] == 0 and pc["exact"] == 0, pc
+    elif variant == "overflow_fallback":
+        assert pc["overflows"] >= 1 and pc["exact"] == pc["overflows"] and pc["optimistic"] == 0, pc
+    else:
+        assert pc["exact"] >= 1 and pc["optimistic"] == 0 and pc["overflows"] == 0, pc
+    assert st["count"] == o.count and st["occurrences"] == o.occurrences and st["kmers_logged"] == o.kmers_logged
+    e = o.dump()
+    d = image_to_dump(arr, nul, o.size)
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], e[k]), k
+    o.close()
+
+
 def test_full_size_properties_C2(dbg, build_path, monkeypatch):
     """BASELINE config C2 at full size (3.07 M reads, 3.68e8 occurrences): size-independent properties
     -- conservation of occurrences in the link lanes, idempotent rebuild, and the direct and the
