@@ -896,14 +896,56 @@ static int partition_tuples(dbg_ctx *c, const void *d_src, uint64_t n, cudaStrea
     const size_t st_bytes = StageBuf<WIDE>::bytes(TP_TILE, nb);
     if (c->stage_cap != 0 && st_bytes <= 200 * 1024) {
         if (st_bytes > 48 * 1024)
-            CU_TRY(cudaFuncSetAttribute(k_tuple_scatter_staged<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
-        k_tuple_scatter_staged<WIDE><<<(unsigned)n_rows, 256, st_bytes, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
+            CU_TRY(cudaFuncSetAttribute(k_tuple_scatter_staged<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
+        k_tuple_scatter_staged<WIDE, false><<<(unsigned)n_rows, 256, st_bytes, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples,
+                                                                                     nullptr, 0, nullptr);
     } else {
         k_tuple_partition<WIDE, 1><<<(unsigned)n_rows, 256, smem, s>>>((const u64 *)d_src, n, t, c->part_shift, nb, c->d_matrix, c->d_tuples);
     }
     CU_TRY(cudaGetLastError());
     c->launches += 5;
     return DBG_OK;
+}
+
+// optimistic single-pass partition of received tuples (see run_partitioned): returns 1 when it was used (the caller
+// inserts with the fixed regions), 0 when it does not apply or overflowed (caller partitions exactly), < 0 on error
+static int ensure_opt_buffers(dbg_ctx *c)
+{
+    if (!c->d_fill) {
+        CU_TRY(cudaMalloc(&c->d_fill, ((size_t)4096 + 1) * sizeof(u32)));
+        CU_TRY(cudaMalloc(&c->d_snap, (CNT_N + 8) * sizeof(u64)));
+        CU_TRY(cudaMallocHost(&c->h_flag, sizeof(u32)));
+    }
+    return DBG_OK;
+}
+
+template <bool WIDE>
+static int partition_tuples_optimistic(dbg_ctx *c, const void *d_src, uint64_t n, cudaStream_t s, uint32_t *capb_out)
+{
+    const uint32_t nb = c->n_buckets;
+    const size_t st_bytes = StageBuf<WIDE>::bytes(TP_TILE, nb);
+    uint64_t capb64 = (c->opt_capb > 0 ? (uint64_t)c->opt_capb : c->cap_tuples / nb) / INS_TILE * INS_TILE;
+    if (!c->optimistic || c->stage_cap == 0 || st_bytes > 200 * 1024 || capb64 < INS_TILE || capb64 * nb > c->cap_tuples ||
+        capb64 * nb >= (1ull << 32)) return 0;
+    const uint32_t capb = (uint32_t)capb64;
+    if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
+    const uint64_t n_rows = (n + TP_TILE - 1) / TP_TILE;
+    CU_TRY(cudaMemsetAsync(c->d_fill, 0, ((size_t)nb + 1) * sizeof(u32), s));
+    if (st_bytes > 48 * 1024)
+        CU_TRY(cudaFuncSetAttribute(k_tuple_scatter_staged<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
+    k_tuple_scatter_staged<WIDE, true><<<(unsigned)n_rows, 256, st_bytes, s>>>((const u64 *)d_src, n, view_of(c), c->part_shift, nb, nullptr, c->d_tuples,
+                                                                               c->d_fill, capb, c->d_fill + nb);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    CU_TRY(cudaMemcpyAsync(c->h_flag, c->d_fill + nb, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (*c->h_flag != 0) { c->path_counts[3]++; return 0; }
+    k_opt_finish<WIDE><<<nb, 256, 0, s>>>(c->d_tuples, c->d_fill, capb, nb, c->d_boffs, (u32)INS_TILE);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->path_counts[2]++;
+    *capb_out = capb;
+    return 1;
 }
 
 extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64_t n, void *stream)
@@ -915,18 +957,28 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     // enough tuples per table slice: put them in slice order first, then insert through L2-resident slices
     bool part = want_partition(c, n) && 2 * (size_t)c->n_buckets * sizeof(u32) <= 48 * 1024;
-    if (part && (ensure_tuples(c, n) != DBG_OK || ensure_matrix(c, (n + TP_TILE - 1) / TP_TILE) != DBG_OK)) part = false;
+    // room for the fixed bucket regions of the optimistic partition: 1/8 slack plus a tile per bucket
+    const uint64_t want_cap = c->optimistic ? n + n / 8 + (uint64_t)c->n_buckets * INS_TILE : n;
+    if (part && ensure_tuples(c, want_cap) != DBG_OK && ensure_tuples(c, n) != DBG_OK) part = false;
+    if (part && ensure_matrix(c, (n + TP_TILE - 1) / TP_TILE) != DBG_OK) part = false;
     EvPair ev;
     int rc = ev_begin(c, s, &ev);
     if (rc) return rc;
     if (part) {
-        rc = c->wide ? partition_tuples<true>(c, d_tuples, n, s) : partition_tuples<false>(c, d_tuples, n, s);
-        if (rc) return rc;
+        uint32_t capb = 0;
+        int opt = c->wide ? partition_tuples_optimistic<true>(c, d_tuples, n, s, &capb) : partition_tuples_optimistic<false>(c, d_tuples, n, s, &capb);
+        if (opt < 0) return opt;
+        if (!opt) {
+            c->path_counts[1]++;
+            rc = c->wide ? partition_tuples<true>(c, d_tuples, n, s) : partition_tuples<false>(c, d_tuples, n, s);
+            if (rc) return rc;
+        }
         EvPair ei;
         rc = ev_begin(c, s, &ei);
         if (rc) return rc;
         ei.slot = 6;
-        rc = insert_any(c, c->d_tuples, n, nullptr, s, true);
+        rc = opt ? insert_any(c, c->d_tuples, (uint64_t)capb * c->n_buckets, nullptr, s, true, c->d_fill)
+                 : insert_any(c, c->d_tuples, n, nullptr, s, true);
         if (rc) return rc;
         CU_TRY(cudaEventRecord(ei.b, s));
         c->build_ev.push_back(ei);

@@ -753,15 +753,15 @@ __global__ void __launch_bounds__(256) k_opt_finish(u64 *tuples, const u32 *__re
 }
 
 // scatter pass of the tuple partition through the shared-memory staging (one batch = the CTA's tile of TP_TILE tuples)
-template <bool WIDE>
+template <bool WIDE, bool OPT>
 __global__ void __launch_bounds__(256) k_tuple_scatter_staged(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
-                                                              const u32 *__restrict__ matrix, u64 *dst)
+                                                              const u32 *__restrict__ matrix, u64 *dst, u32 *fill, u32 capb, u32 *flag)
 {
     extern __shared__ u32 tp_smem[];
     StageBuf<WIDE> sb;
     sb.carve(tp_smem, TP_TILE, nb);
-    const u32 *row = matrix + (size_t)blockIdx.x * nb;
-    for (u32 b = threadIdx.x; b < nb; b += 256) { sb.bh[b] = 0; sb.base[b] = row[b]; }
+    const u32 *row = OPT ? nullptr : matrix + (size_t)blockIdx.x * nb;
+    for (u32 b = threadIdx.x; b < nb; b += 256) { sb.bh[b] = 0; sb.base[b] = OPT ? 0u : row[b]; }
     const u64 i0 = (u64)blockIdx.x * TP_TILE;
     const u32 cnt = (u32)((n - i0) < (u64)TP_TILE ? (n - i0) : (u64)TP_TILE);
     if (threadIdx.x == 0) sb.misc[0] = cnt;
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(256) k_tuple_scatter_staged(const u64 *__restr
         sb.put(e, (u32)((mod_P(h, t.P, t.M) - t.lo) >> shift), klo, khi, meta);
     }
     __syncthreads();
-    sb.flush(dst);
+    sb.template flush<OPT>(dst, fill, capb, flag);
 }
 
 template <bool WIDE, int MODE>

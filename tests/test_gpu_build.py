@@ -330,10 +330,17 @@ def test_table_full_is_reported_not_hung(dbg):
         assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
 
 
-def test_sharded_tuple_path_single_gpu(dbg, oracle_mod):
+@pytest.mark.parametrize("optimistic", ["1", "0", "overflow"])
+def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic):
     """multi-GPU building blocks on one device: extract tuples bucketed by owner shard, insert each bucket
-    into that shard's context, union of shard dumps == oracle node multiset (ranks emulated in sequence)"""
+    into that shard's context, union of shard dumps == oracle node multiset (ranks emulated in sequence).
+    The owner-side partition of the received tuples runs optimistically (fixed bucket regions), exactly, and
+    through the overflow fallback (regions forced too small)."""
     import torch
+    if optimistic == "overflow":
+        monkeypatch.setenv("DBG_B200_OPT_CAPB", "512")
+    else:
+        monkeypatch.setenv("DBG_B200_OPTIMISTIC", optimistic)
     reads = random_reads(71, 6000, 40, 150, genome_len=30000) + [b"A" * 60] * 50
     bases, offs = reads_to_arrays(reads)
     P_req = 300_000
