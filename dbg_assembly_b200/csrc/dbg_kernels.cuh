@@ -3,10 +3,14 @@
 //   k_chunk_first       : reads -> fixed-size base chunks (one CTA per chunk later)
 //   k_build<..>         : FUSED  stage ASCII -> 2-bit pack in shared memory -> canonical k-mer + neighbour
 //                         bases per occurrence -> sink.  Sinks: InsertSink (direct hash insert),
-//                         PartitionSink<0/1> (exact radix partition by table slice or by owner rank),
+//                         StagedScatterSink<OPT> (radix partition by table slice through shared-memory batches
+//                         copied out in bucket order; OPT = single pass into fixed bucket regions),
+//                         PartitionSink<0/1> (exact two-pass partition: counts, then offsets from the scan),
+//                         PeerStagedSink (owner-sorted runs into the peers' buffers over NVLink),
 //                         FreqSink (kfreq.cu: direct-index k-mer counts).
 //   k_part_scan1/2/3    : column scan of the per-chunk bucket counts -> exact write offsets
-//   k_tuple_partition   : the same partition over received tuples (owner side of the multi-GPU exchange)
+//   k_opt_finish        : bucket offsets + tail zeroing after an optimistic partition
+//   k_tuple_partition, k_tuple_scatter_staged : the same partition over received tuples (owner side of the exchange)
 //   k_insert_tuples     : bucket-ordered hash insert through L2-resident table slices
 //   k_layout_*          : rebuild the reference's slot layout (first-occurrence priority linear probing)
 //   k_links_* / k_compact_* / k_dump_shard : calculate_kmer_links + ordered stream compaction, shard dump
