@@ -6,8 +6,9 @@
 // parameter meaning, stderr log lines and all nine output files are the reference's.
 //
 // It defines the globals DBGgraph.h declares (DBGgraph.h:25-49) and build_debruijn_graph()
-// (DBGgraph.cpp:364): the host keeps the file reader (same framing as DBGgraph.cpp:244-272, through the
-// reference's own igzstream) and hands blocks of reads to the GPU library; hot loops #1 and #2
+// (DBGgraph.cpp:364): the host keeps the file reader (same framing as DBGgraph.cpp:244-272; fast_reader.h: zlib
+// with large buffers, one decoding thread per file, submission in file order) and hands blocks of reads to the GPU
+// library; hot loops #1 and #2
 // (thread_parseBlock / thread_updatekmers) run as CUDA kernels; the finished table comes back in the
 // reference's slot layout (== `debruijn_contig -t 1`) as the global `KmerSet *kset`.
 //
@@ -15,13 +16,16 @@
 // host traversal, and "-e" (enlarge) is not emulated: if the node count passes max_cutoff a warning is
 // printed (the reference would have enlarged and produced a different slot order; contents are the same).
 #include <chrono>
+#include <memory>
 #include <thread>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "DBGgraph.h"     // the reference's header (globals + prototypes), found via -I<reference>/DBG_contig
 #include "dbg_b200.h"
+#include "fast_reader.h"
 
 // ---- globals of DBGgraph.cpp:10-34 (same names, same defaults) -----------------------------------
 int KmerSize = 31;
@@ -55,68 +59,38 @@ static void die(const char *where, int rc)
     exit(1);
 }
 
-// one pinned staging block: bases + offsets
-struct Block {
-    char *bases;
-    uint64_t *offs;
-    uint64_t cap_bases, cap_reads, n_reads, n_bases;
-};
+// Reader of parse_one_reads_file (DBGgraph.cpp:244-272).  The framing rules are the reference's; the mechanics are
+// fast_reader.h: every input file is decoded and framed by its own thread into page-locked blocks, and this (main)
+// thread submits the blocks in file order, so read ordinals -- and with them the slot layout -- are those of a
+// sequential reader.  Blocks never span files.
+static const uint64_t BLOCK_BASES = 128ull << 20;
+static const uint64_t BLOCK_READS = 2ull << 20;
+static const size_t MAX_AHEAD = 4;          // files being decoded at the same time
 
-static const uint64_t BLOCK_BASES = 256ull << 20;
-static const uint64_t BLOCK_READS = 4ull << 20;
-
-static void flush_block(dbg_ctx *ctx, Block &b)
+static void consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod)
 {
-    if (b.n_reads == 0) return;
-    b.offs[b.n_reads] = b.n_bases;
-    int rc = dbg_submit_reads(ctx, b.bases, b.offs, b.n_reads);
-    if (rc) die("dbg_submit_reads", rc);
-    b.n_reads = 0; b.n_bases = 0;
-}
-
-static void add_read(dbg_ctx *ctx, Block &b, const string &s)
-{
-    // only the first maxReadLen bases of a read are used (DBGgraph.cpp:63); a sequence larger than a whole
-    // block (> 256 MB) is cut there -- the only effect is on the logged, untrimmed k-mer count
-    size_t n = s.size() > b.cap_bases ? (size_t)maxReadLen : s.size();
-    if (b.n_reads == b.cap_reads || b.n_bases + n > b.cap_bases) flush_block(ctx, b);
-    b.offs[b.n_reads++] = b.n_bases;
-    memcpy(b.bases + b.n_bases, s.data(), n);
-    b.n_bases += n;
-}
-
-// reader of parse_one_reads_file (DBGgraph.cpp:244-272); blocks never span files
-static void parse_one_reads_file_b200(dbg_ctx *ctx, Block &b, string &reads_file)
-{
-    string LineStr, Seq;
-    igzstream currentFile;
-    currentFile.open(reads_file.c_str());
     uint64_t in_block = 0;
-    if (Input_file_format == 1) {
-        while (getline(currentFile, LineStr, '\n')) {
-            if (LineStr[0] == '@') {
-                getline(currentFile, Seq, '\n');
-                getline(currentFile, LineStr, '\n');
-                getline(currentFile, LineStr, '\n');
-                add_read(ctx, b, Seq);
-                Total_reads_num++;
-                if (++in_block == (uint64_t)BufferNum) { cerr << "Load reads block " << Total_reads_num << endl; in_block = 0; }
-            }
+    for (;;) {
+        dbgio::ReadBlock *b = prod.pop();
+        if (prod.failed()) { cerr << "libdbgb200: out of page-locked host memory for the read blocks" << endl; exit(1); }
+        if (b->n_reads) {
+            int rc = dbg_submit_reads(ctx, b->bases, b->offs, b->n_reads);
+            if (rc) die("dbg_submit_reads", rc);
         }
-    } else {
-        while (getline(currentFile, LineStr, '\n')) {
-            if (LineStr[0] == '>') {
-                getline(currentFile, Seq, '\n');
-                add_read(ctx, b, Seq);
-                Total_reads_num++;
-                if (++in_block == (uint64_t)BufferNum) { cerr << "Load reads block " << Total_reads_num << endl; in_block = 0; }
-            }
+        // the "Load reads block" lines of the reference: one per BufferNum (-b) reads and one at the end of the file
+        uint64_t left = b->n_reads;
+        while (in_block + left >= (uint64_t)BufferNum) {
+            const uint64_t take = (uint64_t)BufferNum - in_block;
+            Total_reads_num += take; left -= take; in_block = 0;
+            cerr << "Load reads block " << Total_reads_num << endl;
         }
+        Total_reads_num += left; in_block += left;
+        const bool last = b->last;
+        prod.recycle(b);
+        if (last) break;
     }
     cerr << "Load reads block " << Total_reads_num << endl;
     cerr << "this block has reach the end of file " << endl;
-    flush_block(ctx, b);
-    currentFile.close();
 }
 
 static double wall_now()
@@ -164,27 +138,26 @@ void build_debruijn_graph(vector<string> &reads_files)
     time_end = clock();
     cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
 
-    Block b;
-    memset(&b, 0, sizeof(b));
-    b.cap_bases = BLOCK_BASES; b.cap_reads = BLOCK_READS;
-    void *p = NULL;
-    if ((rc = dbg_host_alloc(&p, b.cap_bases))) die("dbg_host_alloc", rc);
-    b.bases = (char *)p;
-    if ((rc = dbg_host_alloc(&p, (b.cap_reads + 1) * sizeof(uint64_t)))) die("dbg_host_alloc", rc);
-    b.offs = (uint64_t *)p;
-
     const double w1 = wall_now();
     cerr << "\nparse input reads files: " << endl;
-    for (size_t i = 0; i < reads_files.size(); i++) {
-        cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
-        parse_one_reads_file_b200(ctx, b, reads_files[i]);
-        dbg_stats st;
-        if ((rc = dbg_get_stats(ctx, &st))) die("dbg_get_stats", rc);
-        Kmer_total_num = st.kmers_logged;
-        cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
-        cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
-        time_end = clock();
-        cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+    {
+        std::vector<std::unique_ptr<dbgio::FileProducer> > prod(reads_files.size());
+        size_t started = 0;
+        for (size_t i = 0; i < reads_files.size(); i++) {
+            for (; started < reads_files.size() && started < i + MAX_AHEAD; started++)
+                prod[started].reset(new dbgio::FileProducer(reads_files[started], Input_file_format, (uint64_t)maxReadLen, BLOCK_BASES,
+                                                            BLOCK_READS, dbg_host_alloc, dbg_host_free));
+            cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
+            consume_file(ctx, *prod[i]);
+            prod[i].reset();
+            dbg_stats st;
+            if ((rc = dbg_get_stats(ctx, &st))) die("dbg_get_stats", rc);
+            Kmer_total_num = st.kmers_logged;
+            cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
+            cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
+            time_end = clock();
+            cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+        }
     }
 
     // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
@@ -215,8 +188,6 @@ void build_debruijn_graph(vector<string> &reads_files)
     cerr << "libdbgb200 wall clock (s): init " << w1 - w0 << ", read files + submit " << w2 - w1 << ", finalize (GPU build + layout) "
          << w3 - w2 << ", export kmerset " << w4 - w3 << endl;
 
-    dbg_host_free(b.bases);
-    dbg_host_free(b.offs);
     dbg_destroy(ctx);
 
     print_kmerset_parameter(kset);
