@@ -330,8 +330,8 @@ def test_table_full_is_reported_not_hung(dbg):
         assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
 
 
-@pytest.mark.parametrize("optimistic", ["1", "0", "overflow"])
-def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic):
+@pytest.mark.parametrize("optimistic,K", [("1", 31), ("0", 31), ("overflow", 31), ("1", 63), ("overflow", 63)])
+def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic, K):
     """multi-GPU building blocks on one device: extract tuples bucketed by owner shard, insert each bucket
     into that shard's context, union of shard dumps == oracle node multiset (ranks emulated in sequence).
     The owner-side partition of the received tuples runs optimistically (fixed bucket regions), exactly, and
@@ -344,15 +344,17 @@ def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic)
     reads = random_reads(71, 6000, 40, 150, genome_len=30000) + [b"A" * 60] * 50
     bases, offs = reads_to_arrays(reads)
     P_req = 300_000
-    o = oracle_build(oracle_mod, [(bases, offs)], 31, 150, P_req)
+    wide = K > 31
+    tb = 32 if wide else 16
+    o = oracle_build(oracle_mod, [(bases, offs)], K, 150, P_req, wide=wide)
     e = o.dump()
     db = torch.from_numpy(bases).cuda()
     do = torch.from_numpy(offs.astype(np.int64)).cuda()
     n_occ = o.occurrences
     for n_parts in (2, 3):
-        shards = [dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req, shard_rank=r, shard_count=n_parts) for r in range(n_parts)]
+        shards = [dbg.DBGBuilder(K=K, max_read_len=150, init_slots=P_req, shard_rank=r, shard_count=n_parts) for r in range(n_parts)]
         cap = int(offs[-1])
-        tuples = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
+        tuples = torch.empty(cap * (tb // 8), dtype=torch.int64, device="cuda")
         counts = torch.zeros(n_parts, dtype=torch.int64, device="cuda")
         # every rank extracts its own half of the reads (here: one extractor context does both halves)
         half = len(reads) // 2
@@ -365,35 +367,37 @@ def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic)
             c = counts.cpu().numpy()
             off = 0
             for q in range(n_parts):          # tuples are packed by owner: offsets = prefix sums of the counts
-                shards[q].insert_tuples_device(tuples.data_ptr() + 16 * off, int(c[q]))
+                shards[q].insert_tuples_device(tuples.data_ptr() + tb * off, int(c[q]))
                 off += int(c[q])
             torch.cuda.synchronize()
         polyA += shards[0].get_polyA_counts()
         total_nodes = 0
-        merged = {"kmer": [], "l": [], "r": []}
+        merged = {"kmer": [], "kmer_hi": [], "l": [], "r": []}
         for q, s in enumerate(shards):
             st = s.finalize()
             total_nodes += st["count"]
             d = s.dump_shard()
             assert len(d["kmer"]) == st["count"]
-            homes = np.array([dbg.capi.hash_code(int(k)) % o.size for k in d["kmer"][:500].tolist()], dtype=np.int64)
-            assert ((homes // ((o.size + n_parts - 1) // n_parts)) == q).all()
+            if not wide:
+                homes = np.array([dbg.capi.hash_code(int(k)) % o.size for k in d["kmer"][:500].tolist()], dtype=np.int64)
+                assert ((homes // ((o.size + n_parts - 1) // n_parts)) == q).all()
             for k in merged:
                 merged[k].append(d[k])
             s.close()
         assert total_nodes == o.count - 1            # shards do not carry the k-mer-0 node
-        nzm = e["kmer"] != 0
-        so = np.argsort(np.concatenate(merged["kmer"])); eo = np.argsort(e["kmer"][nzm])
-        for k in ("kmer", "l", "r"):
+        nzm = (e["kmer"] != 0) | (e["kmer_hi"] != 0)
+        so = np.lexsort((np.concatenate(merged["kmer"]), np.concatenate(merged["kmer_hi"])))
+        eo = np.lexsort((e["kmer"][nzm], e["kmer_hi"][nzm]))
+        for k in ("kmer", "kmer_hi", "l", "r"):
             assert np.array_equal(np.concatenate(merged[k])[so], e[k][nzm][eo]), (n_parts, k)
         exp_l = np.minimum(polyA[:4], 255); exp_r = np.minimum(polyA[4:], 255)
-        zero = e["kmer"] == 0
+        zero = ~nzm
         assert int(e["l"][zero][0]) == int(exp_l[0]) << 24 | int(exp_l[1]) << 16 | int(exp_l[2]) << 8 | int(exp_l[3])
         assert int(e["r"][zero][0]) == int(exp_r[0]) << 24 | int(exp_r[1]) << 16 | int(exp_r[2]) << 8 | int(exp_r[3])
     # tuples of ALL occurrences into one unsharded context == the fused path == the oracle (layout too)
-    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ex, dbg.DBGBuilder(K=31, max_read_len=150, init_slots=P_req) as ins:
+    with dbg.DBGBuilder(K=K, max_read_len=150, init_slots=P_req) as ex, dbg.DBGBuilder(K=K, max_read_len=150, init_slots=P_req) as ins:
         cap = int(offs[-1])
-        tuples = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
+        tuples = torch.empty(cap * (tb // 8), dtype=torch.int64, device="cuda")
         counts = torch.zeros(1, dtype=torch.int64, device="cuda")
         ex.extract_tuples_device(db.data_ptr(), do.data_ptr(), len(reads), 0, int(offs[-1]), 0, 1, tuples.data_ptr(), cap, counts.data_ptr())
         torch.cuda.synchronize()
@@ -402,7 +406,7 @@ def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic)
         st = ins.finalize()
         arr, nul = ins.export_kmerset()
     d = image_to_dump(arr, nul, o.size)
-    for k in ("slot", "kmer", "l", "r"):
+    for k in ("slot", "kmer", "l", "r") + (("kmer_hi",) if wide else ()):
         assert np.array_equal(d[k], e[k])
     o.close()
 
@@ -424,8 +428,9 @@ def test_medium_synthetic_matches_oracle(dbg, oracle_mod):
     o.close()
 
 
+@pytest.mark.parametrize("K", [31, 55])
 @pytest.mark.parametrize("variant", ["optimistic", "overflow_fallback", "exact", "unstaged"])
-def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatch, variant):
+def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatch, variant, K):
     """the partitioned build's variants on the medium C2-shaped case: the optimistic single-pass partition (fixed bucket
     regions), its overflow fallback (regions forced too small, so every block is redone by the exact two-pass
     partition -- and the side counters must not be double counted), the exact partition alone, and the scatter
@@ -450,8 +455,8 @@ def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatc
     eb = np.frombuffer(b"".join(extra), dtype=np.uint8)
     hb = np.concatenate([hb, eb]); ho = np.concatenate([ho, ho[-1] + 150 * np.arange(1, len(extra) + 1, dtype=ho.dtype)])
     init_slots = 12_000_000
-    o = oracle_build(oracle_mod, [(hb, ho)], 31, 150, init_slots)
-    with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=init_slots, load_factor=0.7) as b:
+    o = oracle_build(oracle_mod, [(hb, ho)], K, 150, init_slots, wide=K > 31)
+    with dbg.DBGBuilder(K=K, max_read_len=150, init_slots=init_slots, load_factor=0.7) as b:
         half = (n // 2)
         b.submit(hb, ho[: half + 1])
         b.submit(hb, ho[half:])
@@ -468,7 +473,7 @@ def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatc
     assert st["count"] == o.count and st["occurrences"] == o.occurrences and st["kmers_logged"] == o.kmers_logged
     e = o.dump()
     d = image_to_dump(arr, nul, o.size)
-    for k in ("slot", "kmer", "l", "r"):
+    for k in ("slot", "kmer", "l", "r") + (("kmer_hi",) if K > 31 else ()):
         assert np.array_equal(d[k], e[k]), k
     o.close()
 
