@@ -558,10 +558,12 @@ static bool want_partition(dbg_ctx *c, uint64_t occ_upper)
 {
     if (c->part_mode == 0) return false;
     if (c->part_mode == 1) return true;
-    // auto (measured on C2, profiles/README.md): the partitioned path costs ~47 ps per occurrence plus one
-    // streaming pass over the table per block (~0.4 ps per table byte), the direct path ~55 ps per occurrence
-    // whatever the table size -> partition when the block has more than about table_bytes / 20 occurrences
-    return c->n_buckets >= 2 && (double)occ_upper * 20.0 > (double)c->n_local * build_node_bytes(c);
+    // auto (measured, profiles/README.md): the partitioned path costs ~34 ps per occurrence with 64-bit keys (C2) and
+    // ~70 ps with 128-bit keys (C3) plus one streaming pass over the table per block (~0.17 ps per table byte); the
+    // direct path ~55 ps (64-bit) / ~130 ps (128-bit) per occurrence whatever the table size.  occ_upper counts BASES
+    // (about 0.6-0.8 occurrences each) -> partition when the block has more than table_bytes / 80 (/ 150) of them.
+    const double per_base = c->wide ? 150.0 : 80.0;
+    return c->n_buckets >= 2 && (double)occ_upper * per_base > (double)c->n_local * build_node_bytes(c);
 }
 
 static int ensure_matrix(dbg_ctx *c, uint64_t n_chunks, uint32_t nb = 0)
