@@ -114,6 +114,7 @@ public:
     }
     void recycle(ReadBlock *b)
     {
+        if (b == &sentinel_) return;
         { std::lock_guard<std::mutex> g(m_); b->n_reads = 0; b->n_bases = 0; b->last = false; free_list_.push_back(b); }
         cv_.notify_all();
     }
@@ -177,9 +178,8 @@ private:
     void publish_failure()
     {
         failed_ = true;
-        static ReadBlock sentinel;      // empty, last
-        sentinel.last = true;
-        { std::lock_guard<std::mutex> g(m_); ready_.push_back(&sentinel); }
+        sentinel_.last = true;          // empty, last: wakes the consumer, which checks failed()
+        { std::lock_guard<std::mutex> g(m_); ready_.push_back(&sentinel_); }
         cv_.notify_all();
     }
 
@@ -193,6 +193,7 @@ private:
     std::condition_variable cv_;
     std::deque<ReadBlock *> ready_, free_list_;
     std::vector<ReadBlock *> all_;
+    ReadBlock sentinel_;
     bool cancelled_ = false;
     volatile bool failed_ = false;
 };
