@@ -22,6 +22,7 @@ REF_DRIVER = os.path.join(REF_DIR, "ref_build_driver")
 REF_CONTIG = os.path.join(REF_DIR, "debruijn_contig_ref")
 REF_ELF = os.path.join(REF_DIR, "debruijn_contig_elf")
 B200_CONTIG = os.path.join(REF_DIR, "debruijn_contig_b200")
+CORRECT_ELF = os.path.join(REF_DIR, "correct_error_reads_elf")   # shipped consumer of the .cz table
 
 _lib = None
 

@@ -43,6 +43,107 @@ def test_cz_loader_restatement_roundtrip(oracle_mod, tmp_path):
     assert np.array_equal(both, both_strand_bits(counts, K, cutoff, oracle_mod))
 
 
+def _sim_reads(seed, genome_len, n_reads, L=100, err=0.01):
+    rng = np.random.default_rng(seed)
+    genome = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=genome_len).tolist())
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads = []
+    for _ in range(n_reads):
+        p = int(rng.integers(0, genome_len - L))
+        r = bytearray(genome[p:p + L])
+        for j in np.nonzero(rng.random(L) < err)[0].tolist():
+            r[j] = b"ACGT"[(b"ACGT".index(r[j]) + int(rng.integers(1, 4))) % 4]
+        r = bytes(r)
+        reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)
+    return reads
+
+
+def _write_cz_1bit(prefix, counts, cutoff):
+    """the format correct_error loads (main_parallel_senior.cpp:334-408): zlib streams of 1 MiB of bits (8 Mi k-mers)"""
+    bits = np.packbits((counts > cutoff).astype(np.uint8))
+    lens = []
+    with open(prefix + ".kmer.freq.cz", "wb") as f:
+        for i in range(0, len(bits), 1 << 20):
+            c = zlib.compress(bits[i:i + (1 << 20)].tobytes())
+            f.write(c); lens.append(len(c))
+    with open(prefix + ".kmer.freq.cz.len", "w") as f:
+        f.write("".join(f"{n}\n" for n in lens))
+
+
+def _run_correct_error(orc, workdir, prefix, reads, K, tag):
+    """the reference's own consumer (shipped binary, oracle/_ref/correct_error_reads_elf): loads <prefix>.kmer.freq.cz
+    and corrects the reads; returns (number of high-frequency k-mers it found in the table, corrected FASTA bytes)"""
+    import gzip
+    import subprocess
+    fa = os.path.join(workdir, f"r_{tag}.fa.gz")
+    with gzip.open(fa, "wb", compresslevel=1) as f:
+        for i, r in enumerate(reads):
+            f.write(b">r%d\n%s\n" % (i, r))
+    lib = os.path.join(workdir, f"r_{tag}.lib")
+    with open(lib, "w") as f:
+        f.write(fa + "\n")
+    p = subprocess.run([orc.CORRECT_ELF, "-k", str(K), "-c", "2", "-f", "2", "-t", "1", "-r", "50", prefix + ".kmer.freq.cz", lib],
+                       cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    log = p.stdout.decode()
+    hifreq = int(log.split("Kmer_hifreq_num")[1].split()[0])
+    return hifreq, gzip.open(fa + ".correct.fa.gz").read()
+
+
+def test_cz_format_is_what_the_reference_consumer_loads(oracle_mod, tmp_path):
+    """CPU pin of the table format against the REAL loader: the shipped correct_error_reads reads a .cz/.cz.len written
+    by this test's plain-zlib writer, reports exactly the number of set canonical entries, and corrects reads with it
+    (most erroneous reads come back as their error-free originals' length, almost nothing is deleted)"""
+    if not os.path.exists(oracle_mod.CORRECT_ELF):
+        pytest.skip("oracle/_ref/correct_error_reads_elf not present (make -C oracle ref)")
+    K, cutoff = 13, 3
+    reads = _sim_reads(3, 30_000, 12_000)
+    bases, offs = reads_to_arrays(reads)
+    counts = oracle_mod.kfreq_count(bases, offs, K)
+    prefix = str(tmp_path / "tab")
+    _write_cz_1bit(prefix, counts, cutoff)
+    both, canon = oracle_mod.load_cz_1bit(prefix, K)
+    hifreq, corrected = _run_correct_error(oracle_mod, str(tmp_path), prefix, reads, K, "cpu")
+    assert hifreq == int(canon.sum()) == int((counts > cutoff).sum())
+    heads = [l for l in corrected.split(b"\n") if l.startswith(b">")]
+    assert len(heads) > 0.95 * len(reads)                      # few reads deleted: the table marks the genome's k-mers
+    modified = sum(1 for h in heads if b"ModifiedBaseNum: 0" not in h)
+    assert modified > 0.3 * len(reads)                         # ~63 % of the reads carry an error; most are corrected
+    # a table with the bit order reversed (LSB first) is a different table for the consumer
+    bad = str(tmp_path / "bad")
+    bits = np.packbits((counts > cutoff).astype(np.uint8), bitorder="little")
+    c = [zlib.compress(bits[i:i + (1 << 20)].tobytes()) for i in range(0, len(bits), 1 << 20)]
+    open(bad + ".kmer.freq.cz", "wb").write(b"".join(c))
+    open(bad + ".kmer.freq.cz.len", "w").write("".join(f"{len(x)}\n" for x in c))
+    _, corrected_bad = _run_correct_error(oracle_mod, str(tmp_path), bad, reads, K, "bad")
+    assert corrected_bad != corrected
+
+
+@pytest.mark.gpu
+def test_gpu_table_drives_the_reference_consumer_identically(oracle_mod, tmp_path):
+    """SURVEY 8c round trip: the table written by the GPU library is loaded by the shipped correct_error_reads and
+    corrects the reads exactly as the table written from the CPU oracle's counts does"""
+    from dbg_assembly_b200.kfreq import KmerFreq
+    if not os.path.exists(oracle_mod.CORRECT_ELF):
+        pytest.skip("oracle/_ref/correct_error_reads_elf not present")
+    K, cutoff = 13, 3
+    reads = _sim_reads(4, 30_000, 12_000)
+    bases, offs = reads_to_arrays(reads)
+    counts = oracle_mod.kfreq_count(bases, offs, K)
+    cpu_prefix = str(tmp_path / "cpu")
+    _write_cz_1bit(cpu_prefix, counts, cutoff)
+    gpu_prefix = str(tmp_path / "gpu")
+    with KmerFreq(K=K) as kf:
+        kf.submit(bases, offs)
+        kf.finalize()
+        kf.write_cz(gpu_prefix, bits=1, cutoff=cutoff)
+    assert open(gpu_prefix + ".kmer.freq.cz.len").read().split() and len(open(gpu_prefix + ".kmer.freq.cz.len").read().split()) == 8
+    h_cpu, out_cpu = _run_correct_error(oracle_mod, str(tmp_path), cpu_prefix, reads, K, "cpu")
+    h_gpu, out_gpu = _run_correct_error(oracle_mod, str(tmp_path), gpu_prefix, reads, K, "gpu")
+    assert h_gpu == h_cpu == int((counts > cutoff).sum())
+    assert out_gpu == out_cpu
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("K", [5, 9, 13])
 def test_kfreq_counts_match_oracle(oracle_mod, tmp_path, K):
