@@ -234,3 +234,37 @@ def test_kfreq_k17_shape_and_sharding(oracle_mod, tmp_path):
             assert (a, b) == (r * 4 ** 17 // 2, (r + 1) * 4 ** 17 // 2)
             parts.append(kf.export(bits=1, cutoff=0))
     assert np.array_equal(np.concatenate(parts), bits)
+
+
+@pytest.mark.gpu
+def test_kmerfreq_front_end_writes_the_table_files(oracle_mod, tmp_path):
+    """integration/kmerfreq_b200.cpp: same command line as the pipeline's `kmerfreq -k K -m 1 -q Q reads.lib`
+    (test/01.clean_correct/work.sh:18); two gzip FASTA files through the threaded reader; the three output files land
+    next to the library file and hold the oracle's counts"""
+    import gzip
+    import subprocess
+    exe = os.path.join(REPO, "integration", "_bin", "kmerfreq_b200")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(REPO, "integration"), "all"], check=True, timeout=300)
+    K, cutoff = 11, 2
+    reads = _sim_reads(9, 20_000, 6_000) + [b"ACGT", b"", b"N" * 40]
+    half = len(reads) // 2
+    paths = []
+    for t, part in enumerate((reads[:half], reads[half:])):
+        p = str(tmp_path / f"part{t}.fa.gz")
+        with gzip.open(p, "wb", compresslevel=1) as f:
+            for i, r in enumerate(part):
+                f.write(b">r%d\n%s\n" % (i, r))
+        paths.append(p)
+    lib = str(tmp_path / "reads.lib")
+    with open(lib, "w") as f:
+        f.write("\n".join(paths) + "\n")
+    p = subprocess.run([exe, "-k", str(K), "-f", "2", "-m", "1", "-q", str(cutoff), lib], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    bases, offs = reads_to_arrays(reads)
+    counts = oracle_mod.kfreq_count(bases, offs, K)
+    both, canon = oracle_mod.load_cz_1bit(lib, K)
+    assert np.array_equal(canon, (counts > cutoff).astype(np.uint8))
+    lines = open(lib + ".kmer.freq.stat").read().split("\n")
+    assert lines[0] == f"#Kmer size: {K}" and lines[2] == f"#Kmer indivdual number: {int(counts.sum())}"
+    assert lines[3] == f"#Kmer species number: {int((counts > 0).sum())}"
