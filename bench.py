@@ -371,8 +371,11 @@ def run_b200(args):
             line["cpu_baseline"] = dict(info, value=float(np.mean(vals)), unit=UNIT)
             if info["kind"] == "reference" and threads > 1:
                 # the reference with -t 1 beside the all-cores figure (same sample)
-                vals1, _ = cpu_reference_run(cfg1, sample, 1, 1, 0, args.workload)
-                line["cpu_baseline"]["value_t1"] = float(np.mean(vals1))
+                try:
+                    vals1, _ = cpu_reference_run(cfg1, sample, 1, 1, 0, args.workload)
+                    line["cpu_baseline"]["value_t1"] = float(np.mean(vals1))
+                except Exception as e1:
+                    line["cpu_baseline"]["value_t1_error"] = str(e1)
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
 
