@@ -43,6 +43,19 @@ class dbg_synth_params(C.Structure):
                 ("err_per_2p24", C.c_uint32), ("n_per_2p24", C.c_uint32)]
 
 
+class dbg_growth_params(C.Structure):
+    _fields_ = [("init_slots", C.c_uint64), ("load_factor", C.c_float), ("wide", C.c_int32),
+                ("max_double_times", C.c_uint64), ("buffer_reads", C.c_uint64)]
+
+
+class dbg_growth_result(C.Structure):
+    _fields_ = [("final_size", C.c_uint64), ("final_max", C.c_uint64), ("doublings", C.c_uint64), ("count", C.c_uint64),
+                ("truncated", C.c_int32), ("truncated_file", C.c_uint32), ("truncated_first_read", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class kfreq_params(C.Structure):
     _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("block_rank", C.c_int32), ("block_count", C.c_int32),
                 ("reserved", C.c_int32 * 4)]
@@ -55,7 +68,7 @@ SYMBOLS = [
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
     "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device", "dbg_insert_sliced_device", "dbg_partition_info",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
-    "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count", "dbg_path_counts",
+    "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count", "dbg_path_counts", "dbg_replay_growth",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
     "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
@@ -112,6 +125,8 @@ def load(build_if_missing: bool = True):
         "dbg_get_timings": (C.c_int, [vp, vp]),
         "dbg_launch_count": (u64, [vp]),
         "dbg_path_counts": (C.c_int, [vp, vp]),
+        "dbg_replay_growth": (C.c_int, [C.POINTER(dbg_growth_params), vp, C.c_uint32, vp, vp, vp, vp, vp, u64, C.c_uint32, C.c_uint32,
+                              C.POINTER(dbg_growth_result), vp, vp]),
         "dbg_reset": (C.c_int, [vp]),
         "dbg_set_stream": (C.c_int, [vp, vp]),
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),

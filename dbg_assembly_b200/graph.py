@@ -257,6 +257,39 @@ class DBGBuilder:
         return dict(direct=int(c[0]), exact=int(c[1]), optimistic=int(c[2]), overflows=int(c[3]))
 
 
+def replay_growth(nodes, reads_per_file, init_slots, load_factor=0.7, max_double_times=10, buffer_reads=10000,
+                  polyA_l=0, polyA_r=0, layout=True):
+    """Host-side replay of the reference's table growth (-e / enlarge) from a finished graph: `nodes` is the dict that
+    DBGBuilder.dump_shard() returns (kmer, kmer_hi, l, r, ord; no k-mer-0 node).  Returns (plan dict, array, nul_flag);
+    array/nul_flag are None when layout=False, or when the reference would have dropped reads (plan["truncated"]).
+    The table comes back in the reference's slot layout AFTER its doublings (dbg_replay_growth, include/dbg_b200.h)."""
+    L = capi.load()
+    n = len(nodes["kmer"])
+    wide = bool(np.any(nodes.get("kmer_hi", np.zeros(0, np.uint64)) != 0)) or bool(nodes.get("wide", False))
+    klo = np.ascontiguousarray(nodes["kmer"], dtype=np.uint64)
+    khi = np.ascontiguousarray(nodes["kmer_hi"], dtype=np.uint64) if "kmer_hi" in nodes else np.zeros(n, np.uint64)
+    ll = np.ascontiguousarray(nodes["l"], dtype=np.uint32); rr = np.ascontiguousarray(nodes["r"], dtype=np.uint32)
+    oo = np.ascontiguousarray(nodes["ord"], dtype=np.uint64)
+    rpf = np.ascontiguousarray(reads_per_file, dtype=np.uint64)
+    g = capi.dbg_growth_params(int(init_slots), float(load_factor), int(wide), int(max_double_times), int(buffer_reads))
+    res = capi.dbg_growth_result()
+
+    def call(arr, nul):
+        capi.check(L.dbg_replay_growth(C.byref(g), rpf.ctypes.data, len(rpf), klo.ctypes.data, khi.ctypes.data, ll.ctypes.data,
+                                       rr.ctypes.data, oo.ctypes.data, n, int(polyA_l), int(polyA_r), C.byref(res),
+                                       arr.ctypes.data if arr is not None else None, nul.ctypes.data if nul is not None else None),
+                   "dbg_replay_growth")
+
+    call(None, None)
+    plan = res.as_dict()
+    if not layout or plan["truncated"]:
+        return plan, None, None
+    arr = np.zeros(plan["final_size"], dtype=NODE32 if wide else NODE16)
+    nul = np.zeros(plan["final_size"] // 8 + 1, dtype=np.uint8)
+    call(arr, nul)
+    return res.as_dict(), arr, nul
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference-shaped interface
 # ---------------------------------------------------------------------------------------------------

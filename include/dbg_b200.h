@@ -211,6 +211,32 @@ int  dbg_synth_reads_host(const dbg_synth_params *p, uint64_t first_read, uint64
 int  dbg_synth_reads_device(const dbg_synth_params *p, uint64_t first_read, uint64_t n_reads, char *d_out,
                             int32_t device, void *stream);
 
+/* ---- host-side replay of the reference's table growth (-e / enlarge) ------------
+ * The GPU table is sized once from -i.  When a run outgrows it (count > max at a block boundary of -b reads), the
+ * reference doubles its table in place (DBGgraph.cpp:337-351, kmerSet.cpp:132-189): same nodes, different slot layout.
+ * dbg_replay_growth rebuilds that layout on the HOST from the finished graph: the nodes with their first-occurrence
+ * ordinals (dbg_dump_shard on an unsharded context; the k-mer-0 node excluded, its link words passed separately) and
+ * the number of reads in every input file.  Call it with array == NULL first: `res` tells whether the reference would
+ * have grown (doublings > 0), the final table size to allocate, or `truncated` (-e exhausted: the reference drops the
+ * rest of a file, which no replay of a full build can reproduce -- nothing is written).  Sequential, ~50 ns per node. */
+typedef struct {
+    uint64_t init_slots;        /* (uint64)(-i * 1e9), as in dbg_params                     */
+    float    load_factor;       /* -l                                                       */
+    int32_t  wide;              /* 1: 128-bit keys (kmer_hi given, 32-byte export nodes)    */
+    uint64_t max_double_times;  /* -e                                                       */
+    uint64_t buffer_reads;      /* -b  reads per block (grow check after every full block)  */
+} dbg_growth_params;
+typedef struct {
+    uint64_t final_size, final_max, doublings, count;   /* KmerSet.size / .max / doubleHashTimes / .count (incl. k-mer 0) */
+    int32_t  truncated;                                   /* 1: "Memory reach the maximum allowed" would have hit          */
+    uint32_t truncated_file;                              /*    in this file (index into reads_per_file) ...               */
+    uint64_t truncated_first_read;                        /*    ... from this global read index on                         */
+} dbg_growth_result;
+int  dbg_replay_growth(const dbg_growth_params *g, const uint64_t *reads_per_file, uint32_t n_files,
+                       const uint64_t *kmer_lo, const uint64_t *kmer_hi, const uint32_t *l_link, const uint32_t *r_link,
+                       const uint64_t *first_ordinal, uint64_t n_nodes, uint32_t polyA_l, uint32_t polyA_r,
+                       dbg_growth_result *res, void *array, uint8_t *nul_flag);
+
 /* ---- K-mer frequency table for correct_error ---------------------------------
  * What the external `kmerfreq` program writes and correct_error loads (correct_error/main_parallel_senior.cpp:
  * 273-408 1-bit form, correct_error/main.cpp:161-220 8-bit form): canonical k-mer counts in a direct-index table

@@ -12,9 +12,10 @@
 // (thread_parseBlock / thread_updatekmers) run as CUDA kernels; the finished table comes back in the
 // reference's slot layout (== `debruijn_contig -t 1`) as the global `KmerSet *kset`.
 //
-// Differences a user can observe: the "conflict:" statistic counts GPU probe steps, "-t" only affects the
-// host traversal, and "-e" (enlarge) is not emulated: if the node count passes max_cutoff a warning is
-// printed (the reference would have enlarged and produced a different slot order; contents are the same).
+// Differences a user can observe: the "conflict:" statistic counts GPU probe steps, "-t" only affects the host
+// traversal.  Table growth ("-e", enlarge) never happens on the GPU; when the reference would have grown its table
+// the post-growth slot layout is replayed on the host (dbg_replay_growth).  Only when "-e" would have been exhausted
+// (the reference then ignores the rest of a file) does the result differ: all reads are used, and an alert says so.
 #include <chrono>
 #include <memory>
 #include <thread>
@@ -67,30 +68,37 @@ static const uint64_t BLOCK_BASES = 128ull << 20;
 static const uint64_t BLOCK_READS = 2ull << 20;
 static const size_t MAX_AHEAD = 4;          // files being decoded at the same time
 
-static void consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod)
+// returns false when the device table turned out to be too small for the input (the caller rebuilds with a larger one)
+static bool consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod, bool quiet)
 {
     uint64_t in_block = 0;
+    bool full = false;
     for (;;) {
         dbgio::ReadBlock *b = prod.pop();
         if (prod.failed()) { cerr << "libdbgb200: out of page-locked host memory for the read blocks" << endl; exit(1); }
         if (b->n_reads) {
             int rc = dbg_submit_reads(ctx, b->bases, b->offs, b->n_reads);
-            if (rc) die("dbg_submit_reads", rc);
+            if (rc == DBG_ERR_TABLE_FULL) full = true;
+            else if (rc) die("dbg_submit_reads", rc);
         }
+        if (full) { prod.recycle(b); return false; }      // the producer is cancelled by its owner
         // the "Load reads block" lines of the reference: one per BufferNum (-b) reads and one at the end of the file
         uint64_t left = b->n_reads;
         while (in_block + left >= (uint64_t)BufferNum) {
             const uint64_t take = (uint64_t)BufferNum - in_block;
             Total_reads_num += take; left -= take; in_block = 0;
-            cerr << "Load reads block " << Total_reads_num << endl;
+            if (!quiet) cerr << "Load reads block " << Total_reads_num << endl;
         }
         Total_reads_num += left; in_block += left;
         const bool last = b->last;
         prod.recycle(b);
         if (last) break;
     }
-    cerr << "Load reads block " << Total_reads_num << endl;
-    cerr << "this block has reach the end of file " << endl;
+    if (!quiet) {
+        cerr << "Load reads block " << Total_reads_num << endl;
+        cerr << "this block has reach the end of file " << endl;
+    }
+    return !full;
 }
 
 static double wall_now()
@@ -122,12 +130,10 @@ void build_debruijn_graph(vector<string> &reads_files)
     prm.load_factor = hashLoadFactor;
     prm.device = getenv("DBG_B200_DEVICE") ? atoi(getenv("DBG_B200_DEVICE")) : 0;
     prm.track_order = 1;                                        // reproduce the -t 1 slot layout
-    dbg_ctx *ctx = NULL;
-    int rc = dbg_create(&ctx, &prm);
-    if (rc) die("dbg_create", rc);
+    const uint64_t ref_init_slots = prm.init_slots;              // what the reference sizes (and grows) its table from
     // the KmerSet the traversal consumes (kmerSet.h:88-99): allocated page-locked, in the background while the
     // reads are being parsed, so that the export is one PCIe-rate copy instead of a page-faulting pageable one
-    const uint64_t P_slots = prm.init_slots < 3 ? 3 : dbg_find_next_prime(prm.init_slots);   // kmerSet.cpp:102-103
+    const uint64_t P_slots = ref_init_slots < 3 ? 3 : dbg_find_next_prime(ref_init_slots);   // kmerSet.cpp:102-103
     KmerNode *pinned_array = NULL;
     std::thread alloc_thread([&]() {
         void *q = NULL;
@@ -135,55 +141,133 @@ void build_debruijn_graph(vector<string> &reads_files)
     });
     cerr << "Hash initialization array size:  " << initHashSize << " G" << endl;
     cerr << "The initialization memory used:  " << initHashSize * 16 << " G" << endl;
-    time_end = clock();
-    cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
 
-    const double w1 = wall_now();
-    cerr << "\nparse input reads files: " << endl;
-    {
-        std::vector<std::unique_ptr<dbgio::FileProducer> > prod(reads_files.size());
-        size_t started = 0;
-        for (size_t i = 0; i < reads_files.size(); i++) {
-            for (; started < reads_files.size() && started < i + MAX_AHEAD; started++)
-                prod[started].reset(new dbgio::FileProducer(reads_files[started], Input_file_format, (uint64_t)maxReadLen, BLOCK_BASES,
-                                                            BLOCK_READS, dbg_host_alloc, dbg_host_free));
-            cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
-            consume_file(ctx, *prod[i]);
-            prod[i].reset();
-            dbg_stats st;
-            if ((rc = dbg_get_stats(ctx, &st))) die("dbg_get_stats", rc);
-            Kmer_total_num = st.kmers_logged;
-            cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
-            cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
+    // The device table never grows.  If -i turns out too small to even HOLD the nodes (the reference would have
+    // enlarged its table, -e), the build is simply redone with a larger device table: the reads are streamed again, a
+    // full build takes milliseconds, and the table the traversal gets is laid out by the growth replay further down from
+    // the reference's own -i, so the size of the device table never shows.
+    dbg_ctx *ctx = NULL;
+    int rc = 0;
+    dbg_stats st;
+    std::vector<uint64_t> reads_per_file;
+    double w1 = 0, w2 = 0;
+    for (int attempt = 0;; attempt++) {
+        rc = dbg_create(&ctx, &prm);
+        if (rc) die("dbg_create", rc);
+        if (attempt == 0) {
             time_end = clock();
             cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+            w1 = wall_now();
+            cerr << "\nparse input reads files: " << endl;
         }
+        bool fits = true;
+        Total_reads_num = 0;
+        reads_per_file.clear();
+        {
+            std::vector<std::unique_ptr<dbgio::FileProducer> > prod(reads_files.size());
+            size_t started = 0;
+            for (size_t i = 0; i < reads_files.size() && fits; i++) {
+                for (; started < reads_files.size() && started < i + MAX_AHEAD; started++)
+                    prod[started].reset(new dbgio::FileProducer(reads_files[started], Input_file_format, (uint64_t)maxReadLen, BLOCK_BASES,
+                                                                BLOCK_READS, dbg_host_alloc, dbg_host_free));
+                if (attempt == 0) cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
+                const uint64_t reads_before = Total_reads_num;
+                fits = consume_file(ctx, *prod[i], attempt > 0);
+                reads_per_file.push_back(Total_reads_num - reads_before);
+                prod[i].reset();
+                if (fits) {
+                    rc = dbg_get_stats(ctx, &st);
+                    if (rc == DBG_ERR_TABLE_FULL) fits = false;
+                    else if (rc) die("dbg_get_stats", rc);
+                }
+                if (fits) {
+                    Kmer_total_num = st.kmers_logged;
+                    cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
+                    cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
+                    time_end = clock();
+                    cerr << "Finished! Run time: " << double(time_end - time_start) / CLOCKS_PER_SEC << endl;
+                }
+            }
+        }
+        // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
+        w2 = wall_now();
+        if (fits) {
+            rc = dbg_finalize(ctx, &st);
+            if (rc == DBG_ERR_TABLE_FULL) fits = false;
+            else if (rc) die("dbg_finalize", rc);
+        }
+        if (fits) break;
+        dbg_destroy(ctx);
+        ctx = NULL;
+        if (attempt >= 12) { cerr << "libdbgb200: the input does not fit a device table of " << prm.init_slots << " slots" << endl; exit(1); }
+        prm.init_slots = prm.init_slots < 1024 ? 2048 : prm.init_slots * 2;
+        cerr << "libdbgb200: -i " << initHashSize << " cannot hold this input; rebuilding with a device table of " << prm.init_slots
+             << " slots (the CPU program would have enlarged its hash)" << endl;
     }
-
-    // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
-    const double w2 = wall_now();
-    dbg_stats st;
-    if ((rc = dbg_finalize(ctx, &st))) die("dbg_finalize", rc);
-    if (st.count - 1 > st.max_cutoff)
-        cerr << "\nAlert message: " << st.count << " kmer nodes exceed max_cutoff " << st.max_cutoff
-             << "; the CPU program would have enlarged its hash (-e). Node contents are unaffected, slot order may differ: raise -i\n" << endl;
+    // Did the reference grow its table on this input (-e / enlarge, DBGgraph.cpp:337-351)?  Only possible if the final
+    // node count passed max_cutoff.  The GPU table never grows; the reference's post-growth slot layout is replayed on the
+    // host from the nodes' first-occurrence ordinals (dbg_replay_growth) so that the traversal sees the table it expects.
+    dbg_growth_result grow;
+    memset(&grow, 0, sizeof(grow));
+    std::vector<uint64_t> g_kmer, g_ord;
+    std::vector<uint32_t> g_l, g_r;
+    float ref_lf = hashLoadFactor;
+    if (ref_lf <= 0) ref_lf = 0.25f; else if (ref_lf >= 1) ref_lf = 0.75f;      // kmerSet.cpp:110-111
+    const uint64_t ref_max = (uint64_t)(P_slots * ref_lf);
+    if (st.count - 1 > ref_max) {
+        uint64_t n = 0;
+        if ((rc = dbg_dump_shard(ctx, NULL, NULL, NULL, NULL, NULL, &n))) die("dbg_dump_shard", rc);
+        g_kmer.resize(n + 1); g_ord.resize(n + 1); g_l.resize(n + 1); g_r.resize(n + 1);
+        uint64_t cap = n + 1;
+        if ((rc = dbg_dump_shard(ctx, g_kmer.data(), NULL, g_l.data(), g_r.data(), g_ord.data(), &cap))) die("dbg_dump_shard", rc);
+        dbg_growth_params gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.init_slots = ref_init_slots; gp.load_factor = hashLoadFactor; gp.wide = 0;
+        gp.max_double_times = maxDoubleHashTimes; gp.buffer_reads = (uint64_t)BufferNum;
+        rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g_kmer.data(), NULL, g_l.data(), g_r.data(),
+                               g_ord.data(), n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, &grow, NULL, NULL);
+        if (rc) die("dbg_replay_growth", rc);
+        if (grow.truncated)
+            cerr << "\nAlert message: Memory reach the maximum allowed in the CPU program (-e " << maxDoubleHashTimes
+                 << "): it would have ignored the reads of file " << grow.truncated_file << " from read " << grow.truncated_first_read
+                 << " on; this build used all reads. Raise -i or -e.\n" << endl;
+        else if (grow.doublings)
+            cerr << "\nHash enlarged " << grow.doublings << " time(s) by the CPU program's rule: array size " << grow.final_size << endl;
+    }
+    const bool grown = grow.doublings > 0 && !grow.truncated;
+    doubleHashTimes = grown ? grow.doublings : 0;
 
     // the KmerSet the traversal consumes (kmerSet.h:88-99, kmerSet.cpp:98-127)
     kset = new KmerSet;
     kset->e_size = sizeof(KmerNode);
-    kset->size = st.array_size;
+    if (!grown && st.array_size != P_slots) {
+        // only reachable when the replay refused (-e exhausted) after the device table had to be enlarged
+        cerr << "libdbgb200: this input needs more than -i " << initHashSize << " and -e " << maxDoubleHashTimes << " allow; raise -i" << endl;
+        exit(1);
+    }
+    kset->size = grown ? grow.final_size : st.array_size;
     kset->count = st.count;
     kset->count_conflict = st.conflict;
     kset->load_factor = st.load_factor;
-    kset->max = st.max_cutoff;
+    kset->max = grown ? grow.final_max : st.max_cutoff;
     kset->iter_ptr = 0;
     alloc_thread.join();
+    if (grown && pinned_array) { dbg_host_free(pinned_array); pinned_array = NULL; }
     kset->array = (pinned_array && P_slots == kset->size) ? pinned_array : (KmerNode *)malloc(kset->size * kset->e_size);
     kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
     kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
     if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
     const double w3 = wall_now();
-    if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
+    if (grown) {
+        const uint64_t n = g_kmer.size() - 1;
+        dbg_growth_params gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.init_slots = ref_init_slots; gp.load_factor = hashLoadFactor; gp.wide = 0;
+        gp.max_double_times = maxDoubleHashTimes; gp.buffer_reads = (uint64_t)BufferNum;
+        rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g_kmer.data(), NULL, g_l.data(), g_r.data(),
+                               g_ord.data(), n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, &grow, kset->array, kset->nul_flag);
+        if (rc) die("dbg_replay_growth", rc);
+    } else if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
     const double w4 = wall_now();
     cerr << "libdbgb200 wall clock (s): init " << w1 - w0 << ", read files + submit " << w2 - w1 << ", finalize (GPU build + layout) "
          << w3 - w2 << ", export kmerset " << w4 - w3 << endl;
