@@ -349,22 +349,54 @@ def _is_gzip(path):
 
 
 def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_format=1, initHashSize=1.0,
-                         hashLoadFactor=0.7, BufferNum=10000, device=0, track_order=True, log=None):
+                         hashLoadFactor=0.7, BufferNum=10000, maxDoubleHashTimes=10, device=0, track_order=True, log=None):
     """build_debruijn_graph (DBGgraph.cpp:364-430) with the build phase on the GPU.  `reads_files` is the
-    list reading_file_list() returns (seqKmer.cpp:101-114), or a list of (bases, offs) arrays."""
+    list reading_file_list() returns (seqKmer.cpp:101-114), or a list of (bases, offs) arrays.
+    Table growth (-e): the device table never grows; when -i cannot hold the nodes the build is redone with a larger
+    device table, and when the reference would have enlarged its hash the returned KmerSet is laid out by the
+    host-side replay of its doublings (replay_growth), exactly like integration/DBGgraph_b200.cpp."""
     log = log or (lambda s: None)
-    with DBGBuilder(K=KmerSize, max_read_len=maxReadLen, init_g=initHashSize, load_factor=hashLoadFactor,
-                    device=device, track_order=track_order) as b:
-        for f in reads_files:
-            bases, offs = f if isinstance(f, tuple) else read_reads_file(f, Input_file_format)
-            b.submit(bases, offs)
-        st = b.finalize()
-        if st["count"] - 1 > st["max_cutoff"]:
-            print("Alert: node count exceeds max_cutoff; the reference may have enlarged its hash here, "
-                  "slot layout parity with the reference is not guaranteed (raise -i)", file=sys.stderr)
-        array, nul = b.export_kmerset()
-        ks = KmerSet(e_size=32 if b.wide else 16, size=st["array_size"], count=st["count"], count_conflict=st["conflict"],
-                     max=st["max_cutoff"], load_factor=st["load_factor"], iter_ptr=0, array=array, nul_flag=nul,
-                     del_flag=np.zeros(st["array_size"] // 8 + 1, dtype=np.uint8), Total_reads_num=st["reads"],
-                     Kmer_total_num=st["kmers_logged"], occurrences=st["occurrences"], timings=b.timings())
-    return ks
+    files = [f if isinstance(f, tuple) else read_reads_file(f, Input_file_format) for f in reads_files]
+    ref_slots = init_slots_from_g(initHashSize)
+    ref_P = 3 if ref_slots < 3 else capi.find_next_prime(ref_slots)
+    lf = np.float32(hashLoadFactor)
+    lf = np.float32(0.25) if lf <= 0 else (np.float32(0.75) if lf >= 1 else lf)
+    ref_max = int(np.float32(ref_P) * lf)                       # uint64 * float -> float, kmerSet.cpp:115
+    dev_slots = ref_slots
+    for attempt in range(13):
+        try:
+            with DBGBuilder(K=KmerSize, max_read_len=maxReadLen, init_slots=dev_slots, load_factor=hashLoadFactor,
+                            device=device, track_order=track_order) as b:
+                for bases, offs in files:
+                    b.submit(bases, offs)
+                st = b.finalize()
+                plan = None
+                if st["count"] - 1 > ref_max and track_order:
+                    nodes = b.dump_shard()
+                    nodes["wide"] = b.wide
+                    rpf = [len(offs) - 1 for _, offs in files]
+                    plan, garr, gnul = replay_growth(nodes, rpf, ref_slots, hashLoadFactor, maxDoubleHashTimes, BufferNum,
+                                                     st["polyA_l"], st["polyA_r"])
+                    if plan["truncated"]:
+                        print(f"Alert: the CPU program would have run out of -e {maxDoubleHashTimes} doublings and ignored the reads of "
+                              f"file {plan['truncated_file']} from read {plan['truncated_first_read']} on; this build used all reads "
+                              "(raise -i or -e)", file=sys.stderr)
+                grown = plan is not None and plan["doublings"] > 0 and not plan["truncated"]
+                if grown:
+                    array, nul, size, mx = garr, gnul, plan["final_size"], plan["final_max"]
+                else:
+                    if st["array_size"] != ref_P:
+                        raise capi.DbgError(capi.DBG_ERR_TABLE_FULL, "build_debruijn_graph",
+                                            f"the input needs more than -i {initHashSize} and -e {maxDoubleHashTimes} allow")
+                    array, nul = b.export_kmerset()
+                    size, mx = st["array_size"], st["max_cutoff"]
+                return KmerSet(e_size=32 if b.wide else 16, size=size, count=st["count"], count_conflict=st["conflict"],
+                               max=mx, load_factor=st["load_factor"], iter_ptr=0, array=array, nul_flag=nul,
+                               del_flag=np.zeros(size // 8 + 1, dtype=np.uint8), Total_reads_num=st["reads"],
+                               Kmer_total_num=st["kmers_logged"], occurrences=st["occurrences"], timings=b.timings())
+        except capi.DbgError as e:
+            if e.code != capi.DBG_ERR_TABLE_FULL or attempt == 12:
+                raise
+            dev_slots = 2048 if dev_slots < 1024 else dev_slots * 2
+            log(f"-i {initHashSize} cannot hold this input; rebuilding with a device table of {dev_slots} slots")
+    raise AssertionError("unreachable")

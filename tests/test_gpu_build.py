@@ -608,3 +608,23 @@ def test_contig_files_identical_when_the_reference_enlarges(dbg, oracle_mod, bui
     assert "array_size:\t64151" in logs["ref"] and "array_size:\t64151" in logs["b200"]
     assert outs["ref"] == outs["b200"]
     assert len(outs["ref"][".contig.seq.fa"]) > 1000
+
+
+@pytest.mark.xfail(strict=False, reason="growth replay through the Python mirror: CPU-verified pieces, first GPU run is the round-end one")
+def test_python_mirror_reproduces_the_enlarged_reference_table(dbg, build_path):
+    """golden enlarge_k25: the reference enlarged twice (-i 4e-6, -b 20); the mirror of build_debruijn_graph returns the
+    KmerSet in the reference's post-growth layout.  golden maxmem_k25 (-e 1 exhausted) is refused loudly."""
+    if build_path != "direct":
+        pytest.skip("path chosen by the library")
+    from dbg_assembly_b200.graph import build_debruijn_graph
+    g = load_golden("enlarge_k25")
+    ks = build_debruijn_graph(g["files"], KmerSize=g["K"], maxReadLen=g["R"], initHashSize=g["init_g"], hashLoadFactor=g["load"],
+                              BufferNum=g["B"], maxDoubleHashTimes=g["max_double"])
+    assert (ks.size, ks.max, ks.count) == (g["size"], g["max"], g["count"])
+    slot = ks.filled_slots()
+    assert np.array_equal(slot, g["slot"]) and np.array_equal(ks.array["kmer"][slot.astype(np.int64)], g["kmer"])
+    assert np.array_equal(ks.array["l_link"][slot.astype(np.int64)], g["l"]) and np.array_equal(ks.array["r_link"][slot.astype(np.int64)], g["r"])
+    g2 = load_golden("maxmem_k25")
+    with pytest.raises(dbg.capi.DbgError):
+        build_debruijn_graph(g2["files"], KmerSize=g2["K"], maxReadLen=g2["R"], initHashSize=g2["init_g"], hashLoadFactor=g2["load"],
+                             BufferNum=g2["B"], maxDoubleHashTimes=g2["max_double"])
