@@ -116,3 +116,38 @@ def test_reader_many_files_in_order(reader_check, tmp_path):
     assert run(reader_check, 2, 8192, 64, 150, paths) == exp
     missing = str(tmp_path / "nope.fa")
     assert run(reader_check, 2, 8192, 64, 150, [missing, paths[0]]) == [(0, 0, 1469598103934665603), exp[0]]
+
+
+def test_framing_rules_are_the_reference_readers(tmp_path):
+    """the framing restated above (and implemented by fast_reader.h) against the REAL reader: the reference's build
+    driver (oracle/_ref/ref_build_driver: parse_one_reads_file with igzstream + getline) reads awkward FASTQ / FASTA
+    files -- quality lines starting with '@', junk between records, a missing final newline -- and must end with exactly
+    the table the oracle builds from the reads this framing extracts"""
+    from oracle import oracle as orc
+    if not orc.have_reference():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(11)
+    recs_fq, recs_fa = [], []
+    for i in range(400):
+        s = rand_seq(rng, int(rng.integers(30, 90))).replace(b"N", b"A")
+        q = (b"@" if i % 3 == 0 else b"I") + b"I" * (len(s) - 1)          # '@' first: must be skipped, not taken as a header
+        recs_fq.append(b"@r%d\n%s\n+\n%s\n" % (i, s, q))
+        recs_fa.append((b"junk line\n" if i % 7 == 0 else b"") + b">r%d\n%s\n" % (i, s) + (b"\n" if i % 5 == 0 else b""))
+    cases = {1: b"".join(recs_fq)[:-1], 2: b"".join(recs_fa)}                   # FASTQ without the final newline
+    for fmt, data in cases.items():
+        path = str(tmp_path / f"in{fmt}.txt")
+        with open(path, "wb") as fh:
+            fh.write(data)
+        reads = frame(data, fmt)
+        assert len(reads) == 400
+        stats, ref = orc.run_ref_build([path], 21, 100, 0.0001, threads=1, fmt=fmt)
+        lens = np.array([len(r) for r in reads], dtype=np.uint64)
+        offs = np.zeros(len(reads) + 1, dtype=np.uint64); np.cumsum(lens, out=offs[1:])
+        bases = np.frombuffer(b"".join(reads), dtype=np.uint8)
+        o = orc.OracleGraph(21, 100, 100000, 0.7, 10, 10000)
+        o.add_file(bases, offs); o.finish()
+        e = o.dump()
+        assert ref["size"] == o.size and ref["count"] == o.count
+        for k in ("slot", "kmer", "l", "r"):
+            assert np.array_equal(ref[k], e[k]), (fmt, k)
+        o.close()
