@@ -14,13 +14,14 @@
 //      node is inserted next (the swap chain of kmerSet.cpp:163-183);
 //   3. the k-mer-0 node goes in last (DBGgraph.cpp:418).
 //
-// It is sequential like the code it mirrors (~50 ns per node) and only needed when a run outgrows -i; the front end
+// It is sequential like the code it mirrors (a few hundred ns per node: hashing and cache misses, again per doubling)
+// and only needed when a run outgrows -i; the front end
 // calls it instead of dbg_export_kmerset in that case.  If -e is exhausted the reference stops reading the current
 // file ("Memory reach the maximum allowed"): contents then differ from a full build, which a replay cannot undo --
 // the plan reports `truncated` and no layout is produced.
 #include <algorithm>
 #include <cstring>
-#include <numeric>
+#include <utility>
 #include <vector>
 
 #include "dbg_core.cuh"
@@ -89,33 +90,54 @@ extern "C" int dbg_replay_growth(const dbg_growth_params *g, const uint64_t *rea
     uint64_t max = (uint64_t)(size * lf);
     const uint64_t B = g->buffer_reads ? g->buffer_reads : 10000;
 
-    // nodes in first-occurrence order
-    std::vector<int64_t> order(n_nodes);
-    std::iota(order.begin(), order.end(), (int64_t)0);
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return first_ordinal[a] < first_ordinal[b]; });
-    for (uint64_t i = 1; i < n_nodes; i++)
-        if (first_ordinal[order[i]] == first_ordinal[order[i - 1]]) return DBG_ERR_INVALID;   // ordinals must be unique
+    // the blocks of -b reads, file by file, in reading order: block q ends before global read index block_end[q];
+    // a grow check follows every FULL block (parse_one_reads_file, DBGgraph.cpp:217-359: the final, short -- possibly
+    // empty -- block of a file has none)
+    std::vector<uint64_t> file_base(n_files + 1, 0), file_block0(n_files + 1, 0);
+    for (uint32_t f = 0; f < n_files; f++) {
+        file_base[f + 1] = file_base[f] + reads_per_file[f];
+        file_block0[f + 1] = file_block0[f] + reads_per_file[f] / B + 1;            // full blocks + the final short one
+    }
+    const uint64_t n_blocks = file_block0[n_files];
+    // new nodes per block (no sort needed for the plan)
+    std::vector<uint64_t> new_in_block(n_blocks + 1, 0);
+    for (uint64_t i = 0; i < n_nodes; i++) {
+        const uint64_t read = first_ordinal[i] >> 16;
+        if (read >= file_base[n_files]) return DBG_ERR_INVALID;                     // ordinal beyond the declared reads
+        const uint32_t f = (uint32_t)(std::upper_bound(file_base.begin(), file_base.end(), read) - file_base.begin() - 1);
+        const uint64_t q = file_block0[f] + (read - file_base[f]) / B;
+        new_in_block[q]++;
+    }
 
     const bool layout = array != nullptr;
     Replay rp;
     rp.wide = g->wide != 0; rp.klo = kmer_lo; rp.khi = kmer_hi; rp.size = size;
-    if (layout) rp.slot.assign(size, -1);
+    // layout: nodes in first-occurrence order (sort (ordinal, index) pairs: sequential compares, no indirection)
+    std::vector<int64_t> order;
+    if (layout) {
+        rp.slot.assign(size, -1);
+        std::vector<std::pair<uint64_t, int64_t> > keyed(n_nodes);
+        for (uint64_t i = 0; i < n_nodes; i++) keyed[i] = std::make_pair(first_ordinal[i], (int64_t)i);
+        std::sort(keyed.begin(), keyed.end());
+        order.resize(n_nodes);
+        for (uint64_t i = 0; i < n_nodes; i++) {
+            if (i && keyed[i].first == keyed[i - 1].first) return DBG_ERR_INVALID;  // ordinals must be unique
+            order[i] = keyed[i].second;
+        }
+    }
 
-    uint64_t pos = 0, count = 0, doublings = 0, read_base = 0;
+    uint64_t pos = 0, count = 0, doublings = 0;
     for (uint32_t f = 0; f < n_files && !res->truncated; f++) {
         const uint64_t nf = reads_per_file[f];
-        uint64_t next = 0;
-        for (;;) {                                                        // parse_one_reads_file, DBGgraph.cpp:217-359
-            const uint64_t nblk = (nf - next) < B ? (nf - next) : B;
-            const uint64_t read_end = read_base + next + nblk;
-            while (pos < n_nodes && (first_ordinal[order[pos]] >> 16) < read_end) {
-                // a block that fills the table makes the reference probe forever (no free slot): report it instead
-                if (count + 1 >= size) return DBG_ERR_TABLE_FULL;
-                if (layout) rp.insert(order[pos]);
-                pos++; count++;
-            }
-            next += nblk;
-            if (nblk < B) break;                                          // final block of the file: no grow check (:329-331)
+        const uint64_t full_blocks = nf / B;
+        for (uint64_t qb = 0; qb <= full_blocks; qb++) {
+            const uint64_t q = file_block0[f] + qb;
+            // a block that fills the table makes the reference probe forever (no free slot): report it instead
+            if (count + new_in_block[q] >= size && new_in_block[q]) return DBG_ERR_TABLE_FULL;
+            if (layout)
+                for (uint64_t e = pos + new_in_block[q]; pos < e; pos++) rp.insert(order[pos]);
+            count += new_in_block[q];
+            if (qb == full_blocks) break;                                 // final block of the file: no grow check (:329-331)
             if (count > max) {                                            // :337-351
                 if (doublings < g->max_double_times) {
                     uint64_t new_size = size;
@@ -127,16 +149,15 @@ extern "C" int dbg_replay_growth(const dbg_growth_params *g, const uint64_t *rea
                 } else {
                     // the reference ignores the rest of this file: a node first seen there must not exist
                     // (and occurrences there must not have been counted): any ignored read invalidates a full build
-                    if (next < nf) { res->truncated = 1; res->truncated_file = f; res->truncated_first_read = read_base + next; }
+                    const uint64_t next = (qb + 1) * B;
+                    if (next < nf) { res->truncated = 1; res->truncated_file = f; res->truncated_first_read = file_base[f] + next; }
                     break;
                 }
             }
         }
-        read_base += nf;
     }
     res->final_size = size; res->final_max = max; res->doublings = doublings; res->count = count + 1;
     if (res->truncated) return DBG_OK;
-    if (pos != n_nodes) return DBG_ERR_INVALID;                           // ordinals beyond the reads that were declared
     if (!layout) return DBG_OK;
 
     // the k-mer-0 node, last and always (add_node_to_kmerset, kmerSet.cpp:253-273 / DBGgraph.cpp:418)

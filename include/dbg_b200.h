@@ -218,7 +218,8 @@ int  dbg_synth_reads_device(const dbg_synth_params *p, uint64_t first_read, uint
  * ordinals (dbg_dump_shard on an unsharded context; the k-mer-0 node excluded, its link words passed separately) and
  * the number of reads in every input file.  Call it with array == NULL first: `res` tells whether the reference would
  * have grown (doublings > 0), the final table size to allocate, or `truncated` (-e exhausted: the reference drops the
- * rest of a file, which no replay of a full build can reproduce -- nothing is written).  Sequential, ~50 ns per node. */
+ * rest of a file, which no replay of a full build can reproduce -- nothing is written).  The plan call is one pass over
+ * the ordinals; the layout call is sequential like the code it mirrors (a few hundred ns per node). */
 typedef struct {
     uint64_t init_slots;        /* (uint64)(-i * 1e9), as in dbg_params                     */
     float    load_factor;       /* -l                                                       */
