@@ -83,3 +83,30 @@ def test_front_end_refuses_when_the_reference_would_drop_reads(mock_front_end, r
     rc_m, _, log_m = run(mock_front_end, reads_lib, str(tmp_path / "b200"), extra)
     assert rc_r == 0 and "Memory reach the maximum allowed, program have loaded 300 reads" in log_r
     assert rc_m == 1 and "from read 300 on" in log_m and "raise -i" in log_m
+
+
+def test_front_end_gzip_fastq_input(mock_front_end, oracle_mod, tmp_path):
+    """-f 1 on .fq.gz files (quality lines starting with '@' included): threaded zlib reader + binding vs the reference
+    program reading the same files through gzstream"""
+    import gzip
+    reads = random_reads(77, 2500, 100, 100, genome_len=12000, err=0.004, n_rate=0.0, lower=0.0)
+    paths = []
+    for i, part in enumerate((reads[:900], reads[900:])):
+        p = str(tmp_path / f"r{i}.fq.gz")
+        with gzip.open(p, "wb", compresslevel=1) as f:
+            for j, r in enumerate(part):
+                q = (b"@" if j % 4 == 0 else b"I") + b"I" * (len(r) - 1)
+                f.write(b"@read%d\n%s\n+\n%s\n" % (j, r, q))
+        paths.append(p)
+    lib = str(tmp_path / "fq.lib")
+    with open(lib, "w") as f:
+        f.write("\n".join(paths) + "\n")
+    outs = {}
+    for tag, exe in (("ref", REF_BIN), ("b200", mock_front_end)):
+        pre = str(tmp_path / tag)
+        r = subprocess.run([exe, "-k", "25", "-r", "100", "-f", "1", "-t", "1", "-i", "0.0005", "-M", "100", "-o", pre, lib],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-1500:]
+        outs[tag] = {s: open(pre + s, "rb").read() for s in SUF}
+        assert "Total number of reads loaded into memory: 2500" in r.stderr.decode()
+    assert outs["ref"] == outs["b200"] and len(outs["ref"][".contig.seq.fa"]) > 1000
