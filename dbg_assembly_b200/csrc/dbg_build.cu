@@ -150,6 +150,9 @@ struct dbg_ctx {
     u32 *d_fill = nullptr;         // [n_buckets] tuples per bucket + [n_buckets] overflow flag
     u64 *d_snap = nullptr;         // counters + polyA before an optimistic scatter (restored on overflow)
     u32 *h_flag = nullptr;         // pinned
+    u64 *h_cnt = nullptr;          // pinned copy of the counters taken after every host batch (prompt table-full report)
+    cudaEvent_t ev_cnt = nullptr;
+    bool cnt_pending = false;
     uint64_t path_counts[4] = {0, 0, 0, 0};   // blocks: direct, partitioned exact, partitioned optimistic, overflow fallbacks
     int stage_cap;                 // env DBG_B200_STAGE_CAP: batch size of the staged scatter (-1 default, 0 off)
     int peer_unstaged;             // env DBG_B200_PEER_UNSTAGED=1: fused exchange stores tuples one by one (experiments)
@@ -166,6 +169,7 @@ struct dbg_ctx {
     uint64_t reads_total, next_read_index, launches;
     dbg_stats st;
     std::vector<EvPair> build_ev;
+    std::vector<cudaEvent_t> ev_all, ev_free_list;   // every timing event this context ever created / the idle ones
     float ms[8];
 };
 
@@ -180,11 +184,27 @@ static TableView view_of(dbg_ctx *c)
     return t;
 }
 
+// timing events come from a per-context pool: an error return between ev_begin and ev_put loses nothing (the
+// events stay owned by the context and die with it)
+static int ev_get(dbg_ctx *c, cudaEvent_t *e)
+{
+    if (!c->ev_free_list.empty()) { *e = c->ev_free_list.back(); c->ev_free_list.pop_back(); return DBG_OK; }
+    CU_TRY(cudaEventCreate(e));
+    c->ev_all.push_back(*e);
+    return DBG_OK;
+}
+
+static void ev_put(dbg_ctx *c, EvPair &p)
+{
+    c->ev_free_list.push_back(p.a); c->ev_free_list.push_back(p.b);
+}
+
 static int ev_begin(dbg_ctx *c, cudaStream_t s, EvPair *p)
 {
     p->slot = 1;
-    CU_TRY(cudaEventCreate(&p->a));
-    CU_TRY(cudaEventCreate(&p->b));
+    int rc = ev_get(c, &p->a);
+    if (rc) return rc;
+    if ((rc = ev_get(c, &p->b))) { c->ev_free_list.push_back(p->a); return rc; }
     CU_TRY(cudaEventRecord(p->a, s));
     return DBG_OK;
 }
@@ -205,7 +225,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_finalize_buffers(c);
-    for (auto &e : c->build_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (cudaEvent_t e : c->ev_all) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_bases[i]); cudaFree(c->d_offs[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -215,6 +235,8 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_fill); cudaFree(c->d_snap); if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    if (c->ev_cnt) cudaEventDestroy(c->ev_cnt);
     delete c;
 }
 
@@ -229,7 +251,7 @@ static int clear_table(dbg_ctx *c)
     CU_TRY(cudaEventRecord(e.b, c->stream));
     CU_TRY(cudaEventSynchronize(e.b));
     CU_TRY(cudaEventElapsedTime(&c->ms[0], e.a, e.b));
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    ev_put(c, e);
     return DBG_OK;
 }
 
@@ -323,10 +345,11 @@ extern "C" int dbg_reset(dbg_ctx *c)
     if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaDeviceSynchronize());
-    for (auto &e : c->build_ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto &e : c->build_ev) ev_put(c, e);
     c->build_ev.clear();
     c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
     c->batch_reads = 0; c->batch_bases = 0; c->part_blocks = 0;
+    c->cnt_pending = false;
     for (int i = 0; i < 4; i++) c->path_counts[i] = 0;
     c->links_cutoff = INT32_MIN;
     for (int i = 1; i < 8; i++) c->ms[i] = 0;
@@ -674,13 +697,41 @@ __global__ void k_append_offs(const u64 *__restrict__ stage, u64 n, u64 *dst, u6
     if (i <= n) dst[i] = stage[i] - stage[0] + base;
 }
 
+// A table that cannot hold the input is reported as soon as a batch has shown it (the counters travel to pinned memory
+// behind every batch): DBG_ERR_TABLE_FULL from the next dbg_submit_reads / flush, so that a front end can rebuild with a
+// larger table right away instead of streaming the rest of the input into a full one.
+static int check_table_full(dbg_ctx *c, bool wait)
+{
+    if (!c->cnt_pending) return DBG_OK;
+    if (wait) CU_TRY(cudaEventSynchronize(c->ev_cnt));
+    else {
+        cudaError_t q = cudaEventQuery(c->ev_cnt);
+        if (q == cudaErrorNotReady) { cudaGetLastError(); return DBG_OK; }
+        CU_TRY(q);
+    }
+    c->cnt_pending = false;
+    if (c->h_cnt[CNT_ERROR] || (c->n_shards <= 1 && c->h_cnt[CNT_NEW] + 1 > c->P))
+        return set_err(DBG_ERR_TABLE_FULL, "%llu nodes so far: the table of %llu slots cannot hold this input", (unsigned long long)c->h_cnt[CNT_NEW],
+                       (unsigned long long)c->P);
+    return DBG_OK;
+}
+
 static int flush_batch(dbg_ctx *c)
 {
     if (c->batch_reads == 0) return DBG_OK;
     int b = c->cur;
-    int rc = build_device(c, c->d_bases[b], c->d_offs[b], c->batch_reads, 0, c->batch_bases, c->batch_read_index0, c->stream,
-                          0, nullptr, 0, nullptr);
+    int rc = check_table_full(c, true);       // (the previous batch's kernels precede this batch's on the stream anyway)
     if (rc) return rc;
+    rc = build_device(c, c->d_bases[b], c->d_offs[b], c->batch_reads, 0, c->batch_bases, c->batch_read_index0, c->stream,
+                      0, nullptr, 0, nullptr);
+    if (rc) return rc;
+    if (!c->h_cnt) {
+        CU_TRY(cudaMallocHost(&c->h_cnt, CNT_N * sizeof(u64)));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_cnt, cudaEventDisableTiming));
+    }
+    CU_TRY(cudaMemcpyAsync(c->h_cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaEventRecord(c->ev_cnt, c->stream));
+    c->cnt_pending = true;
     CU_TRY(cudaEventRecord(c->ev_free[b], c->stream));
     c->cur ^= 1;
     c->batch_reads = 0; c->batch_bases = 0;
@@ -695,7 +746,9 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
     if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
     if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "sharded contexts take tuples (dbg_insert_tuples_device)");
     CU_TRY(cudaSetDevice(c->device));
-    int rc = ensure_batch(c);
+    int rc = check_table_full(c, false);
+    if (rc) return rc;
+    rc = ensure_batch(c);
     if (rc) return rc;
     const uint64_t SUB_BASES = c->sub_bases, SUB_READS = c->sub_reads;
     uint64_t r0 = 0;
@@ -735,7 +788,7 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
         CU_TRY(cudaEventRecord(ev.b, c->copy_stream));
         CU_TRY(cudaEventSynchronize(ev.b));          // host buffer is reusable from here on
         float t = 0; CU_TRY(cudaEventElapsedTime(&t, ev.a, ev.b)); c->ms[4] += t;
-        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+        ev_put(c, ev);
         c->batch_bases += copy_nb; c->batch_reads += nr;
         c->next_read_index += nr; c->reads_total += nr;
         r0 = r1;
@@ -1148,7 +1201,7 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
     if (rc) return rc;
     if (!c->finalized) {
         // build time = sum over blocks
-        for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; ev_put(c, e); }
         c->build_ev.clear();
         if (c->n_shards <= 1) {
             if (cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
@@ -1166,7 +1219,7 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
             CU_TRY(cudaEventRecord(e.b, c->stream));
             CU_TRY(cudaEventSynchronize(e.b));
             CU_TRY(cudaEventElapsedTime(&c->ms[2], e.a, e.b));
-            cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+            ev_put(c, e);
             CU_TRY(cudaMemcpy(&c->polyA_links, c->d_counters + 6, sizeof(u64), cudaMemcpyDeviceToHost));
         }
         c->finalized = true;
@@ -1210,7 +1263,7 @@ extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
     CU_TRY(cudaEventRecord(e.b, c->stream));
     CU_TRY(cudaEventSynchronize(e.b));
     CU_TRY(cudaEventElapsedTime(&c->ms[5], e.a, e.b));
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    ev_put(c, e);
     return DBG_OK;
 }
 
@@ -1244,7 +1297,7 @@ static int run_links(dbg_ctx *c, int cutoff)
     CU_TRY(cudaEventRecord(e.b, c->stream));
     CU_TRY(cudaEventSynchronize(e.b));
     CU_TRY(cudaEventElapsedTime(&c->ms[3], e.a, e.b));
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    ev_put(c, e);
     c->links_cutoff = cutoff;
     return DBG_OK;
 }

@@ -33,6 +33,9 @@ constexpr int G = 4;           // consecutive occurrences per thread run (rollin
 #define DBG_MIN_CTAS 2
 #endif
 constexpr int MIN_CTAS = DBG_MIN_CTAS;    // register budget of the insert kernels: CTAs (x8 warps) per SM
+// longest probe sequence an insert follows before it gives up and raises CNT_ERROR: a table that is (nearly) full
+// must be reported promptly, not scanned slot by slot (the front end then rebuilds with a larger device table)
+constexpr u32 PROBE_CAP = 16384;
 constexpr u64 EMPTY_PRI = ~0ULL;
 constexpr u64 POLYA_PRI = ~0ULL - 1;
 
@@ -97,7 +100,9 @@ __device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p,
                                              u32 &n_new, u32 &n_conf)
 {
     typedef NodeT<WIDE> Nd;
-    Nd *const p_end = static_cast<Nd *>(t.nodes) + t.n_local;
+    // the probe ends at the end of the shard (+ margin) or after PROBE_CAP slots, whichever comes first
+    Nd *p_end = static_cast<Nd *>(t.nodes) + t.n_local;
+    if (p_end - p > (long long)PROBE_CAP) p_end = p + PROBE_CAP;
     for (;;) {
         if ((n.klo | n.khi) == 0) {
             if (WIDE) {
@@ -134,8 +139,9 @@ struct InsertSink {
     static constexpr int MIN_BLOCKS = MIN_CTAS;
     TableView t;
     u32 n_new, n_conf;     // per-thread, reduced at kernel end
+    bool dead;             // the table was already found full: skip the inserts (the host reports DBG_ERR_TABLE_FULL)
 
-    __device__ __forceinline__ void init(u32 *) { n_new = 0; n_conf = 0; }
+    __device__ __forceinline__ void init(u32 *) { n_new = 0; n_conf = 0; dead = __ldcg(t.counters + CNT_ERROR) != 0; }
 
     __device__ __forceinline__ void polyA(const Occ &o)
     {
@@ -147,6 +153,7 @@ struct InsertSink {
 
     __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
     {
+        if (dead) return;
         for (int g = 0; g < nv; g++) {
             if ((o[g].klo | o[g].khi) == 0) polyA(o[g]);
             else insert_one<WIDE, TRACK>(t, o[g].klo, o[g].khi, o[g].lb, o[g].rb, o[g].ord, n_new, n_conf);
@@ -868,13 +875,14 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
     // let fast CTAs run buckets ahead and the slices fell out of L2).  The counter is read one tile ahead (its
     // round trip hides behind the current tile) and published through a ping-pong slot: one barrier per tile.
     u64 next_tile = 0;
-    if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+    if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? ~0ULL / INS_TILE : atomicAdd(tile_counter, 1ULL);
     for (u32 par = 0;; par ^= 1) {
         if (threadIdx.x == 0) s_tile[par] = next_tile;
         __syncthreads();
         const u64 tile = s_tile[par] * INS_TILE;
         if (tile >= n) break;
-        if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+        // (a table found full ends the kernel at the next tile: nothing scans a full table slot by slot)
+        if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? ~0ULL / INS_TILE : atomicAdd(tile_counter, 1ULL);
         if (boffs && tile >= b1 && b + 1 < n_buckets) {
             // entered a new bucket (rare path): its region, its tuple count, the prefetch ratio of the next slice
             while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }

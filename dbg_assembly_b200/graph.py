@@ -354,7 +354,9 @@ def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_fo
     list reading_file_list() returns (seqKmer.cpp:101-114), or a list of (bases, offs) arrays.
     Table growth (-e): the device table never grows; when -i cannot hold the nodes the build is redone with a larger
     device table, and when the reference would have enlarged its hash the returned KmerSet is laid out by the
-    host-side replay of its doublings (replay_growth), exactly like integration/DBGgraph_b200.cpp."""
+    host-side replay of its doublings (replay_growth).  When -e is exhausted the reference stops reading the current
+    file and takes only the first block of every later one (DBGgraph.cpp:346-350): the replay finds that point and the
+    build is redone on exactly those reads -- the same flow as integration/DBGgraph_b200.cpp."""
     log = log or (lambda s: None)
     files = [f if isinstance(f, tuple) else read_reads_file(f, Input_file_format) for f in reads_files]
     ref_slots = init_slots_from_g(initHashSize)
@@ -363,7 +365,8 @@ def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_fo
     lf = np.float32(0.25) if lf <= 0 else (np.float32(0.75) if lf >= 1 else lf)
     ref_max = int(np.float32(ref_P) * lf)                       # uint64 * float -> float, kmerSet.cpp:115
     dev_slots = ref_slots
-    for attempt in range(13):
+    limited = False
+    for attempt in range(26):
         try:
             with DBGBuilder(K=KmerSize, max_read_len=maxReadLen, init_slots=dev_slots, load_factor=hashLoadFactor,
                             device=device, track_order=track_order) as b:
@@ -378,10 +381,18 @@ def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_fo
                     plan, garr, gnul = replay_growth(nodes, rpf, ref_slots, hashLoadFactor, maxDoubleHashTimes, BufferNum,
                                                      st["polyA_l"], st["polyA_r"])
                     if plan["truncated"]:
-                        print(f"Alert: the CPU program would have run out of -e {maxDoubleHashTimes} doublings and ignored the reads of "
-                              f"file {plan['truncated_file']} from read {plan['truncated_first_read']} on; this build used all reads "
-                              "(raise -i or -e)", file=sys.stderr)
-                grown = plan is not None and plan["doublings"] > 0 and not plan["truncated"]
+                        if limited:
+                            raise AssertionError("the truncated read set is truncated again")
+                        tf, base, cut = plan["truncated_file"], 0, []
+                        for f, (bases, offs) in enumerate(files):
+                            n = len(offs) - 1
+                            lim = plan["truncated_first_read"] - base if f == tf else (min(n, BufferNum) if f > tf else n)
+                            cut.append((bases[: int(offs[lim])], offs[: lim + 1]))
+                            base += n
+                        log(f"-e {maxDoubleHashTimes} is exhausted inside file {tf}: rebuilding on exactly the reads the CPU program used")
+                        files, limited, dev_slots = cut, True, ref_slots
+                        continue
+                grown = plan is not None and plan["doublings"] > 0
                 if grown:
                     array, nul, size, mx = garr, gnul, plan["final_size"], plan["final_max"]
                 else:
@@ -395,7 +406,7 @@ def build_debruijn_graph(reads_files, KmerSize=31, maxReadLen=250, Input_file_fo
                                del_flag=np.zeros(size // 8 + 1, dtype=np.uint8), Total_reads_num=st["reads"],
                                Kmer_total_num=st["kmers_logged"], occurrences=st["occurrences"], timings=b.timings())
         except capi.DbgError as e:
-            if e.code != capi.DBG_ERR_TABLE_FULL or attempt == 12:
+            if e.code != capi.DBG_ERR_TABLE_FULL or attempt == 25:
                 raise
             dev_slots = 2048 if dev_slots < 1024 else dev_slots * 2
             log(f"-i {initHashSize} cannot hold this input; rebuilding with a device table of {dev_slots} slots")

@@ -12,10 +12,13 @@
 // (thread_parseBlock / thread_updatekmers) run as CUDA kernels; the finished table comes back in the
 // reference's slot layout (== `debruijn_contig -t 1`) as the global `KmerSet *kset`.
 //
-// Differences a user can observe: the "conflict:" statistic counts GPU probe steps, "-t" only affects the host
-// traversal.  Table growth ("-e", enlarge) never happens on the GPU; when the reference would have grown its table
-// the post-growth slot layout is replayed on the host (dbg_replay_growth).  Only when "-e" would have been exhausted
-// (the reference then ignores the rest of a file) does the result differ: all reads are used, and an alert says so.
+// Differences a user can observe (INTEGRATION.md lists them): the "conflict:" statistic counts GPU probe steps, "-t" only
+// affects the host traversal, the per-block progress lines come in bursts (the reader runs ahead of them) and the
+// "Enlarge hash array size" lines are printed after the file loop, once.  Table growth ("-e", enlarge) never happens on
+// the GPU; when the reference would have grown its table the post-growth slot layout is replayed on the host
+// (dbg_replay_growth).  When "-e" is exhausted the reference ignores the rest of a file (DBGgraph.cpp:346-350): the
+// replay finds that point and the build is redone on exactly the reads the reference used, so the result is again
+// the reference's, file by file.
 #include <chrono>
 #include <memory>
 #include <thread>
@@ -68,42 +71,88 @@ static const uint64_t BLOCK_BASES = 128ull << 20;
 static const uint64_t BLOCK_READS = 2ull << 20;
 static const size_t MAX_AHEAD = 4;          // files being decoded at the same time
 
-// returns false when the device table turned out to be too small for the input (the caller rebuilds with a larger one)
-static bool consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod, bool quiet)
+// returns false when the device table turned out to be too small for the input (the caller rebuilds with a larger one).
+// `limit`: use at most this many reads of the file (the reference stops reading a file when -e is exhausted,
+// DBGgraph.cpp:346-350); UINT64_MAX = the whole file.  *cut is set when reads were left unread.
+static bool consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod, bool quiet, uint64_t limit, bool *cut)
 {
-    uint64_t in_block = 0;
-    bool full = false;
+    uint64_t in_block = 0, taken = 0;
+    bool full = false, stop = false;
+    *cut = false;
+    if (!quiet) cerr << "\n" << threadNum << " children threads created!" << endl;       // DBGgraph.cpp:241
     for (;;) {
         dbgio::ReadBlock *b = prod.pop();
         if (prod.failed()) { cerr << "libdbgb200: out of page-locked host memory for the read blocks" << endl; exit(1); }
-        if (b->n_reads) {
-            int rc = dbg_submit_reads(ctx, b->bases, b->offs, b->n_reads);
+        uint64_t use = b->n_reads;
+        if (taken + use >= limit) { if (taken + use > limit || !b->last) *cut = true; use = limit - taken; stop = true; }
+        if (use) {
+            int rc = dbg_submit_reads(ctx, b->bases, b->offs, use);
             if (rc == DBG_ERR_TABLE_FULL) full = true;
             else if (rc) die("dbg_submit_reads", rc);
         }
+        taken += use;
         if (full) { prod.recycle(b); return false; }      // the producer is cancelled by its owner
-        // the "Load reads block" lines of the reference: one per BufferNum (-b) reads and one at the end of the file
-        uint64_t left = b->n_reads;
+        // the per-block lines of the reference (DBGgraph.cpp:241,276,301,323): one set per BufferNum (-b) reads and one
+        // at the end of the file
+        uint64_t left = use;
         while (in_block + left >= (uint64_t)BufferNum) {
             const uint64_t take = (uint64_t)BufferNum - in_block;
             Total_reads_num += take; left -= take; in_block = 0;
-            if (!quiet) cerr << "Load reads block " << Total_reads_num << endl;
+            if (!quiet) {
+                cerr << "Load reads block " << Total_reads_num << endl;
+                cerr << "chop reads to kmers done" << endl << "add kmers to hash done" << endl;
+                if (!(stop && left == 0)) cerr << "\n" << threadNum << " children threads created!" << endl;
+            }
         }
         Total_reads_num += left; in_block += left;
         const bool last = b->last;
         prod.recycle(b);
-        if (last) break;
+        if (last || stop) break;
     }
-    if (!quiet) {
+    if (!quiet && !*cut) {
         cerr << "Load reads block " << Total_reads_num << endl;
         cerr << "this block has reach the end of file " << endl;
+        cerr << "chop reads to kmers done" << endl << "add kmers to hash done" << endl;
     }
+    if (!quiet && *cut)                                                                 // DBGgraph.cpp:348
+        cerr << "\nAlert message: Memory reach the maximum allowed, program have loaded " << Total_reads_num
+             << " reads, the left others are ignored\n" << endl;
     return !full;
 }
 
 static double wall_now()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// the nodes of a finished build with their first-occurrence ordinals + the growth replay (plan only or layout)
+struct GrowthInput {
+    std::vector<uint64_t> kmer, ord;
+    std::vector<uint32_t> l, r;
+    uint64_t n = 0;
+};
+
+static void fetch_nodes(dbg_ctx *ctx, GrowthInput &g)
+{
+    int rc;
+    uint64_t n = 0;
+    if ((rc = dbg_dump_shard(ctx, NULL, NULL, NULL, NULL, NULL, &n))) die("dbg_dump_shard", rc);
+    g.kmer.resize(n + 1); g.ord.resize(n + 1); g.l.resize(n + 1); g.r.resize(n + 1);
+    uint64_t cap = n + 1;
+    if ((rc = dbg_dump_shard(ctx, g.kmer.data(), NULL, g.l.data(), g.r.data(), g.ord.data(), &cap))) die("dbg_dump_shard", rc);
+    g.n = n;
+}
+
+static void replay(const GrowthInput &g, uint64_t ref_init_slots, const std::vector<uint64_t> &reads_per_file, const dbg_stats &st,
+                   dbg_growth_result *grow, void *array, uint8_t *nul_flag)
+{
+    dbg_growth_params gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.init_slots = ref_init_slots; gp.load_factor = hashLoadFactor; gp.wide = 0;
+    gp.max_double_times = maxDoubleHashTimes; gp.buffer_reads = (uint64_t)BufferNum;
+    int rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g.kmer.data(), NULL, g.l.data(), g.r.data(),
+                               g.ord.data(), g.n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, grow, array, nul_flag);
+    if (rc) die("dbg_replay_growth", rc);
 }
 
 void build_debruijn_graph(vector<string> &reads_files)
@@ -137,19 +186,27 @@ void build_debruijn_graph(vector<string> &reads_files)
     KmerNode *pinned_array = NULL;
     std::thread alloc_thread([&]() {
         void *q = NULL;
-        if (dbg_host_alloc(&q, P_slots * sizeof(KmerNode)) == DBG_OK) pinned_array = (KmerNode *)q;
+        if (dbg_host_alloc(&q, (P_slots + 1) * sizeof(KmerNode)) == DBG_OK) pinned_array = (KmerNode *)q;
     });
     cerr << "Hash initialization array size:  " << initHashSize << " G" << endl;
     cerr << "The initialization memory used:  " << initHashSize * 16 << " G" << endl;
+    float ref_lf = hashLoadFactor;
+    if (ref_lf <= 0) ref_lf = 0.25f; else if (ref_lf >= 1) ref_lf = 0.75f;      // kmerSet.cpp:110-111
+    const uint64_t ref_max = (uint64_t)(P_slots * ref_lf);
 
     // The device table never grows.  If -i turns out too small to even HOLD the nodes (the reference would have
     // enlarged its table, -e), the build is simply redone with a larger device table: the reads are streamed again, a
     // full build takes milliseconds, and the table the traversal gets is laid out by the growth replay further down from
     // the reference's own -i, so the size of the device table never shows.
+    // The same loop reproduces "-e exhausted" (DBGgraph.cpp:346-350: the reference stops reading the current file, and
+    // every later file after its first block): the replay of the full build tells where the reference stopped, and the
+    // build is redone on exactly the reads the reference used (`limits`).
     dbg_ctx *ctx = NULL;
     int rc = 0;
     dbg_stats st;
-    std::vector<uint64_t> reads_per_file;
+    std::vector<uint64_t> reads_per_file, limits;
+    dbg_growth_result grow;
+    GrowthInput gin;
     double w1 = 0, w2 = 0;
     for (int attempt = 0;; attempt++) {
         rc = dbg_create(&ctx, &prm);
@@ -172,15 +229,23 @@ void build_debruijn_graph(vector<string> &reads_files)
                                                                 BLOCK_READS, dbg_host_alloc, dbg_host_free));
                 if (attempt == 0) cerr << "\nStart to parse reads file: " << reads_files[i] << endl;
                 const uint64_t reads_before = Total_reads_num;
-                fits = consume_file(ctx, *prod[i], attempt > 0);
+                bool cut = false;
+                fits = consume_file(ctx, *prod[i], attempt > 0 && limits.empty(), limits.empty() ? UINT64_MAX : limits[i], &cut);
                 reads_per_file.push_back(Total_reads_num - reads_before);
+                if (!cut) {
+                    const std::string io = prod[i]->io_error();
+                    if (!io.empty() && (attempt == 0 || !limits.empty())) {
+                        cerr << "libdbgb200: WARNING: input problem: " << io << endl;
+                        if (getenv("DBG_B200_STRICT_IO")) exit(1);
+                    }
+                }
                 prod[i].reset();
                 if (fits) {
                     rc = dbg_get_stats(ctx, &st);
                     if (rc == DBG_ERR_TABLE_FULL) fits = false;
                     else if (rc) die("dbg_get_stats", rc);
                 }
-                if (fits) {
+                if (fits && (attempt == 0 || !limits.empty())) {
                     Kmer_total_num = st.kmers_logged;
                     cerr << "\nTotal number of reads loaded into memory: " << Total_reads_num << endl;
                     cerr << "Total number of kmers loaded into memory: " << Kmer_total_num << endl;
@@ -196,52 +261,59 @@ void build_debruijn_graph(vector<string> &reads_files)
             if (rc == DBG_ERR_TABLE_FULL) fits = false;
             else if (rc) die("dbg_finalize", rc);
         }
-        if (fits) break;
-        dbg_destroy(ctx);
-        ctx = NULL;
-        if (attempt >= 12) { cerr << "libdbgb200: the input does not fit a device table of " << prm.init_slots << " slots" << endl; exit(1); }
-        prm.init_slots = prm.init_slots < 1024 ? 2048 : prm.init_slots * 2;
-        cerr << "libdbgb200: -i " << initHashSize << " cannot hold this input; rebuilding with a device table of " << prm.init_slots
-             << " slots (the CPU program would have enlarged its hash)" << endl;
+        if (!fits) {
+            dbg_destroy(ctx);
+            ctx = NULL;
+            if (attempt >= 24) { cerr << "libdbgb200: the input does not fit a device table of " << prm.init_slots << " slots" << endl; exit(1); }
+            prm.init_slots = prm.init_slots < 1024 ? 2048 : prm.init_slots * 2;
+            cerr << "libdbgb200: -i " << initHashSize << " cannot hold this input; rebuilding with a device table of " << prm.init_slots
+                 << " slots (the CPU program would have enlarged its hash)" << endl;
+            continue;
+        }
+        // Did the reference grow its table on this input (-e / enlarge, DBGgraph.cpp:337-351)?  Only possible if the final
+        // node count passed max_cutoff.  The GPU table never grows; the reference's post-growth slot layout is replayed on
+        // the host from the nodes' first-occurrence ordinals (dbg_replay_growth) so that the traversal sees the table it
+        // expects.
+        memset(&grow, 0, sizeof(grow));
+        if (st.count - 1 > ref_max) {
+            fetch_nodes(ctx, gin);
+            replay(gin, ref_init_slots, reads_per_file, st, &grow, NULL, NULL);
+            if (grow.truncated) {
+                if (!limits.empty()) { cerr << "libdbgb200: internal error: the truncated read set is truncated again" << endl; exit(1); }
+                // -e exhausted inside file `truncated_file`: the reference used its reads up to there, and of every later
+                // file only the first block of -b reads (a later file's first full block ends with count > max again)
+                uint64_t base = 0;
+                for (size_t f = 0; f < reads_per_file.size(); f++) {
+                    uint64_t lim = reads_per_file[f];
+                    if (f == grow.truncated_file) lim = grow.truncated_first_read - base;
+                    else if (f > grow.truncated_file && lim > (uint64_t)BufferNum) lim = (uint64_t)BufferNum;
+                    limits.push_back(lim);
+                    base += reads_per_file[f];
+                }
+                cerr << "\nlibdbgb200: -e " << maxDoubleHashTimes << " is exhausted inside file " << grow.truncated_file
+                     << ": the CPU program ignores the rest of it; rebuilding on exactly the reads it used" << endl;
+                dbg_destroy(ctx);
+                ctx = NULL;
+                prm.init_slots = ref_init_slots;       // the reduced read set starts over from the reference's -i
+                continue;
+            }
+            if (grow.doublings) {
+                cerr << "Enlarge hash array size to be: " << grow.final_size << endl;                    // DBGgraph.cpp:343-344
+                cerr << "The expanded memory used now:  " << (double)grow.final_size / 1000000000 * 16 << " G" << endl;
+                cerr << "\nHash enlarged " << grow.doublings << " time(s) by the CPU program's rule: array size " << grow.final_size << endl;
+            }
+        }
+        break;
     }
-    // Did the reference grow its table on this input (-e / enlarge, DBGgraph.cpp:337-351)?  Only possible if the final
-    // node count passed max_cutoff.  The GPU table never grows; the reference's post-growth slot layout is replayed on the
-    // host from the nodes' first-occurrence ordinals (dbg_replay_growth) so that the traversal sees the table it expects.
-    dbg_growth_result grow;
-    memset(&grow, 0, sizeof(grow));
-    std::vector<uint64_t> g_kmer, g_ord;
-    std::vector<uint32_t> g_l, g_r;
-    float ref_lf = hashLoadFactor;
-    if (ref_lf <= 0) ref_lf = 0.25f; else if (ref_lf >= 1) ref_lf = 0.75f;      // kmerSet.cpp:110-111
-    const uint64_t ref_max = (uint64_t)(P_slots * ref_lf);
-    if (st.count - 1 > ref_max) {
-        uint64_t n = 0;
-        if ((rc = dbg_dump_shard(ctx, NULL, NULL, NULL, NULL, NULL, &n))) die("dbg_dump_shard", rc);
-        g_kmer.resize(n + 1); g_ord.resize(n + 1); g_l.resize(n + 1); g_r.resize(n + 1);
-        uint64_t cap = n + 1;
-        if ((rc = dbg_dump_shard(ctx, g_kmer.data(), NULL, g_l.data(), g_r.data(), g_ord.data(), &cap))) die("dbg_dump_shard", rc);
-        dbg_growth_params gp;
-        memset(&gp, 0, sizeof(gp));
-        gp.init_slots = ref_init_slots; gp.load_factor = hashLoadFactor; gp.wide = 0;
-        gp.max_double_times = maxDoubleHashTimes; gp.buffer_reads = (uint64_t)BufferNum;
-        rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g_kmer.data(), NULL, g_l.data(), g_r.data(),
-                               g_ord.data(), n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, &grow, NULL, NULL);
-        if (rc) die("dbg_replay_growth", rc);
-        if (grow.truncated)
-            cerr << "\nAlert message: Memory reach the maximum allowed in the CPU program (-e " << maxDoubleHashTimes
-                 << "): it would have ignored the reads of file " << grow.truncated_file << " from read " << grow.truncated_first_read
-                 << " on; this build used all reads. Raise -i or -e.\n" << endl;
-        else if (grow.doublings)
-            cerr << "\nHash enlarged " << grow.doublings << " time(s) by the CPU program's rule: array size " << grow.final_size << endl;
-    }
-    const bool grown = grow.doublings > 0 && !grow.truncated;
-    doubleHashTimes = grown ? grow.doublings : 0;
+    const bool grown = grow.doublings > 0;
+    doubleHashTimes = grow.doublings;
 
     // the KmerSet the traversal consumes (kmerSet.h:88-99, kmerSet.cpp:98-127)
     kset = new KmerSet;
     kset->e_size = sizeof(KmerNode);
     if (!grown && st.array_size != P_slots) {
-        // only reachable when the replay refused (-e exhausted) after the device table had to be enlarged
+        // the device table had to be enlarged although the reference's rule never grows: only possible when a final
+        // (unchecked) block overfills the table, where the reference itself would probe forever
         cerr << "libdbgb200: this input needs more than -i " << initHashSize << " and -e " << maxDoubleHashTimes << " allow; raise -i" << endl;
         exit(1);
     }
@@ -253,21 +325,17 @@ void build_debruijn_graph(vector<string> &reads_files)
     kset->iter_ptr = 0;
     alloc_thread.join();
     if (grown && pinned_array) { dbg_host_free(pinned_array); pinned_array = NULL; }
-    kset->array = (pinned_array && P_slots == kset->size) ? pinned_array : (KmerNode *)malloc(kset->size * kset->e_size);
+    // one spare, zeroed node behind the table: the traversal reads array[kset->size] when a walk ends without a last node
+    // (contig.cpp:320-338 with last_idx == size: out of bounds in the reference, where the bytes behind a freshly mapped
+    // table are zero) -- keeps the printed "EndKmer: 0" independent of heap history
+    kset->array = (pinned_array && P_slots == kset->size) ? pinned_array : (KmerNode *)malloc((kset->size + 1) * kset->e_size);
+    if (kset->array) memset(kset->array + kset->size, 0, sizeof(KmerNode));
     kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
     kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
     if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
     const double w3 = wall_now();
-    if (grown) {
-        const uint64_t n = g_kmer.size() - 1;
-        dbg_growth_params gp;
-        memset(&gp, 0, sizeof(gp));
-        gp.init_slots = ref_init_slots; gp.load_factor = hashLoadFactor; gp.wide = 0;
-        gp.max_double_times = maxDoubleHashTimes; gp.buffer_reads = (uint64_t)BufferNum;
-        rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g_kmer.data(), NULL, g_l.data(), g_r.data(),
-                               g_ord.data(), n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, &grow, kset->array, kset->nul_flag);
-        if (rc) die("dbg_replay_growth", rc);
-    } else if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
+    if (grown) replay(gin, ref_init_slots, reads_per_file, st, &grow, kset->array, kset->nul_flag);
+    else if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
     const double w4 = wall_now();
     cerr << "libdbgb200 wall clock (s): init " << w1 - w0 << ", read files + submit " << w2 - w1 << ", finalize (GPU build + layout) "
          << w3 - w2 << ", export kmerset " << w4 - w3 << endl;

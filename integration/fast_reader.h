@@ -37,6 +37,8 @@ public:
     }
     ~LineSource() { if (f_) gzclose(f_); }
     bool ok() const { return f_ != nullptr; }
+    // non-empty after a read error (truncated / corrupt .gz, I/O error): the data delivered so far is a prefix
+    const std::string &error() const { return err_; }
 
     // next line without its '\n'; the view stays valid until the next call.  false = no characters left
     // (the contract of std::getline on a good stream: a last line without '\n' is still delivered)
@@ -67,10 +69,17 @@ private:
         if (!f_) { eof_ = true; return; }
         const size_t want = buf_.size() - end_;
         const int got = gzread(f_, buf_.data() + end_, (unsigned)(want > (1u << 30) ? (1u << 30) : want));
-        if (got <= 0) eof_ = true;
-        else end_ += (size_t)got;
+        if (got <= 0) {
+            eof_ = true;
+            // gzread() <= 0 is a clean end of file only if zlib agrees (the reference's gzstream cannot tell: it would
+            // silently use the prefix; here the front end gets to say so)
+            int zerr = Z_OK;
+            const char *msg = gzerror(f_, &zerr);
+            if (got < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) err_ = msg && *msg ? msg : "read error";
+        } else end_ += (size_t)got;
     }
     gzFile f_ = nullptr;
+    std::string err_;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;
@@ -119,6 +128,14 @@ public:
         cv_.notify_all();
     }
     bool failed() const { return failed_; }
+    // input problem, if any, known once the file's last block has been popped: "" = none.  The reads delivered are
+    // what the reference's reader would have used (nothing for a file that does not open, the decodable prefix of a
+    // damaged .gz); the front end reports it instead of staying silent.
+    std::string io_error()
+    {
+        std::lock_guard<std::mutex> g(m_);
+        return io_error_;
+    }
 
 private:
     ReadBlock *get_free()
@@ -151,6 +168,7 @@ private:
     void run()
     {
         LineSource src(path_.c_str());
+        if (!src.ok()) { std::lock_guard<std::mutex> g(m_); io_error_ = "cannot open " + path_; }
         ReadBlock *b = get_free();
         if (!b) { publish_failure(); return; }
         const char hdr = format_ == 1 ? '@' : '>';
@@ -172,6 +190,7 @@ private:
             b->n_bases += sn;
             if (format_ == 1) { const char *q; size_t qn; if (src.next(q, qn)) src.next(q, qn); }
         }
+        if (!src.error().empty()) { std::lock_guard<std::mutex> g(m_); io_error_ = path_ + ": " + src.error() + " (reads up to the damage were used)"; }
         b->last = true;
         publish(b);
     }
@@ -194,6 +213,7 @@ private:
     std::deque<ReadBlock *> ready_, free_list_;
     std::vector<ReadBlock *> all_;
     ReadBlock sentinel_;
+    std::string io_error_;
     bool cancelled_ = false;
     volatile bool failed_ = false;
 };

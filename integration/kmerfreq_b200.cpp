@@ -130,6 +130,13 @@ int main(int argc, char **argv)
                 prod[i]->recycle(b);
                 if (last) break;
             }
+            {
+                const std::string io = prod[i]->io_error();
+                if (!io.empty()) {
+                    cerr << "kmerfreq_b200: WARNING: input problem: " << io << endl;
+                    if (getenv("DBG_B200_STRICT_IO")) return 1;
+                }
+            }
             prod[i].reset();
         }
     }

@@ -34,6 +34,8 @@ int main(int argc, char **argv)
             prod[f]->recycle(b);
             if (last) break;
         }
+        const std::string io = prod[f]->io_error();
+        if (!io.empty()) fprintf(stderr, "input problem: %s\n", io.c_str());
         printf("%llu %llu %llu\n", (unsigned long long)n_reads, (unsigned long long)n_bases, (unsigned long long)h);
     }
     return 0;

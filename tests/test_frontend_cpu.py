@@ -56,7 +56,7 @@ def reads_lib(tmp_path_factory, oracle_mod):
 
 def run(exe, lib, pre, extra):
     r = subprocess.run([exe, "-k", "25", "-r", "100", "-f", "2", "-t", "1", "-M", "100", "-o", pre, lib] + extra,
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     files = {s: open(pre + s, "rb").read() for s in SUF if os.path.exists(pre + s)}
     return r.returncode, files, r.stderr.decode()
 
@@ -71,18 +71,32 @@ def test_front_end_files_identical_to_the_reference(mock_front_end, reads_lib, t
     rc_m, files_m, log_m = run(mock_front_end, reads_lib, str(tmp_path / "b200"), extra)
     assert rc_r == 0 and rc_m == 0, log_m[-1500:]
     assert f"array_size:\t{size}" in log_r and f"array_size:\t{size}" in log_m
-    assert log_r.count("Enlarge hash array size") == grows
+    assert log_r.count("Enlarge hash array size") == grows and log_m.count("Enlarge hash array size") == (1 if grows else 0)
     assert (f"Hash enlarged {grows} time(s)" in log_m) == (grows > 0)
     assert len(files_r) == len(SUF) and files_r == files_m
     assert len(files_r[".contig.seq.fa"]) > 1000
 
 
-def test_front_end_refuses_when_the_reference_would_drop_reads(mock_front_end, reads_lib, tmp_path):
-    extra = ["-i", "0.000008", "-b", "100", "-e", "1"]
-    rc_r, _, log_r = run(REF_BIN, reads_lib, str(tmp_path / "ref"), extra)
-    rc_m, _, log_m = run(mock_front_end, reads_lib, str(tmp_path / "b200"), extra)
-    assert rc_r == 0 and "Memory reach the maximum allowed, program have loaded 300 reads" in log_r
-    assert rc_m == 1 and "from read 300 on" in log_m and "raise -i" in log_m
+@pytest.mark.parametrize("extra,loaded", [
+    (["-i", "0.000008", "-b", "100", "-e", "1"], (300, 400)),      # -e exhausted in file 0; file 1 contributes one block
+    (["-i", "0.00002", "-b", "150", "-e", "0"], (450, 600)),       # no doubling allowed at all
+    (["-i", "0.00001", "-b", "50", "-e", "1"], (350, 400)),
+    (["-i", "0.00003", "-b", "400", "-e", "0"], (1200, 1600)),
+])
+def test_front_end_reproduces_the_reference_when_it_drops_reads(mock_front_end, reads_lib, tmp_path, extra, loaded):
+    """-e exhausted (DBGgraph.cpp:346-350): the reference stops reading the current file and uses only the first block of
+    every later one.  The binding finds that point with the growth replay of a full build and rebuilds on exactly the
+    reads the reference used: same eight files, same alert lines."""
+    rc_r, files_r, log_r = run(REF_BIN, reads_lib, str(tmp_path / "ref"), extra)
+    rc_m, files_m, log_m = run(mock_front_end, reads_lib, str(tmp_path / "b200"), extra)
+    assert rc_r == 0 and rc_m == 0, log_m[-1500:]
+    assert "Memory reach the maximum allowed" in log_r
+    if loaded:
+        for n in loaded:
+            assert f"program have loaded {n} reads" in log_r and f"program have loaded {n} reads" in log_m
+    size = [l for l in log_r.split("\n") if l.startswith("array_size:")]
+    assert size and size == [l for l in log_m.split("\n") if l.startswith("array_size:")]
+    assert len(files_r) == len(SUF) and files_r == files_m
 
 
 def test_front_end_gzip_fastq_input(mock_front_end, oracle_mod, tmp_path):

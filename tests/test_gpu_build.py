@@ -581,7 +581,6 @@ def test_contig_files_byte_identical_to_reference(dbg, oracle_mod, tmp_path):
         assert len(outs["ref"][".contig.seq.fa"]) > 1000
 
 
-@pytest.mark.xfail(strict=False, reason="growth replay glue of the front end: CPU-verified (tests/test_growth_cpu.py), first GPU run is the round-end one")
 def test_contig_files_identical_when_the_reference_enlarges(dbg, oracle_mod, build_path, tmp_path):
     """-i far too small, -b 100: the reference enlarges its hash three times (DBGgraph.cpp:337-351).  The GPU front end
     rebuilds with a device table that can hold the nodes and lays the KmerSet out with the host-side growth replay
@@ -610,10 +609,10 @@ def test_contig_files_identical_when_the_reference_enlarges(dbg, oracle_mod, bui
     assert len(outs["ref"][".contig.seq.fa"]) > 1000
 
 
-@pytest.mark.xfail(strict=False, reason="growth replay through the Python mirror: CPU-verified pieces, first GPU run is the round-end one")
 def test_python_mirror_reproduces_the_enlarged_reference_table(dbg, build_path):
     """golden enlarge_k25: the reference enlarged twice (-i 4e-6, -b 20); the mirror of build_debruijn_graph returns the
-    KmerSet in the reference's post-growth layout.  golden maxmem_k25 (-e 1 exhausted) is refused loudly."""
+    KmerSet in the reference's post-growth layout.  golden maxmem_k25 (-e 1 exhausted: the reference dropped reads,
+    DBGgraph.cpp:346-350) is reproduced too: the mirror rebuilds on exactly the reads the reference used."""
     if build_path != "direct":
         pytest.skip("path chosen by the library")
     from dbg_assembly_b200.graph import build_debruijn_graph
@@ -625,6 +624,9 @@ def test_python_mirror_reproduces_the_enlarged_reference_table(dbg, build_path):
     assert np.array_equal(slot, g["slot"]) and np.array_equal(ks.array["kmer"][slot.astype(np.int64)], g["kmer"])
     assert np.array_equal(ks.array["l_link"][slot.astype(np.int64)], g["l"]) and np.array_equal(ks.array["r_link"][slot.astype(np.int64)], g["r"])
     g2 = load_golden("maxmem_k25")
-    with pytest.raises(dbg.capi.DbgError):
-        build_debruijn_graph(g2["files"], KmerSize=g2["K"], maxReadLen=g2["R"], initHashSize=g2["init_g"], hashLoadFactor=g2["load"],
-                             BufferNum=g2["B"], maxDoubleHashTimes=g2["max_double"])
+    ks2 = build_debruijn_graph(g2["files"], KmerSize=g2["K"], maxReadLen=g2["R"], initHashSize=g2["init_g"], hashLoadFactor=g2["load"],
+                               BufferNum=g2["B"], maxDoubleHashTimes=g2["max_double"])
+    assert (ks2.size, ks2.max, ks2.count, ks2.Total_reads_num) == (g2["size"], g2["max"], g2["count"], g2["reads"])
+    slot2 = ks2.filled_slots()
+    assert np.array_equal(slot2, g2["slot"]) and np.array_equal(ks2.array["kmer"][slot2.astype(np.int64)], g2["kmer"])
+    assert np.array_equal(ks2.array["l_link"][slot2.astype(np.int64)], g2["l"]) and np.array_equal(ks2.array["r_link"][slot2.astype(np.int64)], g2["r"])

@@ -104,6 +104,23 @@ def test_reader_oversize_read_is_trimmed(reader_check, tmp_path):
     assert got == [fnv(frame(data, 2), 150, 4096)] and got[0][1] == 150 + 4
 
 
+def test_reader_reports_damaged_and_missing_input(reader_check, tmp_path):
+    """gzread() <= 0 is a clean EOF only if zlib agrees: a truncated .gz and a missing file still deliver what the
+    reference's reader would have used (the decodable prefix / nothing), but the producer says so (io_error)"""
+    rng = np.random.default_rng(5)
+    body = b"".join(b">r%d\n" % i + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=90)) + b"\n" for i in range(4000))
+    good = str(tmp_path / "good.fa.gz"); open(good, "wb").write(gzip.compress(body))
+    bad = str(tmp_path / "cut.fa.gz"); open(bad, "wb").write(gzip.compress(body)[:20000])
+    missing = str(tmp_path / "nope.fa")
+    rr = subprocess.run([reader_check, "2", "65536", "512", "150", good, bad, missing], check=True, timeout=120,
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    lines = [tuple(int(x) for x in l.split()) for l in rr.stdout.decode().split("\n") if l]
+    assert lines[0] == fnv(frame(body, 2), 150, 65536)
+    assert 0 < lines[1][0] < 4000 and lines[2][0] == 0
+    err = rr.stderr.decode()
+    assert "cut.fa.gz" in err and "cannot open" in err and "good.fa.gz" not in err
+
+
 def test_reader_many_files_in_order(reader_check, tmp_path):
     rng = np.random.default_rng(5)
     paths, exp = [], []
