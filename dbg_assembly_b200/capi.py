@@ -69,6 +69,7 @@ SYMBOLS = [
     "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device", "dbg_insert_sliced_device", "dbg_partition_info",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
     "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count", "dbg_path_counts", "dbg_replay_growth",
+    "dbg_shard_tail_export", "dbg_shard_tail_import", "dbg_shard_slice_info", "dbg_export_shard_slice", "dbg_host_fix_nul_bytes", "dbg_host_polyA_insert",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
     "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
@@ -127,6 +128,12 @@ def load(build_if_missing: bool = True):
         "dbg_path_counts": (C.c_int, [vp, vp]),
         "dbg_replay_growth": (C.c_int, [C.POINTER(dbg_growth_params), vp, C.c_uint32, vp, vp, vp, vp, vp, u64, C.c_uint32, C.c_uint32,
                               C.POINTER(dbg_growth_result), vp, vp]),
+        "dbg_shard_tail_export": (C.c_int, [vp, vp, u64, C.POINTER(u64)]),
+        "dbg_shard_tail_import": (C.c_int, [vp, vp, u64]),
+        "dbg_shard_slice_info": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp)]),
+        "dbg_export_shard_slice": (C.c_int, [vp, vp, vp, vp]),
+        "dbg_host_fix_nul_bytes": (C.c_int, [vp, vp, u64, i32, vp, u64]),
+        "dbg_host_polyA_insert": (C.c_int, [vp, vp, u64, i32, C.c_uint32, C.c_uint32, C.POINTER(u64)]),
         "dbg_reset": (C.c_int, [vp]),
         "dbg_set_stream": (C.c_int, [vp, vp]),
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),
@@ -172,6 +179,19 @@ def find_next_prime(n: int) -> int:
 
 def hash_code(k: int) -> int:
     return int(load().dbg_hash_code(int(k)))
+
+
+def host_fix_nul_bytes(array: np.ndarray, nul_flag: np.ndarray, P: int, wide: bool, slots):
+    a = np.ascontiguousarray(slots, dtype=np.uint64)
+    check(load().dbg_host_fix_nul_bytes(array.ctypes.data, nul_flag.ctypes.data, int(P), int(bool(wide)), a.ctypes.data, len(a)),
+          "dbg_host_fix_nul_bytes")
+
+
+def host_polyA_insert(array: np.ndarray, nul_flag: np.ndarray, P: int, wide: bool, l_link: int, r_link: int) -> int:
+    s = C.c_uint64(0)
+    check(load().dbg_host_polyA_insert(array.ctypes.data, nul_flag.ctypes.data, int(P), int(bool(wide)), int(l_link), int(r_link),
+                                       C.byref(s)), "dbg_host_polyA_insert")
+    return int(s.value)
 
 
 def hash_code_wide(lo: int, hi: int) -> int:

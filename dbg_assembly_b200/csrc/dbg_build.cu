@@ -119,7 +119,17 @@ struct dbg_ctx {
     uint64_t shard_lo, shard_hi, shard_size, n_local;
     int n_shards;
     cudaStream_t stream, copy_stream, own_stream;
-    void *d_nodes;                 // n_local x NodeT<wide>
+    void *d_nodes;                 // n_local x NodeT<wide>: local slot 0 (behind the porch)
+    void *d_nodes_alloc = nullptr; // the allocation: [porch | n_local]
+    uint64_t porch = 0;            // sharded contexts: slots in front of local slot 0 that receive the left neighbour's tail cluster
+    TailInfo *d_tail = nullptr;    // cross-shard hand-off scratch
+    void *d_tail_nodes = nullptr;  // staging of imported margin nodes
+    uint64_t tail_nodes_cap = 0;
+    uint64_t tail_a_own = 0, tail_mt_own = 0, tail_a_in = 0;
+    bool tail_exported = false, tail_imported = false, tail_moved = false;
+    int64_t nodes_delta = 0;       // nodes handed to / adopted from the neighbours (dump_shard counts what is physically here)
+    u32 *d_nul_slice = nullptr;    // occupancy words of the laid-out slice (global word positions)
+    uint64_t nul_slice_words = 0;
     u64 *d_counters, *d_polyA;
     // host-submit staging (double buffered)
     char *d_bases[2];
@@ -230,7 +240,8 @@ extern "C" void dbg_destroy(dbg_ctx *c)
         cudaFree(c->d_bases[i]); cudaFree(c->d_offs[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
-    cudaFree(c->d_chunk_first); cudaFree(c->d_nodes); cudaFree(c->d_counters); cudaFree(c->d_polyA);
+    cudaFree(c->d_chunk_first); cudaFree(c->d_nodes_alloc); cudaFree(c->d_counters); cudaFree(c->d_polyA);
+    cudaFree(c->d_tail); cudaFree(c->d_tail_nodes); cudaFree(c->d_nul_slice);
     cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_roffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -245,7 +256,7 @@ static int clear_table(dbg_ctx *c)
     EvPair e;
     int rc = ev_begin(c, c->stream, &e);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(c->d_nodes, 0, c->n_local * build_node_bytes(c), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_nodes_alloc, 0, (c->porch + c->n_local) * build_node_bytes(c), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(u64), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_polyA, 0, 8 * sizeof(u64), c->stream));
     CU_TRY(cudaEventRecord(e.b, c->stream));
@@ -290,6 +301,9 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (c->shard_lo > size) c->shard_lo = size;
     c->shard_hi = c->shard_lo + c->shard_size < size ? c->shard_lo + c->shard_size : size;
     c->n_local = (c->shard_hi - c->shard_lo) + MARGIN_SLOTS;
+    // porch for the cross-shard hand-off of boundary clusters (see k_shard_tail_scan); window [porch | own range] must
+    // stay shorter than the ring of P slots so that home -> virtual slot is unambiguous
+    c->porch = n_shards > 1 ? (MARGIN_SLOTS < c->shard_size / 2 ? MARGIN_SLOTS : c->shard_size / 2) : 0;
     c->links_cutoff = INT32_MIN;
     c->sub_bases = SUB_BASES_DEFAULT; c->sub_reads = SUB_READS_DEFAULT;
     if (const char *e = getenv("DBG_B200_SUB_BASES")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 16) c->sub_bases = v; }
@@ -323,7 +337,8 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU_TRY(cudaMalloc(&c->d_nodes, c->n_local * build_node_bytes(c)));
+    CU_TRY(cudaMalloc(&c->d_nodes_alloc, (c->porch + c->n_local) * build_node_bytes(c)));
+    c->d_nodes = static_cast<char *>(c->d_nodes_alloc) + c->porch * build_node_bytes(c);
     CU_TRY(cudaMalloc(&c->d_counters, CNT_N * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_polyA, 8 * sizeof(u64)));
     CU_TRY(cudaMalloc(&c->d_boffs, ((size_t)c->n_buckets + 1) * sizeof(u64)));
@@ -350,6 +365,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
     c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
     c->batch_reads = 0; c->batch_bases = 0; c->part_blocks = 0;
     c->cnt_pending = false;
+    c->tail_exported = c->tail_imported = c->tail_moved = false; c->tail_a_own = c->tail_mt_own = c->tail_a_in = 0; c->nodes_delta = 0;
     for (int i = 0; i < 4; i++) c->path_counts[i] = 0;
     c->links_cutoff = INT32_MIN;
     for (int i = 1; i < 8; i++) c->ms[i] = 0;
@@ -1149,29 +1165,51 @@ static int run_layout_global(dbg_ctx *c)
 }
 
 // cluster-local method: one streaming pass, regions (long clusters, wrap-around) on a small scratch
+static LayoutGeom layout_geom(const dbg_ctx *c)
+{
+    LayoutGeom g;
+    g.P = c->P; g.M = c->M;
+    if (c->n_shards <= 1) { g.gbase = 0; g.v_begin = 0; g.v_end = c->P; }
+    else {
+        // window = [imported tail cluster (end of the porch) | own home range minus the own tail cluster]
+        g.gbase = (c->shard_lo + c->P - c->porch % c->P) % c->P;
+        g.v_begin = c->porch - c->tail_a_in;
+        g.v_end = c->porch + ((c->shard_hi - c->shard_lo) - c->tail_a_own);
+    }
+    return g;
+}
+
+static int ensure_layout_scratch(dbg_ctx *c)
+{
+    if (c->owner_cap < SCRATCH_CAP) {
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(c->d_owner); c->d_owner = nullptr; c->owner_cap = 0;
+        CU_TRY(cudaMalloc(&c->d_owner, SCRATCH_CAP * sizeof(u64)));
+        c->owner_cap = SCRATCH_CAP;
+    }
+    if (!c->d_layout_info) {
+        CU_TRY(cudaMalloc(&c->d_layout_info, sizeof(LayoutInfo)));
+        CU_TRY(cudaMalloc(&c->d_regions, (size_t)MAX_REGIONS * sizeof(LayoutRegion)));
+    }
+    return DBG_OK;
+}
+
 template <bool WIDE, bool TRACK>
 static int run_layout(dbg_ctx *c)
 {
     const NodeT<WIDE> *nodes = (const NodeT<WIDE> *)c->d_nodes;
     bool use_global = c->layout_mode == 1;
     if (!use_global) {
-        if (c->owner_cap < SCRATCH_CAP) {
-            CU_TRY(cudaDeviceSynchronize());
-            cudaFree(c->d_owner); c->d_owner = nullptr; c->owner_cap = 0;
-            CU_TRY(cudaMalloc(&c->d_owner, SCRATCH_CAP * sizeof(u64)));
-            c->owner_cap = SCRATCH_CAP;
-        }
-        if (!c->d_layout_info) {
-            CU_TRY(cudaMalloc(&c->d_layout_info, sizeof(LayoutInfo)));
-            CU_TRY(cudaMalloc(&c->d_regions, (size_t)MAX_REGIONS * sizeof(LayoutRegion)));
-        }
+        int rc = ensure_layout_scratch(c);
+        if (rc) return rc;
+        const LayoutGeom geo = layout_geom(c);
         CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
         k_layout_wrapscan<WIDE><<<1, 32, 0, c->stream>>>(nodes, c->n_local, c->P, c->d_layout_info, c->d_regions, SCRATCH_CAP);
         CU_TRY(cudaGetLastError());
-        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info,
                                                                              c->d_regions, SCRATCH_CAP);
         CU_TRY(cudaGetLastError());
-        k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(nodes, c->P, c->M, c->d_out, c->d_nul32, c->d_layout_info,
+        k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info,
                                                                             c->d_regions, c->d_owner);
         CU_TRY(cudaGetLastError());
         c->launches += 3;
@@ -1192,6 +1230,61 @@ static int run_layout(dbg_ctx *c)
     return DBG_OK;
 }
 
+// sharded context: lay out this rank's window [imported tail | own range minus own tail] (dbg_shard_tail_export /
+// _import came first) into d_out (virtual slot order) and derive the occupancy words of the slice in global positions.
+// The k-mer-0 node is NOT placed here: it goes in last, on the merged table (dbg_host_polyA_insert).
+static uint64_t slice_first_word(const dbg_ctx *c, const LayoutGeom &g) { return ((g.gbase + g.v_begin) % c->P) / 32; }
+
+template <bool WIDE, bool TRACK>
+static int run_layout_sharded(dbg_ctx *c)
+{
+    const NodeT<WIDE> *base = (const NodeT<WIDE> *)c->d_nodes_alloc;       // virtual slot 0
+    int rc = ensure_layout_scratch(c);
+    if (rc) return rc;
+    const LayoutGeom geo = layout_geom(c);
+    LayoutInfo li0;
+    memset(&li0, 0, sizeof(li0));
+    li0.e = ~0ULL;                                                           // no wrap region inside a shard window
+    CU_TRY(cudaMemcpyAsync(c->d_layout_info, &li0, sizeof(li0), cudaMemcpyHostToDevice, c->stream));
+    if (geo.v_end > geo.v_begin) {
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(base, geo, c->d_out, nullptr, c->d_layout_info, c->d_regions, SCRATCH_CAP);
+        CU_TRY(cudaGetLastError());
+        k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(base, geo, c->d_out, nullptr, c->d_layout_info, c->d_regions, c->d_owner);
+        CU_TRY(cudaGetLastError());
+        c->launches += 2;
+    }
+    LayoutInfo li;
+    CU_TRY(cudaMemcpyAsync(&li, c->d_layout_info, sizeof(li), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->layout_regions = li.n_regions;
+    if (li.overflow) return set_err(DBG_ERR_STATE, "shard too dense for the windowed layout (cluster scratch exhausted): merge the shard dumps instead");
+    // occupancy words of the slice, in global word positions (a slice that wraps past slot P-1 produces two runs)
+    const uint64_t n = geo.v_end - geo.v_begin;
+    const uint64_t g_first = (geo.gbase + geo.v_begin) % c->P;
+    const uint64_t words = n ? (n + 31) / 32 + 2 : 0;
+    if (words > c->nul_slice_words) {
+        cudaFree(c->d_nul_slice); c->d_nul_slice = nullptr; c->nul_slice_words = 0;
+        CU_TRY(cudaMalloc(&c->d_nul_slice, 2 * (words + 2) * sizeof(u32)));
+        c->nul_slice_words = words;
+    }
+    if (n) {
+        // run 1: words from g_first/32 up to the end of the slice or of the table; run 2 (wrap): words from 0
+        const uint64_t first_len = g_first + n <= c->P ? n : c->P - g_first;
+        const uint64_t w1 = g_first / 32, nw1 = (g_first + first_len + 31) / 32 - w1;
+        k_nul_from_image<WIDE><<<(unsigned)((nw1 * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_out, c->P, geo.gbase, g_first, n, w1, nw1, c->d_nul_slice);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        if (first_len < n) {
+            const uint64_t nw2 = (n - first_len + 31) / 32;
+            k_nul_from_image<WIDE><<<(unsigned)((nw2 * 32 + 255) / 256), 256, 0, c->stream>>>(c->d_out, c->P, geo.gbase, g_first, n, 0, nw2,
+                                                                                          c->d_nul_slice + c->nul_slice_words + 2);
+            CU_TRY(cudaGetLastError());
+            c->launches++;
+        }
+    }
+    return DBG_OK;
+}
+
 extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
 {
     if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
@@ -1203,29 +1296,230 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
         // build time = sum over blocks
         for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; ev_put(c, e); }
         c->build_ev.clear();
-        if (c->n_shards <= 1) {
-            if (cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
+        const bool sharded_layout = c->n_shards > 1 && c->tail_exported && c->tail_imported;
+        if (c->n_shards <= 1 || sharded_layout) {
+            if (c->n_shards <= 1 && cnt[CNT_NEW] + 1 > c->P) return set_err(DBG_ERR_TABLE_FULL, "%llu nodes do not fit %llu slots", (unsigned long long)cnt[CNT_NEW] + 1, (unsigned long long)c->P);
             size_t nb = (size_t)node_bytes(c);
             if (!c->d_out) {
-                CU_TRY(cudaMalloc(&c->d_out, c->P * nb));
-                CU_TRY(cudaMalloc(&c->d_nul32, nul_words(c->P) * sizeof(u32)));
+                // unsharded: the whole image (global slot order); sharded: the window [porch | own range] (virtual order)
+                const uint64_t slots = c->n_shards <= 1 ? c->P : c->porch + (c->shard_hi - c->shard_lo) + 1;
+                CU_TRY(cudaMalloc(&c->d_out, slots * nb));
+                if (c->n_shards <= 1) CU_TRY(cudaMalloc(&c->d_nul32, nul_words(c->P) * sizeof(u32)));
             }
             EvPair e;
             rc = ev_begin(c, c->stream, &e);
             if (rc) return rc;
-            if (c->wide) rc = c->track ? run_layout<true, true>(c) : run_layout<true, false>(c);
-            else rc = c->track ? run_layout<false, true>(c) : run_layout<false, false>(c);
+            if (sharded_layout) {
+                if (c->wide) rc = c->track ? run_layout_sharded<true, true>(c) : run_layout_sharded<true, false>(c);
+                else rc = c->track ? run_layout_sharded<false, true>(c) : run_layout_sharded<false, false>(c);
+            } else {
+                if (c->wide) rc = c->track ? run_layout<true, true>(c) : run_layout<true, false>(c);
+                else rc = c->track ? run_layout<false, true>(c) : run_layout<false, false>(c);
+            }
             if (rc) return rc;
             CU_TRY(cudaEventRecord(e.b, c->stream));
             CU_TRY(cudaEventSynchronize(e.b));
             CU_TRY(cudaEventElapsedTime(&c->ms[2], e.a, e.b));
             ev_put(c, e);
-            CU_TRY(cudaMemcpy(&c->polyA_links, c->d_counters + 6, sizeof(u64), cudaMemcpyDeviceToHost));
+            if (!sharded_layout) CU_TRY(cudaMemcpy(&c->polyA_links, c->d_counters + 6, sizeof(u64), cudaMemcpyDeviceToHost));
+            else {
+                // the k-mer-0 node's link words from the (all-reduced) side counters; it is placed on the merged table
+                u64 pa[8];
+                CU_TRY(cudaMemcpy(pa, c->d_polyA, sizeof(pa), cudaMemcpyDeviceToHost));
+                u64 l = 0, r = 0;
+                for (int b = 0; b < 4; b++) { l |= (pa[b] > 255 ? 255 : pa[b]) << (24 - 8 * b); r |= (pa[4 + b] > 255 ? 255 : pa[4 + b]) << (24 - 8 * b); }
+                c->polyA_links = l | (r << 32);
+            }
         }
         c->finalized = true;
     }
     fill_stats(c, cnt);
     if (stats) *stats = c->st;
+    return DBG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cross-shard reference layout: tail hand-off, slice export, host-side merge helpers
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dbg_shard_tail_export(dbg_ctx *c, void *blob, uint64_t cap_bytes, uint64_t *n_bytes)
+{
+    if (!c || !n_bytes) return set_err(DBG_ERR_INVALID, "NULL argument");
+    if (c->n_shards <= 1) return set_err(DBG_ERR_STATE, "dbg_shard_tail_export: unsharded context");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "dbg_shard_tail_export after finalize");
+    CU_TRY(cudaSetDevice(c->device));
+    u64 cnt[CNT_N];
+    int rc = read_counters(c, cnt);        // waits for the inserts; reports a shard that overflowed
+    if (rc) return rc;
+    const size_t nbb = build_node_bytes(c);
+    const uint64_t own = c->shard_hi - c->shard_lo;
+    if (!c->tail_exported) {
+        if (!c->d_tail) CU_TRY(cudaMalloc(&c->d_tail, sizeof(TailInfo)));
+        CU_TRY(cudaMemsetAsync(c->d_tail, 0, sizeof(TailInfo), c->stream));
+        // the receiver keeps the in-range part in its porch: a run longer than the porch cannot be handed over
+        const uint64_t max_a = c->porch;
+        if (c->wide) k_shard_tail_scan<true><<<1, 32, 0, c->stream>>>((const NodeT<true> *)c->d_nodes, own, c->n_local, max_a, c->d_tail);
+        else k_shard_tail_scan<false><<<1, 32, 0, c->stream>>>((const NodeT<false> *)c->d_nodes, own, c->n_local, max_a, c->d_tail);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        TailInfo ti;
+        CU_TRY(cudaMemcpyAsync(&ti, c->d_tail, sizeof(ti), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (ti.a > max_a || (own && ti.a >= own)) return set_err(DBG_ERR_STATE, "boundary cluster of %llu slots does not fit the hand-off porch (%llu): merge the shard dumps instead",
+                                                         (unsigned long long)ti.a, (unsigned long long)max_a);
+        c->tail_a_own = ti.a; c->tail_mt_own = ti.mt;
+        c->tail_exported = true;
+    }
+    const uint64_t n_nodes = c->tail_a_own + c->tail_mt_own;
+    const uint64_t need = 4 * sizeof(uint64_t) + n_nodes * nbb;
+    *n_bytes = need;
+    if (!blob) return DBG_OK;                                    // size query
+    if (cap_bytes < need) return set_err(DBG_ERR_BUFFER, "tail blob needs %llu bytes", (unsigned long long)need);
+    uint64_t hdr[4] = {c->tail_a_own, c->tail_mt_own, (uint64_t)nbb, (uint64_t)c->prm.shard_rank};
+    memcpy(blob, hdr, sizeof(hdr));
+    if (n_nodes) {
+        const char *src = static_cast<const char *>(c->d_nodes) + (own - c->tail_a_own) * nbb;      // [tail run | margin run] is contiguous
+        CU_TRY(cudaMemcpyAsync(static_cast<char *>(blob) + sizeof(hdr), src, n_nodes * nbb, cudaMemcpyDeviceToHost, c->stream));
+        // the margin nodes now belong to the right neighbour (their slots are in its home range)
+        if (c->tail_mt_own && !c->tail_moved) {
+            CU_TRY(cudaMemsetAsync(static_cast<char *>(c->d_nodes) + own * nbb, 0, c->tail_mt_own * nbb, c->stream));
+            c->nodes_delta -= (int64_t)c->tail_mt_own;
+            c->tail_moved = true;
+        }
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return DBG_OK;
+}
+
+extern "C" int dbg_shard_tail_import(dbg_ctx *c, const void *blob, uint64_t n_bytes)
+{
+    if (!c || !blob) return set_err(DBG_ERR_INVALID, "NULL argument");
+    if (c->n_shards <= 1) return set_err(DBG_ERR_STATE, "dbg_shard_tail_import: unsharded context");
+    if (!c->tail_exported) return set_err(DBG_ERR_STATE, "dbg_shard_tail_import before dbg_shard_tail_export (the own tail is fixed first)");
+    if (c->tail_imported) return set_err(DBG_ERR_STATE, "tail already imported");
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t nbb = build_node_bytes(c);
+    uint64_t hdr[4];
+    if (n_bytes < sizeof(hdr)) return set_err(DBG_ERR_INVALID, "short tail blob");
+    memcpy(hdr, blob, sizeof(hdr));
+    const uint64_t a = hdr[0], mt = hdr[1];
+    if (hdr[2] != nbb || n_bytes < sizeof(hdr) + (a + mt) * nbb) return set_err(DBG_ERR_INVALID, "tail blob does not match this context");
+    if (a > c->porch) return set_err(DBG_ERR_STATE, "incoming boundary cluster exceeds the porch");
+    const char *nodes_h = static_cast<const char *>(blob) + sizeof(hdr);
+    const uint64_t own = c->shard_hi - c->shard_lo;
+    // in-range part: verbatim into the end of the porch (same relative slots: they end at the shard boundary)
+    if (a) CU_TRY(cudaMemcpyAsync(static_cast<char *>(c->d_nodes) - a * nbb, nodes_h, a * nbb, cudaMemcpyHostToDevice, c->stream));
+    if (mt) {
+        if (mt > c->tail_nodes_cap) {
+            cudaFree(c->d_tail_nodes); c->d_tail_nodes = nullptr; c->tail_nodes_cap = 0;
+            CU_TRY(cudaMalloc(&c->d_tail_nodes, mt * nbb));
+            c->tail_nodes_cap = mt;
+        }
+        CU_TRY(cudaMemcpyAsync(c->d_tail_nodes, nodes_h + a * nbb, mt * nbb, cudaMemcpyHostToDevice, c->stream));
+        if (c->wide) k_shard_adopt<true><<<1, 32, 0, c->stream>>>((NodeT<true> *)c->d_nodes, c->n_local, (const NodeT<true> *)c->d_tail_nodes, mt, c->d_tail);
+        else k_shard_adopt<false><<<1, 32, 0, c->stream>>>((NodeT<false> *)c->d_nodes, c->n_local, (const NodeT<false> *)c->d_tail_nodes, mt, c->d_tail);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        TailInfo ti;
+        CU_TRY(cudaMemcpyAsync(&ti, c->d_tail, sizeof(ti), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        c->nodes_delta += (int64_t)ti.adopted;
+        // the adopted chain must end before this rank's own tail cluster starts (otherwise the hand-off cascades
+        // through the whole shard: tiny tables only) -- the caller then merges the shard dumps instead
+        if (ti.landing_max == ~0ULL || ti.landing_max + 1 >= own - c->tail_a_own)
+            return set_err(DBG_ERR_STATE, "boundary hand-off cascades through the whole shard: merge the shard dumps instead");
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));      // the blob may go away
+    c->tail_a_in = a;
+    c->tail_imported = true;
+    return DBG_OK;
+}
+
+extern "C" int dbg_shard_slice_info(dbg_ctx *c, uint64_t *g_first, uint64_t *n_slots, void **d_slice)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    if (c->n_shards <= 1 || !c->finalized || !c->d_out || !c->tail_imported) return set_err(DBG_ERR_STATE, "no laid-out shard slice (tail export/import + finalize first)");
+    const LayoutGeom g = layout_geom(c);
+    if (g_first) *g_first = (g.gbase + g.v_begin) % c->P;
+    if (n_slots) *n_slots = g.v_end - g.v_begin;
+    if (d_slice) *d_slice = static_cast<char *>(c->d_out) + g.v_begin * (size_t)node_bytes(c);
+    return DBG_OK;
+}
+
+// copy this rank's slice into the FULL host table: array[P] (reference node size) and the nul_flag bytes this slice
+// covers completely; the (at most two) bytes it shares with its neighbours are returned in edge_slots[4] (UINT64_MAX =
+// unused) for dbg_host_fix_nul_bytes once every rank has exported
+extern "C" int dbg_export_shard_slice(dbg_ctx *c, void *array, uint8_t *nul_flag, uint64_t edge_slots[4])
+{
+    if (!c || !array) return set_err(DBG_ERR_INVALID, "NULL argument");
+    uint64_t g_first = 0, n = 0;
+    void *d_slice = nullptr;
+    int rc = dbg_shard_slice_info(c, &g_first, &n, &d_slice);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(c->device));
+    if (edge_slots) for (int i = 0; i < 4; i++) edge_slots[i] = UINT64_MAX;
+    if (n == 0) return DBG_OK;
+    EvPair e;
+    rc = ev_begin(c, c->stream, &e);
+    if (rc) return rc;
+    const size_t nb = (size_t)node_bytes(c);
+    const uint64_t first_len = g_first + n <= c->P ? n : c->P - g_first;
+    CU_TRY(cudaMemcpyAsync(static_cast<char *>(array) + g_first * nb, d_slice, first_len * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (first_len < n) CU_TRY(cudaMemcpyAsync(array, static_cast<char *>(d_slice) + first_len * nb, (n - first_len) * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (nul_flag) {
+        // run 1 covers global slots [g_first, g_first + first_len), its words start at word g_first / 32
+        int k = 0;
+        auto copy_run = [&](uint64_t s0, uint64_t len, const u32 *d_words, uint64_t w0) -> int {
+            if (len == 0) return DBG_OK;
+            const uint64_t s1 = s0 + len;                               // exclusive
+            uint64_t b0 = (s0 + 7) / 8, b1 = s1 / 8;                     // bytes covered completely
+            if (s1 == c->P) b1 = c->P / 8 + 1;                           // the table's last byte belongs to the slice that ends it
+            if (s0 % 8 && edge_slots && k < 4) edge_slots[k++] = s0;
+            if (s1 % 8 && s1 != c->P && edge_slots && k < 4) edge_slots[k++] = s1 - 1;
+            if (b1 > b0) CU_TRY(cudaMemcpyAsync(nul_flag + b0, reinterpret_cast<const uint8_t *>(d_words) + (b0 - w0 * 4), b1 - b0, cudaMemcpyDeviceToHost, c->stream));
+            return DBG_OK;
+        };
+        rc = copy_run(g_first, first_len, c->d_nul_slice, g_first / 32);
+        if (rc) return rc;
+        if (first_len < n) { rc = copy_run(0, n - first_len, c->d_nul_slice + c->nul_slice_words + 2, 0); if (rc) return rc; }
+    }
+    CU_TRY(cudaEventRecord(e.b, c->stream));
+    CU_TRY(cudaEventSynchronize(e.b));
+    CU_TRY(cudaEventElapsedTime(&c->ms[5], e.a, e.b));
+    ev_put(c, e);
+    return DBG_OK;
+}
+
+// host helpers for whoever merges the slices (no device work): recompute the nul_flag bytes that contain the given
+// slots from the table image, and append the k-mer-0 node last (add_node_to_kmerset, kmerSet.cpp:253-273,
+// DBGgraph.cpp:418).  Fix the edge bytes BEFORE the k-mer-0 node goes in (its key is 0, like an empty slot).
+extern "C" int dbg_host_fix_nul_bytes(const void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, const uint64_t *slots, uint64_t n)
+{
+    if (!array || !nul_flag || (!slots && n)) return DBG_ERR_INVALID;
+    for (uint64_t i = 0; i < n; i++) {
+        if (slots[i] == UINT64_MAX || slots[i] >= P) continue;
+        const uint64_t byte = slots[i] / 8;
+        uint8_t v = 0;
+        for (uint64_t s = byte * 8; s < byte * 8 + 8 && s < P; s++) {
+            bool occ;
+            if (wide) { const dbg_node32 *nd = static_cast<const dbg_node32 *>(array) + s; occ = (nd->kmer_lo | nd->kmer_hi) != 0; }
+            else occ = static_cast<const dbg_node16 *>(array)[s].kmer != 0;
+            if (occ) v |= (uint8_t)(0x80u >> (s & 7));
+        }
+        nul_flag[byte] = v;
+    }
+    return DBG_OK;
+}
+
+extern "C" int dbg_host_polyA_insert(void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, uint32_t l_link, uint32_t r_link, uint64_t *slot_out)
+{
+    if (!array || !nul_flag || P == 0) return DBG_ERR_INVALID;
+    uint64_t s = (wide ? hash_code_wide(0, 0) : hash_code(0)) % P;
+    uint64_t steps = 0;
+    while (nul_flag[s >> 3] & (0x80u >> (s & 7))) { s = (s + 1 == P) ? 0 : s + 1; if (++steps > P) return DBG_ERR_TABLE_FULL; }
+    if (wide) { dbg_node32 *nd = static_cast<dbg_node32 *>(array) + s; nd->kmer_lo = 0; nd->kmer_hi = 0; nd->l_link = l_link; nd->r_link = r_link; nd->pad = 0; }
+    else { dbg_node16 *nd = static_cast<dbg_node16 *>(array) + s; nd->kmer = 0; nd->l_link = l_link; nd->r_link = r_link; }
+    nul_flag[s >> 3] |= (uint8_t)(0x80u >> (s & 7));
+    if (slot_out) *slot_out = s;
     return DBG_OK;
 }
 
@@ -1244,7 +1538,7 @@ extern "C" int dbg_get_stats(dbg_ctx *c, dbg_stats *stats)
 extern "C" int dbg_device_image(dbg_ctx *c, void **d_array, void **d_nul_flag)
 {
     if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
-    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "no finalized image (unsharded contexts only)");
+    if (!c->finalized || !c->d_out || c->n_shards > 1) return set_err(DBG_ERR_STATE, "no finalized image (unsharded contexts only; sharded: dbg_shard_slice_info)");
     if (d_array) *d_array = c->d_out;
     if (d_nul_flag) *d_nul_flag = c->d_nul32;
     return DBG_OK;
@@ -1253,7 +1547,7 @@ extern "C" int dbg_device_image(dbg_ctx *c, void **d_array, void **d_nul_flag)
 extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
 {
     if (!c || !array || !nul_flag) return set_err(DBG_ERR_INVALID, "NULL argument");
-    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "dbg_export_kmerset needs dbg_finalize on an unsharded context");
+    if (!c->finalized || !c->d_out || c->n_shards > 1) return set_err(DBG_ERR_STATE, "dbg_export_kmerset needs dbg_finalize on an unsharded context (sharded: dbg_export_shard_slice)");
     CU_TRY(cudaSetDevice(c->device));
     EvPair e;
     int rc = ev_begin(c, c->stream, &e);
@@ -1272,7 +1566,7 @@ extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
 // ---------------------------------------------------------------------------------------------------
 static int run_links(dbg_ctx *c, int cutoff)
 {
-    if (!c->finalized || !c->d_out) return set_err(DBG_ERR_STATE, "needs dbg_finalize on an unsharded context");
+    if (!c->finalized || !c->d_out || c->n_shards > 1) return set_err(DBG_ERR_STATE, "needs dbg_finalize on an unsharded context");
     if (c->links_cutoff == cutoff) return DBG_OK;
     uint64_t n_tiles = (c->P + TILE - 1) / TILE;
     if (!c->d_klink) {
@@ -1390,7 +1684,7 @@ extern "C" int dbg_dump_shard(dbg_ctx *c, uint64_t *kmers_lo, uint64_t *kmers_hi
     u64 cnt[CNT_N];
     int rc = read_counters(c, cnt);
     if (rc) return rc;
-    uint64_t m = cnt[CNT_NEW], cap = *n;
+    uint64_t m = (uint64_t)((int64_t)cnt[CNT_NEW] + c->nodes_delta), cap = *n;      // what is physically in this shard's table
     *n = m;
     if (!kmers_lo && !kmers_hi && !l_link && !r_link && !first_ordinal) return DBG_OK;   // size query
     if (cap < m) return set_err(DBG_ERR_BUFFER, "dump capacity %llu < %llu", (unsigned long long)cap, (unsigned long long)m);

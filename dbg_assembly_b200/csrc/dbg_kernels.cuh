@@ -986,6 +986,27 @@ __global__ void k_layout_place(const NodeT<WIDE> *__restrict__ nodes, u64 n_loca
 // walks it (clusters average 2-3 slots at load 0.5), simulates the replay on a 64-bit occupancy mask and
 // writes the 16-B image nodes; clusters longer than 64 slots and the region where the table wraps around
 // go to k_layout_regions, which runs the atomicMin priority probing on a per-region scratch.
+// Window of the table a layout pass works on, in VIRTUAL slot numbers v (index into the physical node array):
+//   unsharded : v = global slot, window [0, P), gbase = 0
+//   sharded   : the physical array of rank r is [porch | own home range | margin]; v = 0 is global slot gbase =
+//               (lo_r - porch) mod P.  The porch holds the neighbour's tail cluster (cross-shard hand-off), so a
+//               cluster that crosses the shard boundary is replayed as one unit by the rank on its right.
+// Every key found inside the window has its home inside [gbase, gbase + window) (mod P), so home -> virtual is
+// home - gbase (+ P when that is negative).
+struct LayoutGeom {
+    u64 P, M;
+    u64 gbase;        // global slot of v = 0
+    u64 v_begin;      // first slot laid out
+    u64 v_end;        // one past the last slot laid out (slots >= v_end are treated as absent)
+};
+
+__device__ __forceinline__ u64 home_virtual(const LayoutGeom &g, u64 klo, u64 khi, bool wide)
+{
+    const u64 h = wide ? hash_code_wide(klo, khi) : hash_code(klo);
+    const u64 home = mod_P(h, g.P, g.M);
+    return home >= g.gbase ? home - g.gbase : home + (g.P - g.gbase);
+}
+
 struct LayoutInfo {
     u64 e;              // first slot of the cluster that runs over the end of the table (== P: none)
     u64 g;              // slots [0, g) take part in the wrap-around region
@@ -1069,41 +1090,43 @@ __device__ __forceinline__ void cluster_bounds(const u32 *W, int k, bool prev_oc
 }
 
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+__global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, LayoutGeom geo, void *out, u32 *nul32,
                                                         LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
 {
     // the tile's nodes, loaded coalesced and digested in parallel: key, ordinal, packed link words, home slot;
     // then EVERY occupied slot's thread replays its own key with priority probing (atomicMin on the ordinal) in
-    // shared memory -- the same algorithm as the global method, but on chip, per tile, with no idle lanes
+    // shared memory -- the same algorithm as the global method, but on chip, per tile, with no idle lanes.
+    // nul32 == nullptr (sharded windows): the occupancy bitmap is produced afterwards from the image (k_nul_from_image),
+    // because a window's 32-slot groups are not aligned with the global bitmap words.
     __shared__ u64 s_klo[LT + LH], s_khi[WIDE ? LT + LH : 1], s_ord[LT + LH], s_links[LT + LH], s_owner[LT + LH];
     __shared__ u32 s_home[LT + LH];     // home - tile start (>= 0 for every cluster that starts in the tile)
     __shared__ u32 s_W[LW];             // occupancy bitmap of the window
     __shared__ int s_prev;
     const u64 e_skip = info->e, g_skip = info->g;
+    const u64 v_end = geo.v_end;
     const int t = threadIdx.x;
     const u32 lane = t & 31;
-    for (u64 i0 = (u64)blockIdx.x * LT; i0 < P; i0 += (u64)gridDim.x * LT) {
+    for (u64 i0 = geo.v_begin + (u64)blockIdx.x * LT; i0 < v_end; i0 += (u64)gridDim.x * LT) {
         for (int k = t; k < LT + LH; k += LT) {          // k = t, and t + LT for the first LH threads (warp uniform)
             const u64 s = i0 + k;
             NodeRegs nd; nd.klo = 0; nd.khi = 0; nd.nord = 0; nd.c0 = 0; nd.c1 = 0;
-            if (s < P) load_node(nodes + s, nd);
+            if (s < v_end) load_node(nodes + s, nd);
             const bool o = (nd.klo | nd.khi) != 0;
             s_klo[k] = nd.klo; if (WIDE) s_khi[k] = nd.khi;
             s_owner[k] = EMPTY_PRI;
             if (o) {
-                u64 h = WIDE ? hash_code_wide(nd.klo, nd.khi) : hash_code(nd.klo);
-                s_home[k] = (u32)(mod_P(h, P, M) - i0);
+                s_home[k] = (u32)(home_virtual(geo, nd.klo, nd.khi, WIDE) - i0);
                 s_ord[k] = TRACK ? ~nd.nord : s;
                 s_links[k] = (u64)pack_link(nd.c0) | ((u64)pack_link(nd.c1) << 32);
             }
             const u32 bal = __ballot_sync(0xffffffffu, o);
             if (lane == 0) {
                 s_W[k >> 5] = bal;
-                if (k < LT && s < P) nul32[s >> 5] = __byte_perm(__brev(bal), 0, 0x0123);   // MSB-first bitmap word of 32 slots
+                if (nul32 && k < LT && s < v_end) nul32[s >> 5] = __byte_perm(__brev(bal), 0, 0x0123);   // MSB-first bitmap word of 32 slots
             }
-            if (k < LT && s < P && !o) write_image<WIDE>(out, s, 0, 0, 0);
+            if (k < LT && s < v_end && !o) write_image<WIDE>(out, s, 0, 0, 0);
         }
-        if (t == 0) s_prev = (i0 > 0) && slot_occupied<WIDE>(nodes, i0 - 1);
+        if (t == 0) s_prev = (i0 > geo.v_begin) && slot_occupied<WIDE>(nodes, i0 - 1);
         __syncthreads();
         bool mine[2] = {false, false};
         for (int r = 0, k = t; k < LT + LH; k += LT, r++) {
@@ -1117,7 +1140,7 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
                 // longer than the shared-memory window: measure it in global memory, hand it to k_layout_regions
                 if (k == start) {
                     u64 len = (u64)(end > LT + LH ? LT + LH - start : end - start);
-                    while (cs + len < P && slot_occupied<WIDE>(nodes, cs + len)) len++;
+                    while (cs + len < v_end && slot_occupied<WIDE>(nodes, cs + len)) len++;
                     u32 rr = atomicAdd(&info->n_regions, 1u);
                     u64 off = atomicAdd(&info->scratch_used, len);
                     if (rr >= MAX_REGIONS || off + len > scratch_cap) info->overflow = 1;
@@ -1149,10 +1172,11 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
 
 // long clusters and the wrap-around region: priority probing (atomicMin on the ordinal) inside a private scratch
 template <bool WIDE, bool TRACK>
-__global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__restrict__ nodes, u64 P, u64 M, void *out, u32 *nul32,
+__global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__restrict__ nodes, LayoutGeom geo, void *out, u32 *nul32,
                                                         const LayoutInfo *__restrict__ info, const LayoutRegion *__restrict__ regions, u64 *scratch)
 {
     if (info->overflow) return;
+    const u64 P = geo.P;
     const u32 n_regions = info->n_regions < MAX_REGIONS ? info->n_regions : MAX_REGIONS;
     const u64 e = info->e, mt = info->mt, g = info->g;
     for (u32 r = blockIdx.x; r < n_regions; r += gridDim.x) {
@@ -1168,8 +1192,7 @@ __global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__res
                 NodeRegs nd;
                 load_node(nodes + s, nd);
                 if ((nd.klo | nd.khi) == 0) continue;
-                u64 h = WIDE ? hash_code_wide(nd.klo, nd.khi) : hash_code(nd.klo);
-                u64 home = mod_P(h, P, M);
+                u64 home = home_virtual(geo, nd.klo, nd.khi, WIDE);      // (wrap regions exist only in unsharded windows: virtual == global)
                 u64 pos = rg.wrap ? (home >= e ? home - e : home + (P - e)) : home - rg.a;
                 const u64 pri = TRACK ? ~nd.nord : s;
                 if (pass == 0) {
@@ -1185,12 +1208,74 @@ __global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__res
                     u64 slot = rg.wrap ? (e + pos >= P ? e + pos - P : e + pos) : rg.a + pos;
                     u64 links = (u64)pack_link(nd.c0) | ((u64)pack_link(nd.c1) << 32);
                     write_image<WIDE>(out, slot, nd.klo, nd.khi, links);
-                    atomicOr(nul32 + (slot >> 5), flag_mask(slot));
+                    if (nul32) atomicOr(nul32 + (slot >> 5), flag_mask(slot));
                 }
             }
             __syncthreads();
         }
     }
+}
+
+// ---- cross-shard hand-off (sharded contexts) ---------------------------------------------------------------
+// A probe cluster that crosses the boundary between two shards must be replayed as ONE unit.  The rank on the left
+// hands its TAIL UNIT to the rank on its right: the run of occupied slots that ends at its last home slot (`a` nodes,
+// kept in place by the receiver, in its porch) plus whatever its inserts pushed into the overflow margin (`mt` nodes:
+// in the global table they sit in the right neighbour's first free slots, so the receiver adopts them by probing from
+// its slot 0).  The receiver then lays out [porch tail | own range minus its own tail unit].
+struct TailInfo { u64 a, mt, landing_max, adopted; };
+
+template <bool WIDE>
+__global__ void k_shard_tail_scan(const NodeT<WIDE> *__restrict__ nodes /* local slot 0 */, u64 own_size, u64 n_local, u64 max_a, TailInfo *ti)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u64 mt = 0, a = 0;
+    while (own_size + mt < n_local && slot_occupied<WIDE>(nodes, own_size + mt)) mt++;
+    while (a < own_size && a <= max_a && slot_occupied<WIDE>(nodes, own_size - 1 - a)) a++;
+    ti->a = a; ti->mt = mt;
+}
+
+// adopt the left neighbour's margin nodes: first free slot from local slot 0, whole node (key, ordinal, counts) copied.
+// The table is quiescent (no inserts in flight), one thread, plain stores.
+template <bool WIDE>
+__global__ void k_shard_adopt(NodeT<WIDE> *nodes /* local slot 0 */, u64 n_local, const NodeT<WIDE> *__restrict__ src, u64 n, TailInfo *ti)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u64 pos = 0, last = 0;
+    bool any = false;
+    for (u64 i = 0; i < n; i++) {
+        while (pos < n_local && slot_occupied<WIDE>(nodes, pos)) pos++;
+        if (pos >= n_local) { ti->landing_max = ~0ULL; ti->adopted = i; return; }
+        nodes[pos] = src[i];
+        last = pos; any = true;
+    }
+    // the chain continues through the occupied run behind the last adopted node: report where it ends
+    if (any) { u64 q = last; while (q + 1 < n_local && slot_occupied<WIDE>(nodes, q + 1)) q++; ti->landing_max = q; }
+    else ti->landing_max = 0;
+    ti->adopted = n;
+}
+
+// occupancy bitmap of a range of GLOBAL slots from the laid-out image (sharded windows): word w covers global slots
+// 32 w .. 32 w + 31, MSB-first bytes like nul_flag (kmerSet.h:144-155).  img is indexed by virtual slot; a global slot
+// outside [g_first, g_first + n) (mod P) contributes 0.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_nul_from_image(const void *__restrict__ img, u64 P, u64 gbase, u64 g_first, u64 n, u64 w_first,
+                                                        u64 n_words, u32 *nul32)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 w = gid >> 5;
+    if (w >= n_words) return;
+    const u64 gslot = (w_first + w) * 32 + (threadIdx.x & 31);
+    bool o = false;
+    if (gslot < P) {
+        const u64 rel = gslot >= g_first ? gslot - g_first : gslot + (P - g_first);     // distance from the range start (mod P)
+        if (rel < n) {
+            const u64 v = gslot >= gbase ? gslot - gbase : gslot + (P - gbase);
+            if (WIDE) { ulonglong2 k = __ldg(reinterpret_cast<const ulonglong2 *>(img) + 2 * v); o = (k.x | k.y) != 0; }
+            else o = __ldg(reinterpret_cast<const u64 *>(img) + 2 * v) != 0;
+        }
+    }
+    const u32 bal = __ballot_sync(0xffffffffu, o);
+    if ((threadIdx.x & 31) == 0) nul32[w] = __byte_perm(__brev(bal), 0, 0x0123);
 }
 
 // add_node_to_kmerset(kset, PolyA) (kmerSet.cpp:253-273, DBGgraph.cpp:418): last, always, first null slot

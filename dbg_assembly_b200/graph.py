@@ -169,6 +169,32 @@ class DBGBuilder:
         a = np.ascontiguousarray(a, dtype=np.uint64)
         capi.check(self.L.dbg_set_polyA_counts(self.h, a.ctypes.data), "dbg_set_polyA_counts")
 
+    # ---- cross-shard reference layout (include/dbg_b200.h: dbg_shard_tail_export ...) ----
+    def shard_tail_export(self) -> bytes:
+        """this rank's tail unit (boundary cluster + overflow nodes) for the rank on its right"""
+        n = C.c_uint64(0)
+        capi.check(self.L.dbg_shard_tail_export(self.h, None, 0, C.byref(n)), "dbg_shard_tail_export")
+        buf = (C.c_uint8 * n.value)()
+        capi.check(self.L.dbg_shard_tail_export(self.h, buf, n.value, C.byref(n)), "dbg_shard_tail_export")
+        return bytes(buf)
+
+    def shard_tail_import(self, blob: bytes):
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        capi.check(self.L.dbg_shard_tail_import(self.h, buf, len(blob)), "dbg_shard_tail_import")
+
+    def shard_slice_info(self):
+        """-> (first global slot, number of slots, device pointer) of the laid-out slice"""
+        g, n, d = C.c_uint64(0), C.c_uint64(0), C.c_void_p()
+        capi.check(self.L.dbg_shard_slice_info(self.h, C.byref(g), C.byref(n), C.byref(d)), "dbg_shard_slice_info")
+        return g.value, n.value, d.value
+
+    def export_shard_slice(self, array_ptr, nul_ptr):
+        """copy the slice into the FULL table image at array_ptr / nul_ptr (host); -> edge slots whose nul_flag byte is
+        shared with a neighbour (fix them with capi host_fix_nul_bytes once every slice is in)"""
+        edges = (C.c_uint64 * 4)()
+        capi.check(self.L.dbg_export_shard_slice(self.h, array_ptr, nul_ptr, edges), "dbg_export_shard_slice")
+        return [int(e) for e in edges if e != UINT64_MAX]
+
     # ---- results ----
     def finalize(self):
         st = capi.dbg_stats()

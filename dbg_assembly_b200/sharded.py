@@ -25,6 +25,159 @@ def owner_of(home_slot, P: int, n: int):
     return home_slot // shard_size(P, n)
 
 
+# ---------------------------------------------------------------------------------------------------
+# cross-shard reference layout: transport-agnostic pieces (include/dbg_b200.h, dbg_shard_tail_export ...)
+# ---------------------------------------------------------------------------------------------------
+def blob_margin_nodes(blob: bytes):
+    """the overflow (margin) nodes inside a tail blob as a dump dict (kmer, kmer_hi, l, r, ord): what a rank handed to
+    its right neighbour.  Only the dump-merging fallback needs it."""
+    a, mt, nbb, _ = np.frombuffer(blob[:32], dtype=np.uint64).tolist()
+    raw = np.frombuffer(blob, dtype=np.uint8, offset=32 + a * nbb, count=mt * nbb).reshape(mt, nbb)
+    w = raw.view(np.uint64).reshape(mt, nbb // 8)
+    if nbb == 32:
+        klo, khi, nord, c = w[:, 0], np.zeros(mt, np.uint64), w[:, 1], raw[:, 16:32]
+    else:
+        klo, khi, nord, c = w[:, 0], w[:, 1], w[:, 2], raw[:, 32:48]
+    cnt = np.minimum(np.ascontiguousarray(c).view(np.float16).reshape(mt, 8).astype(np.uint32), 255)
+    link = lambda q: (q[:, 0] << 24) | (q[:, 1] << 16) | (q[:, 2] << 8) | q[:, 3]      # lane of base b = byte 3-b
+    return dict(kmer=klo.copy(), kmer_hi=khi.copy(), l=link(cnt[:, :4]).astype(np.uint32), r=link(cnt[:, 4:]).astype(np.uint32),
+                ord=~nord)
+
+
+def merge_dumps_host(dumps, P_request, load_factor, wide, polyA_l, polyA_r):
+    """Fallback of the windowed cross-shard layout (boundary cluster too long for the hand-off: tiny or pathologically
+    dense tables): rebuild the reference's table from the union of the shard dumps by replaying the keys in
+    first-occurrence order on the host (dbg_replay_growth with the growth checks switched off)."""
+    from .graph import replay_growth
+    cat = {k: np.concatenate([d[k] for d in dumps]) for k in ("kmer", "kmer_hi", "l", "r", "ord")}
+    # a node can show up twice (adopted by the right neighbour AND listed from the blob): keep one
+    key = np.stack([cat["kmer_hi"], cat["kmer"]], axis=1)
+    _, first = np.unique(key, axis=0, return_index=True)
+    cat = {k: v[np.sort(first)] for k, v in cat.items()}
+    cat["wide"] = bool(wide)
+    n_reads = int(cat["ord"].max() >> np.uint64(16)) + 1 if len(cat["ord"]) else 1
+    plan, arr, nul = replay_growth(cat, [n_reads], P_request, load_factor, max_double_times=0, buffer_reads=1 << 62,
+                                   polyA_l=polyA_l, polyA_r=polyA_r)
+    return arr, nul, plan
+
+
+def ring_layout(builders):
+    """single process, all ranks at hand (tests, one process driving several GPUs): tail hand-off around the ring, then
+    every rank lays out its window.  Returns (list of stats, blobs)."""
+    n = len(builders)
+    blobs = [b.shard_tail_export() for b in builders]
+    for r, b in enumerate(builders):
+        b.shard_tail_import(blobs[(r - 1) % n])
+    return [b.finalize() for b in builders], blobs
+
+
+def export_merged(builders, stats, array=None, nul_flag=None):
+    """slices of all ranks -> ONE host table in the reference's layout (array[P], nul_flag[P/8+1]) + the k-mer-0 node"""
+    from .graph import NODE16, NODE32
+    from . import capi
+    P, wide = stats[0]["array_size"], bool(stats[0]["wide"])
+    if array is None:
+        array = np.zeros(P, dtype=NODE32 if wide else NODE16)
+    if nul_flag is None:
+        nul_flag = np.zeros(P // 8 + 1, dtype=np.uint8)
+    edges = []
+    for b in builders:
+        edges += b.export_shard_slice(array.ctypes.data, nul_flag.ctypes.data)
+    capi.host_fix_nul_bytes(array, nul_flag, P, wide, edges)
+    capi.host_polyA_insert(array, nul_flag, P, wide, stats[0]["polyA_l"], stats[0]["polyA_r"])
+    return array, nul_flag
+
+
+class LocalShards:
+    """N sharded contexts driven by ONE process (all on `devices[r]`; the same device may repeat): the complete
+    multi-GPU flow -- fused peer exchange (count, exact offsets, scatter into the owners' receive buffers), owner-side
+    insert, k-mer-0 counters summed, cross-shard layout, merged export -- without torch.distributed.  What the GPU
+    tests run on a single device, and what a single-process front end would run on several."""
+
+    def __init__(self, n, K, max_read_len, init_slots, load_factor=0.7, devices=None, track_order=True, force_wide=False,
+                 by_slice=False):
+        import torch
+        from .graph import DBGBuilder
+        self.n = n
+        self.devices = devices or [0] * n
+        self.b = [DBGBuilder(K=K, max_read_len=max_read_len, init_slots=init_slots, load_factor=load_factor, device=self.devices[r],
+                             track_order=track_order, shard_rank=r, shard_count=n, force_wide=force_wide) for r in range(n)]
+        self.tb = self.b[0].tuple_bytes
+        self.by_slice = by_slice
+        self.torch = torch
+        self.P_request, self.load_factor = init_slots, load_factor
+        self.blobs = None
+
+    def close(self):
+        for b in self.b:
+            b.close()
+
+    def add_blocks(self, blocks):
+        """blocks[r] = (d_bases tensor, d_offs tensor, n_reads, first_base, total_bases, first_read_index): the reads rank r
+        contributes to this round (None = nothing).  One exchange round: count on every rank, offsets, scatter, insert."""
+        torch, n = self.torch, self.n
+        nbl = self.b[0].partition_info()[0] if self.by_slice else 1
+        nbt = n * nbl
+        counts = []
+        for r, blk in enumerate(blocks):
+            dev = torch.device("cuda", self.devices[r])
+            c = torch.zeros(nbt, dtype=torch.int64, device=dev)
+            if blk is not None:
+                db, do, nr, fb, tbases, fri = blk
+                self.b[r].exchange_count_device(db.data_ptr(), do.data_ptr(), nr, fb, tbases, n, c.data_ptr(), by_slice=self.by_slice)
+            counts.append(c)
+        for r in range(n):
+            torch.cuda.synchronize(self.devices[r])
+        allc = torch.stack([c.cpu() for c in counts])                      # [source][bucket]
+        col = allc.sum(dim=0).view(n, nbl)
+        start = torch.cumsum(col, dim=1) - col
+        recv_total = col.sum(dim=1).tolist()
+        recv = [torch.zeros(max(int(recv_total[q]), 1) * (self.tb // 8), dtype=torch.int64, device=torch.device("cuda", self.devices[q]))
+                for q in range(n)]
+        ptrs = [t.data_ptr() for t in recv]
+        for r, blk in enumerate(blocks):
+            if blk is None:
+                continue
+            dev = torch.device("cuda", self.devices[r])
+            db, do, nr, fb, tbases, fri = blk
+            d_base = (start.reshape(-1) + allc[:r].sum(dim=0)).contiguous().to(dev)
+            d_ptrs = torch.tensor([ptrs[q] for q in range(n) for _ in range(nbl)], dtype=torch.int64, device=dev)
+            self.b[r].exchange_scatter_device(db.data_ptr(), do.data_ptr(), nr, fb, tbases, fri, n, d_ptrs.data_ptr(), d_base.data_ptr(),
+                                              by_slice=self.by_slice)
+            torch.cuda.synchronize(self.devices[r])
+        for q in range(n):
+            if recv_total[q] == 0:
+                continue
+            if self.by_slice:
+                so = torch.cat([start[q], col[q].sum().reshape(1)]).contiguous().to(recv[q].device)
+                self.b[q].insert_sliced_device(recv[q].data_ptr(), int(recv_total[q]), so.data_ptr())
+            else:
+                self.b[q].insert_tuples_device(recv[q].data_ptr(), int(recv_total[q]))
+            torch.cuda.synchronize(self.devices[q])
+        return recv_total
+
+    def finalize(self, layout=True):
+        polyA = sum(b.get_polyA_counts() for b in self.b)
+        for b in self.b:
+            b.set_polyA_counts(polyA)
+        if not layout:
+            return [b.finalize() for b in self.b]
+        stats, self.blobs = ring_layout(self.b)
+        return stats
+
+    def export_kmerset(self, stats):
+        return export_merged(self.b, stats)
+
+    def export_kmerset_fallback(self, stats=None):
+        """merge the shard dumps on the host (used when the windowed layout refuses: DbgError with DBG_ERR_STATE)"""
+        dumps = [b.dump_shard() for b in self.b]
+        if self.blobs:
+            dumps += [blob_margin_nodes(bl) for bl in self.blobs]
+        polyA = self.b[0].get_polyA_counts()
+        cl = lambda q: sum(int(min(int(q[i]), 255)) << (24 - 8 * i) for i in range(4))
+        return merge_dumps_host(dumps, self.P_request, self.load_factor, self.b[0].wide, cl(polyA[:4]), cl(polyA[4:]))
+
+
 class Exchange:
     """all-to-all(v) of fixed-width tuples: sizes first, then payload."""
 
@@ -202,10 +355,30 @@ class ShardedBuilder:
         self._keep = recv    # keep alive until the insert kernel ran
         return total
 
-    def finalize(self):
+    def _ring_blobs(self, blob: bytes) -> bytes:
+        """every rank's tail blob goes to the rank on its right (sizes first, then one padded all-gather: blobs are
+        a few hundred bytes)"""
+        n, dev = self.n, self.device
+        size = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
+        sizes = torch.empty(n, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, size, group=self.ex.group)
+        sizes = sizes.cpu().tolist()
+        mx = (max(sizes) + 7) // 8 * 8
+        mine = torch.zeros(mx, dtype=torch.uint8)
+        mine[: len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        allb = torch.empty(n * mx, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine.to(dev), group=self.ex.group)
+        left = (self.rank - 1) % n
+        return bytes(allb[left * mx: left * mx + sizes[left]].cpu().numpy().tobytes())
+
+    def finalize(self, layout=False):
+        """layout=True: cross-shard hand-off of the boundary clusters, then every rank lays out its slice of the
+        reference's table (dbg_export_shard_slice / export_slice copies it out)"""
         torch.cuda.synchronize(self.device)
         polyA = self.ex.allreduce_sum_u64(self.b.get_polyA_counts(), self.device)
         self.b.set_polyA_counts(polyA)
+        if layout and self.n > 1:
+            self.b.shard_tail_import(self._ring_blobs(self.b.shard_tail_export()))
         st = self.b.finalize()
         tot = self.ex.allreduce_sum_u64(np.array([st["count"], st["occurrences"]], dtype=np.uint64), self.device)
         st["global_count"] = int(tot[0]) + 1          # + the k-mer-0 node

@@ -148,6 +148,31 @@ int  dbg_tuple_bytes(const dbg_ctx *ctx);               /* 16 or 32 */
 int  dbg_get_polyA_counts(dbg_ctx *ctx, uint64_t counts[8]);
 int  dbg_set_polyA_counts(dbg_ctx *ctx, const uint64_t counts[8]);
 
+/* ---- cross-shard reference layout: the multi-GPU build as a drop-in ------------------------------------------
+ * Owner = slot range (DBGgraph.cpp:148 lifted to GPUs), so the shards' tables concatenate into the reference's table --
+ * except for probe clusters that cross a shard boundary, which must be replayed as one unit.
+ * Protocol, on every rank r of the ring, after the last insert:
+ *   1. dbg_shard_tail_export : the TAIL UNIT of r -- the run of occupied slots ending at r's last home slot plus the
+ *                              nodes r's inserts pushed past it (they belong into r+1's first free slots) -- as a blob
+ *                              of host bytes (blob == NULL: size query).  r excludes that run from its own layout.
+ *   2. (caller moves the blob to rank (r+1) % n: torch.distributed, MPI, memcpy ...)
+ *   3. dbg_shard_tail_import : r+1 keeps the run in the porch in front of its table and adopts the overflow nodes.
+ *   4. dbg_finalize          : lays out [imported run | own range minus own tail run] in the reference's slot order.
+ *   5. dbg_export_shard_slice: copies that slice into the caller's FULL table image array[P] (+ the nul_flag bytes it
+ *                              covers completely; the bytes shared with a neighbour come back in edge_slots).
+ *   6. once, by whoever holds the merged table: dbg_host_fix_nul_bytes(edge slots of all ranks), then
+ *      dbg_host_polyA_insert (the k-mer-0 node goes in last, DBGgraph.cpp:418; link words = stats.polyA_l/_r after the
+ *      side counters were summed over the ranks).
+ * DBG_ERR_STATE from 1/3/4 means the boundary cluster does not fit the hand-off (tables of a few thousand slots, or
+ * pathologically dense ones): merge the dbg_dump_shard outputs with dbg_replay_growth instead (same layout). */
+int  dbg_shard_tail_export(dbg_ctx *ctx, void *blob, uint64_t cap_bytes, uint64_t *n_bytes);
+int  dbg_shard_tail_import(dbg_ctx *ctx, const void *blob, uint64_t n_bytes);
+/* the laid-out slice: first global slot, length (it may wrap past slot P-1), device pointer (reference node size) */
+int  dbg_shard_slice_info(dbg_ctx *ctx, uint64_t *g_first, uint64_t *n_slots, void **d_slice);
+int  dbg_export_shard_slice(dbg_ctx *ctx, void *array, uint8_t *nul_flag, uint64_t edge_slots[4]);
+int  dbg_host_fix_nul_bytes(const void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, const uint64_t *slots, uint64_t n);
+int  dbg_host_polyA_insert(void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, uint32_t l_link, uint32_t r_link, uint64_t *slot_out);
+
 /* ---- results ---------------------------------------------------------------------------------- */
 /* Tail of build_debruijn_graph: waits for all blocks, builds the reference-layout image on the device
  * and appends the k-mer-0 node last (DBGgraph.cpp:418).  Fills *stats (may be NULL). */

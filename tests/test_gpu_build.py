@@ -330,6 +330,27 @@ def test_table_full_is_reported_not_hung(dbg):
         assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
 
 
+def test_table_full_is_reported_promptly_on_a_large_table(dbg, build_path, monkeypatch):
+    """a table of 2 M slots fed 6 M distinct k-mers in several host batches: DBG_ERR_TABLE_FULL comes back from a
+    submit (or the finalize) within seconds -- probes are capped, a full table ends the kernels early, and the counters
+    travel to the host behind every batch"""
+    import time
+    from dbg_assembly_b200 import synth
+    if build_path != "direct":
+        pytest.skip("batching set by this test")
+    monkeypatch.setenv("DBG_B200_BATCH_BASES", "40000000")
+    p = synth.make_params(seed=5, genome_len=50_000_000, read_len=150, insert=400, err=0.0, n_rate=0.0)
+    hb, ho = synth.reads_host(p, 0, 400_000)
+    t0 = time.perf_counter()
+    with pytest.raises(dbg.capi.DbgError) as ei:
+        with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=2_000_000) as b:
+            for r0 in range(0, 400_000, 50_000):
+                b.submit(hb[r0 * 150:(r0 + 50_000) * 150], ho[: 50_001])
+            b.finalize()
+    assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
+    assert time.perf_counter() - t0 < 60
+
+
 @pytest.mark.parametrize("optimistic,K", [("1", 31), ("0", 31), ("overflow", 31), ("1", 63), ("overflow", 63)])
 def test_sharded_tuple_path_single_gpu(dbg, oracle_mod, monkeypatch, optimistic, K):
     """multi-GPU building blocks on one device: extract tuples bucketed by owner shard, insert each bucket
