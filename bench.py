@@ -91,40 +91,81 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's own build on the host cores, bounded sample
+# reference arm / cpu baseline: the reference's own build on the host cores, on the FULL named workload
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, sample_reads, threads, steps, warmup, name):
-    """returns (values list [k-mers/s per timed step], info dict)"""
-    from dbg_assembly_b200 import synth
+SYNTH_FASTA = os.path.join(REPO, "oracle", "_bin", "synth_fasta")
+
+
+def write_workload_fasta(cfg, n_reads, path, raw=False):
+    """the workload's reads as one-line FASTA, written by the stand-alone generator (oracle/tools/synth_fasta.cpp: same
+    counter-based generator as the library, but nothing of the product is loaded by this process)"""
+    if not os.access(SYNTH_FASTA, os.X_OK):
+        subprocess.run(["make", "-C", os.path.join(REPO, "oracle"), "tools"], check=True, stdout=subprocess.DEVNULL)
+    err = int(round(cfg["err"] * (1 << 24))); nr = int(round(cfg["n_rate"] * (1 << 24)))
+    cmd = [SYNTH_FASTA, str(cfg["seed"]), str(cfg["genome_len"]), str(cfg["read_len"]), str(cfg["insert"]), str(err), str(nr), "0",
+           str(n_reads), path] + (["raw"] if raw else [])
+    subprocess.run(cmd, check=True)
+
+
+def scratch_dir():
+    """tmpfs when it has room (the reference reads the file through the page cache either way)"""
+    for d in ("/dev/shm", None):
+        try:
+            if d is None or (os.path.isdir(d) and os.statvfs(d).f_bavail * os.statvfs(d).f_frsize > (4 << 30)):
+                return tempfile.TemporaryDirectory(dir=d)
+        except Exception:
+            pass
+    return tempfile.TemporaryDirectory()
+
+
+def cpu_reference_run(cfg, n_reads, threads, steps, warmup, name, budget_s=None):
+    """The reference build (oracle/_ref/ref_build_driver: the unmodified DBG_contig sources around build_debruijn_graph)
+    on the first n_reads reads of the workload (n_reads == cfg["n_reads"]: the whole workload, its own -i).
+    Returns (values [k-mers/s per timed step], info).  budget_s bounds the wall clock: at least one warm-up (if asked
+    for) and two timed builds always run, further ones only while the budget lasts."""
     from oracle import oracle as orc          # test infrastructure: only this leg may touch it
-    p = synth.make_params(cfg["seed"], cfg["genome_len"], cfg["read_len"], cfg["insert"], cfg["err"], cfg["n_rate"])
-    bases, offs = synth.reads_host(p, 0, sample_reads)
-    occ = sample_reads * (cfg["read_len"] - cfg["K"] + 1)
-    frac = sample_reads / cfg["n_reads"]
-    init_g = cfg["init_g"] * frac            # table scaled with the sample so the load factor matches the full run
+    occ = n_reads * (cfg["read_len"] - cfg["K"] + 1)
+    frac = n_reads / cfg["n_reads"]
+    init_g = cfg["init_g"] * frac             # == cfg["init_g"] for the whole workload
     vals = []
-    if orc.have_reference():
-        kind = "reference"
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "sample.fa")
-            orc.write_fasta(path, bases, offs)
-            for i in range(warmup + steps):
-                stats, _ = orc.run_ref_build([path], cfg["K"], cfg["max_read_len"], init_g, threads=threads, dump=False, timeout=1500)
-                if i >= warmup:
-                    vals.append(occ / stats["wall_s"])
-    else:
-        kind, threads = "port", 1
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            o = orc.OracleGraph(cfg["K"], cfg["max_read_len"], int(init_g * 1e9), 0.7, 10, 10000)
-            o.add_file(bases, offs); o.finish()
-            dt = time.perf_counter() - t0
-            o.close()
-            if i >= warmup:
-                vals.append(occ / dt)
-    info = {"kind": kind, "cores": threads,
-            "sample": f"first {sample_reads} reads of {name} ({occ} k-mer occurrences, {frac:.3f} of the workload), table -i {init_g:.4g} "
-                      f"(scaled with the sample), one-line FASTA from tmpfs/disk, whole build_debruijn_graph() incl. file read"}
+    t_start = time.perf_counter()
+    with scratch_dir() as td:
+        if orc.have_reference():
+            kind = "reference"
+            path = os.path.join(td, "reads.fa")
+            write_workload_fasta(cfg, n_reads, path)          # once, outside the timed builds
+            done_w = 0
+            while True:
+                elapsed = time.perf_counter() - t_start
+                over = budget_s is not None and elapsed > budget_s
+                # warm-ups: all that were asked for, but beyond the first only while they fit a quarter of the budget
+                if done_w < warmup and (done_w == 0 or budget_s is None or elapsed < budget_s / 4):
+                    orc.run_ref_build([path], cfg["K"], cfg["max_read_len"], init_g, threads=threads, dump=False, timeout=3000)
+                    done_w += 1
+                    continue
+                if len(vals) >= steps or (over and len(vals) >= min(2, steps)):
+                    break
+                stats, _ = orc.run_ref_build([path], cfg["K"], cfg["max_read_len"], init_g, threads=threads, dump=False, timeout=3000)
+                vals.append(occ / stats["wall_s"])
+        else:
+            kind, threads = "port", 1
+            path = os.path.join(td, "reads.raw")
+            write_workload_fasta(cfg, n_reads, path, raw=True)
+            bases = np.fromfile(path, dtype=np.uint8)
+            offs = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(cfg["read_len"])
+            for i in range(min(warmup, 1) + min(steps, 2)):
+                t0 = time.perf_counter()
+                o = orc.OracleGraph(cfg["K"], cfg["max_read_len"], int(init_g * 1e9), 0.7, 10, 10000)
+                o.add_file(bases, offs); o.finish()
+                dt = time.perf_counter() - t0
+                o.close()
+                if i >= min(warmup, 1):
+                    vals.append(occ / dt)
+    whole = n_reads == cfg["n_reads"]
+    info = {"kind": kind, "cores": threads, "steps_run": len(vals),
+            "sample": (f"the WHOLE workload {name}: {n_reads} reads, {occ} k-mer occurrences, -i {init_g:g}" if whole else
+                       f"first {n_reads} reads of {name} ({occ} k-mer occurrences, {frac:.3f} of the workload), table -i {init_g:.4g} (scaled with the sample)")
+                      + ", one-line FASTA written once before the timed builds, whole build_debruijn_graph() incl. file read, wall clock"}
     return vals, info
 
 
@@ -134,15 +175,19 @@ def run_reference_arm(args):
         return 0
     cfg = workload(args.workload, 1, args.scale)
     threads = os.cpu_count() or 1
-    sample = min(cfg["n_reads"], args.ref_sample_reads)
-    vals, info = cpu_reference_run(cfg, sample, threads, args.steps, args.warmup, args.workload)
+    n_reads = cfg["n_reads"] if args.ref_sample_reads <= 0 else min(cfg["n_reads"], args.ref_sample_reads)
+    vals, info = cpu_reference_run(cfg, n_reads, threads, args.steps, args.warmup, args.workload, budget_s=args.ref_budget_s)
     v = float(np.mean(vals))
-    occ = sample * (cfg["read_len"] - cfg["K"] + 1)
+    occ = n_reads * (cfg["read_len"] - cfg["K"] + 1)
+    cd = config_dict(args, cfg, 1)
+    if n_reads != cfg["n_reads"]:
+        cd["reference_sample_reads"] = n_reads
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * occ / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": config_dict(args, cfg, 1),
+            "dtype": "u64", "data": "synthetic", "config": cd,
             "cpu_baseline": dict(info, value=v, unit=UNIT),
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "steps_run": info["steps_run"], "per_step_values": vals}
     print(json.dumps(line))
     return 0
 
@@ -154,7 +199,147 @@ def config_dict(args, cfg, n):
             "K": cfg["K"], "reads_per_gpu": cfg["n_reads"], "read_len": cfg["read_len"], "table_slots_request": int(cfg["init_g"] * n * 1e9),
             "parallelism": f"hash-sharded x{n}" if n > 1 else "single GPU",
             "l2_policy": "inputs (reads 460 MB, table 6.4 GB per GPU) far exceed the 126 MB L2; table re-zeroed every step",
-            "layout_parity": "track_order=1 (reference -t 1 slot layout)" if n == 1 else "sharded: node multiset (layout export is single-GPU)"}
+            "layout_parity": "track_order=1 (reference -t 1 slot layout)" if n == 1 else
+                             "track_order=1; every rank lays out its slice of the reference table after the cross-shard hand-off of boundary clusters (same work per GPU as N=1)"}
+
+
+def short_workload(args, wname, local, dev, torch, dbg, synth, steps=3, warmup=2):
+    """one of the other named workloads on one GPU, device-resident reads: ms per build, k-mers/s, per-phase times, and the
+    end-to-end figure through host buffers (1 step)"""
+    from dbg_assembly_b200.graph import torch_stream_handle
+    cfg = workload(wname, 1, 1.0)
+    n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
+    p = synth.make_params(cfg["seed"], cfg["genome_len"], L, cfg["insert"], cfg["err"], cfg["n_rate"])
+    d_bases = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    synth.reads_device(p, 0, n, d_bases.data_ptr(), device=local)
+    d_offs = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
+    out = {"config": config_dict(argparse.Namespace(workload=wname), cfg, 1)["workload"]}
+    with dbg.DBGBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=int(cfg["init_g"] * 1000000000), device=local, track_order=True) as b:
+        b.set_stream(torch_stream_handle(dev))
+        for _ in range(warmup):
+            b.reset(); b.submit_device(d_bases.data_ptr(), d_offs.data_ptr(), n, 0, n * L, first_read_index=0); st = b.finalize()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            b.reset(); b.submit_device(d_bases.data_ptr(), d_offs.data_ptr(), n, 0, n * L, first_read_index=0); st = b.finalize()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tm = b.timings()
+        out.update({"ms_per_step": ms, "value": st["occurrences"] / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup,
+                    "occurrences_per_step": int(st["occurrences"]), "nodes": int(st["count"]), "dtype": "u128" if K > 31 else "u64",
+                    "clear_ms": tm["clear_ms"], "build_kernels_ms": tm["build_ms"], "insert_ms": tm["insert_ms"], "layout_ms": tm["layout_ms"],
+                    "paths": b.path_counts()})
+    del d_bases, d_offs
+    torch.cuda.empty_cache()
+    return out
+
+
+def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, st, rank, world, dev, dist, torch):
+    import mmap
+    import dbg_assembly_b200 as dbg
+    Lb = dbg.capi.load()
+    P = st["array_size"]
+    wide = K > 31
+    nb = 32 if wide else 16
+    img_bytes, nul_bytes = P * nb, P // 8 + 1
+    total = (img_bytes + 4095) // 4096 * 4096 + (nul_bytes + 4095) // 4096 * 4096
+    path = [f"/dev/shm/dbg_b200_e2e_{os.getpid()}.img"] if rank == 0 else [None]
+    dist.broadcast_object_list(path, src=0)
+    path = path[0]
+    ok = torch.tensor([1], device=dev)
+    if rank == 0:
+        try:
+            sv = os.statvfs("/dev/shm")
+            if sv.f_bavail * sv.f_frsize < total + (1 << 30):
+                raise OSError("not enough room in /dev/shm")
+            with open(path, "wb") as f:
+                f.truncate(total)
+        except Exception:
+            ok[0] = 0
+    dist.broadcast(ok, src=0)
+    if int(ok.item()) == 0:
+        raise RuntimeError(f"/dev/shm cannot hold the {total / 1e9:.1f} GB shared table image")
+    f = open(path, "r+b")
+    mm = mmap.mmap(f.fileno(), total)
+    base = np.frombuffer(mm, dtype=np.uint8)
+    base_ptr = base.ctypes.data
+    nul_off = (img_bytes + 4095) // 4096 * 4096
+    # page-lock only what this rank writes: its slice of the image (it may wrap) and its nul_flag bytes
+    g_first, n_slots, _ = sb.b.shard_slice_info()
+    regs = []
+
+    def reg(off, ln):
+        if ln <= 0:
+            return
+        a0 = off // 4096 * 4096
+        a1 = min(total, (off + ln + 4095) // 4096 * 4096)
+        dbg.capi.check(Lb.dbg_host_register(base_ptr + a0, a1 - a0), "dbg_host_register")
+        regs.append(base_ptr + a0)
+    first_len = min(n_slots, P - g_first)
+    reg(g_first * nb, first_len * nb)
+    if first_len < n_slots:
+        reg(0, (n_slots - first_len) * nb)
+    h_bases = torch.empty(n * L, dtype=torch.uint8).pin_memory()
+    h_offs = (torch.arange(n + 1, dtype=torch.int64) * L).pin_memory()
+    h_bases.copy_(d_bases.cpu())
+    d_b2, d_o2 = torch.empty_like(d_bases), torch.empty_like(d_offs)
+    arr_ptr, nul_ptr = base_ptr, base_ptr + nul_off
+    arr = np.frombuffer(mm, dtype=dbg.NODE32 if wide else dbg.NODE16, count=P)
+    nul = np.frombuffer(mm, dtype=np.uint8, count=nul_bytes, offset=nul_off)
+
+    def e2e_step():
+        d_b2.copy_(h_bases, non_blocking=True)
+        d_o2.copy_(h_offs, non_blocking=True)
+        sb.b.reset()
+        sb.add_reads_device(d_b2, d_o2, n, 0, n * L, first_read, occ_rank)
+        s = sb.finalize(layout=True)
+        edges = sb.b.export_shard_slice(arr_ptr, nul_ptr)
+        torch.cuda.synchronize()
+        e = torch.full((4,), -1, dtype=torch.int64, device=dev)
+        for i, x in enumerate(edges):
+            e[i] = x
+        alle = torch.empty(4 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(alle, e)               # also the barrier: every slice is in the shared image
+        if rank == 0:
+            ed = [int(x) for x in alle.cpu().tolist() if x >= 0]
+            dbg.capi.host_fix_nul_bytes(arr, nul, P, wide, ed)
+            dbg.capi.host_polyA_insert(arr, nul, P, wide, s["polyA_l"], s["polyA_r"])
+        dist.barrier()
+        return s
+    e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        s2 = e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    dt = (time.perf_counter() - t0) / e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    filled = int(np.unpackbits(nul[: min(nul_bytes, 1 << 20)]).sum()) if rank == 0 else 0
+    out = {"value": s2["global_occurrences"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * L + (n + 1) * 8) * world,
+           "d2h_bytes_per_step": int(img_bytes + nul_bytes), "ms_per_step": dt * 1e3, "steps": e_steps,
+           "what": "per rank: pinned host reads -> H2D -> fused exchange -> insert -> cross-shard hand-off -> layout -> D2H of the rank's slice into ONE "
+                   "shared host table image (/dev/shm); rank 0 fixes the shared nul_flag bytes and adds the k-mer-0 node; wall clock, max over ranks",
+           "merged_image_slots": int(P), "nul_bits_set_in_first_MiB": filled}
+    for r in regs:
+        Lb.dbg_host_unregister(r)
+    del arr, nul, base
+    try:
+        mm.close()
+    except BufferError:
+        pass
+    f.close()
+    dist.barrier()
+    if rank == 0:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -223,14 +408,15 @@ def run_b200(args):
     else:
         from dbg_assembly_b200.sharded import ShardedBuilder
         sb = ShardedBuilder(K=K, max_read_len=cfg["max_read_len"], init_slots=init_slots, device=local, track_order=True,
-                            exchange=args.exchange)
+                            exchange=args.exchange, sub_blocks=args.sub_blocks)
         extra["exchange"] = sb.exchange
+        extra["sub_blocks"] = sb.sub_blocks
         sb.b.set_stream(stream)
 
         def step():
             sb.b.reset()
             sb.add_reads_device(d_bases, d_offs, n, 0, n * L, first_read, occ_rank)
-            return sb.finalize()
+            return sb.finalize(layout=True)
         closer = sb
         launch_count = lambda: sb.b.launches  # noqa: E731
         timings = sb.b.timings
@@ -243,11 +429,12 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    build_ms, clear_ms, layout_ms, insert_ms = [], [], [], []
+    build_ms, clear_ms, layout_ms, insert_ms, scatter_ms = [], [], [], [], []
     for _ in range(args.steps):
         st = step()
         tm = timings()
         build_ms.append(tm["build_ms"]); clear_ms.append(tm["clear_ms"]); layout_ms.append(tm["layout_ms"]); insert_ms.append(tm["insert_ms"])
+        scatter_ms.append(tm.get("scatter_ms", 0.0))
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -261,6 +448,13 @@ def run_b200(args):
         occ_total = st["global_occurrences"]
         nodes_total = st["global_count"]
         extra["exchange_bytes_per_step_rank0"] = sb.exchange_bytes // (args.steps + args.warmup)
+        extra["optimistic_exchange_fallbacks"] = sb.opt_fallbacks
+        sc_ms = float(np.mean(scatter_ms))
+        if sc_ms > 0:
+            # NVLink figure of the fused scatter kernel(s): bytes this rank stored into its peers' buffers / kernel time
+            extra["nvlink"] = {"scatter_kernel_ms_per_step": sc_ms, "bytes_out_per_step": extra["exchange_bytes_per_step_rank0"],
+                               "gbs_out": extra["exchange_bytes_per_step_rank0"] / (sc_ms * 1e-3) / 1e9,
+                               "what": "k_build<StagedScatterSink<OPT>> by owner: extraction fused with stores into the owners' receive regions over NVLink peer mappings (rank 0, CUDA events)"}
     else:
         occ_total = st["occurrences"]
         nodes_total = st["count"]
@@ -358,21 +552,37 @@ def run_b200(args):
         for hb in (h_bases, h_offs, h_arr, h_nul):
             hb.close()
     else:
+        # ---- e2e at N>1: every rank's reads start in ITS pinned host memory; H2D, exchange, insert, cross-shard hand-off,
+        # ---- layout; every rank copies its slice into ONE shared host table image (a /dev/shm mapping = the KmerSet a
+        # ---- single consumer process would traverse); rank 0 fixes the shared nul_flag bytes and adds the k-mer-0 node.
+        try:
+            line["e2e"] = e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, st, rank, world, dev, dist, torch)
+        except Exception as e:
+            line["e2e"] = None
+            line["e2e_error"] = f"{type(e).__name__}: {e}"
         closer.close()
-        line["e2e"] = None
 
-    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    # ---- the other named single-GPU workloads, short (device-resident, 3 steps): C1 bundled-test shape, C3 K=63 ----
+    if world == 1 and rank == 0 and not args.no_other and args.scale == 1.0 and args.workload == "C2":
+        line["other_workloads"] = {}
+        for wname in ("C1", "C3"):
+            try:
+                line["other_workloads"][wname] = short_workload(args, wname, local, dev, torch, dbg, synth)
+            except Exception as e:
+                line["other_workloads"][wname] = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference on the WHOLE workload, all host threads, one build;
+    # ---- and with -t 1 ----
     if world == 1 and rank == 0 and not args.no_cpu:
         try:
             threads = os.cpu_count() or 1
             cfg1 = workload(args.workload, 1, args.scale)
-            sample = min(cfg1["n_reads"], args.ref_sample_reads)
-            vals, info = cpu_reference_run(cfg1, sample, threads, 1, 0, args.workload)
+            nr = cfg1["n_reads"] if args.ref_sample_reads <= 0 else min(cfg1["n_reads"], args.ref_sample_reads)
+            vals, info = cpu_reference_run(cfg1, nr, threads, 1, 0, args.workload)
             line["cpu_baseline"] = dict(info, value=float(np.mean(vals)), unit=UNIT)
-            if info["kind"] == "reference" and threads > 1:
-                # the reference with -t 1 beside the all-cores figure (same sample)
+            if info["kind"] == "reference" and threads > 1 and not args.no_cpu_t1:
                 try:
-                    vals1, _ = cpu_reference_run(cfg1, sample, 1, 1, 0, args.workload)
+                    vals1, _ = cpu_reference_run(cfg1, nr, 1, 1, 0, args.workload)
                     line["cpu_baseline"]["value_t1"] = float(np.mean(vals1))
                 except Exception as e1:
                     line["cpu_baseline"]["value_t1_error"] = str(e1)
@@ -398,10 +608,17 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; numbers at scale != 1 are not the metric)")
     ap.add_argument("--init-g", type=float, default=None, help="override the table size -i (experiments only)")
-    ap.add_argument("--ref-sample-reads", type=int, default=400_000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_sliced", "nccl"],
-                    help="multi-GPU: 'peer' = scatter kernel stores tuples into the owners' buffers over NVLink (fused), 'nccl' = pack + send/recv")
+    ap.add_argument("--ref-sample-reads", type=int, default=0,
+                    help="reference arm / cpu_baseline: 0 = the whole workload (default), N = only its first N reads (said so in the output)")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+                    help="reference arm: wall-clock budget; at least 1 warm-up and 2 timed full builds run, more while it lasts")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_exact", "peer_sliced", "nccl"],
+                    help="multi-GPU: 'peer' = ONE extraction pass stores tuples into fixed regions of the owners' buffers over NVLink, pipelined "
+                         "with the owners' inserts; 'peer_exact' = count pass + exact offsets + scatter; 'nccl' = pack + send/recv")
+    ap.add_argument("--sub-blocks", type=int, default=4, help="multi-GPU 'peer': sub-blocks per step (scatter k+1 overlaps insert k)")
+    ap.add_argument("--no-other", action="store_true", help="N=1: skip the short C1 / C3 lines (other_workloads)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu-t1", action="store_true", help="skip the -t 1 run of the reference in cpu_baseline")
     ap.add_argument("--no-micro", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and args.scale == 1.0:

@@ -5,7 +5,7 @@ Only the data-parallel hot path lives here: 2-bit encode +
 DBGgraph), the low-frequency link pass and the compacted dump -- as hand-written CUDA behind the C ABI of
 include/dbg_b200.h.  Everything computes on the GPU; there is no CPU fallback.
 """
-from .graph import DBGBuilder, KmerSet, build_debruijn_graph, read_reads_file, NODE16, NODE32  # noqa: F401
+from .graph import DBGBuilder, MultiGpuBuilder, KmerSet, build_debruijn_graph, read_reads_file, NODE16, NODE32  # noqa: F401
 from . import capi, synth  # noqa: F401
 
-__all__ = ["DBGBuilder", "KmerSet", "build_debruijn_graph", "read_reads_file", "capi", "synth", "NODE16", "NODE32"]
+__all__ = ["DBGBuilder", "MultiGpuBuilder", "KmerSet", "build_debruijn_graph", "read_reads_file", "capi", "synth", "NODE16", "NODE32"]

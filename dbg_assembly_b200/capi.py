@@ -56,6 +56,15 @@ class dbg_growth_result(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class dbg_checkpoint_header(C.Structure):
+    _fields_ = [("magic", C.c_uint64), ("version", C.c_uint32), ("K", C.c_uint32), ("wide", C.c_uint32), ("load_factor", C.c_float),
+                ("size", C.c_uint64), ("max_cutoff", C.c_uint64), ("count", C.c_uint64), ("count_conflict", C.c_uint64),
+                ("reads", C.c_uint64), ("kmers_logged", C.c_uint64), ("records", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class kfreq_params(C.Structure):
     _fields_ = [("K", C.c_int32), ("device", C.c_int32), ("block_rank", C.c_int32), ("block_count", C.c_int32),
                 ("reserved", C.c_int32 * 4)]
@@ -64,12 +73,16 @@ class kfreq_params(C.Structure):
 # every symbol include/dbg_b200.h declares; tests check that the library exports all of them
 SYMBOLS = [
     "dbg_find_next_prime", "dbg_hash_code", "dbg_hash_code_wide", "dbg_strerror", "dbg_last_error",
-    "dbg_device_count", "dbg_host_alloc", "dbg_host_free", "dbg_create", "dbg_destroy", "dbg_submit_reads",
+    "dbg_device_count", "dbg_host_alloc", "dbg_host_free", "dbg_host_register", "dbg_host_unregister", "dbg_create", "dbg_destroy", "dbg_submit_reads",
     "dbg_submit_reads_device", "dbg_extract_tuples_device", "dbg_insert_tuples_device", "dbg_tuple_bytes",
     "dbg_peer_alloc", "dbg_peer_open", "dbg_peer_close", "dbg_peer_free", "dbg_exchange_count_device", "dbg_exchange_scatter_device", "dbg_insert_sliced_device", "dbg_partition_info",
     "dbg_get_polyA_counts", "dbg_set_polyA_counts", "dbg_finalize", "dbg_get_stats", "dbg_export_kmerset",
     "dbg_export_links", "dbg_dump_compact", "dbg_dump_shard", "dbg_device_image", "dbg_get_timings", "dbg_launch_count", "dbg_path_counts", "dbg_replay_growth",
+    "dbg_exchange_scatter_opt_device", "dbg_exchange_scatter_undo", "dbg_insert_tuple_regions_device",
     "dbg_shard_tail_export", "dbg_shard_tail_import", "dbg_shard_slice_info", "dbg_export_shard_slice", "dbg_host_fix_nul_bytes", "dbg_host_polyA_insert",
+    "dbg_mg_create", "dbg_mg_destroy", "dbg_mg_submit_reads", "dbg_mg_finalize", "dbg_mg_get_stats", "dbg_mg_export_kmerset", "dbg_mg_dump_nodes",
+    "dbg_mg_info", "dbg_mg_last_error",
+    "dbg_checkpoint_write", "dbg_checkpoint_read_header", "dbg_checkpoint_read",
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
     "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
@@ -99,6 +112,8 @@ def load(build_if_missing: bool = True):
         "dbg_device_count": (C.c_int, []),
         "dbg_host_alloc": (C.c_int, [C.POINTER(vp), u64]),
         "dbg_host_free": (C.c_int, [vp]),
+        "dbg_host_register": (C.c_int, [vp, u64]),
+        "dbg_host_unregister": (C.c_int, [vp]),
         "dbg_create": (C.c_int, [C.POINTER(vp), C.POINTER(dbg_params)]),
         "dbg_destroy": (None, [vp]),
         "dbg_submit_reads": (C.c_int, [vp, vp, vp, u64]),
@@ -128,12 +143,27 @@ def load(build_if_missing: bool = True):
         "dbg_path_counts": (C.c_int, [vp, vp]),
         "dbg_replay_growth": (C.c_int, [C.POINTER(dbg_growth_params), vp, C.c_uint32, vp, vp, vp, vp, vp, u64, C.c_uint32, C.c_uint32,
                               C.POINTER(dbg_growth_result), vp, vp]),
+        "dbg_exchange_scatter_opt_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, i32, vp, u64, C.c_uint32, vp, vp]),
+        "dbg_insert_tuple_regions_device": (C.c_int, [vp, vp, C.c_uint32, u64, vp, vp]),
+        "dbg_exchange_scatter_undo": (C.c_int, [vp, vp]),
         "dbg_shard_tail_export": (C.c_int, [vp, vp, u64, C.POINTER(u64)]),
         "dbg_shard_tail_import": (C.c_int, [vp, vp, u64]),
         "dbg_shard_slice_info": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp)]),
         "dbg_export_shard_slice": (C.c_int, [vp, vp, vp, vp]),
         "dbg_host_fix_nul_bytes": (C.c_int, [vp, vp, u64, i32, vp, u64]),
         "dbg_host_polyA_insert": (C.c_int, [vp, vp, u64, i32, C.c_uint32, C.c_uint32, C.POINTER(u64)]),
+        "dbg_mg_create": (C.c_int, [C.POINTER(vp), C.POINTER(dbg_params), i32, vp]),
+        "dbg_mg_destroy": (None, [vp]),
+        "dbg_mg_submit_reads": (C.c_int, [vp, vp, vp, u64]),
+        "dbg_mg_finalize": (C.c_int, [vp, C.POINTER(dbg_stats)]),
+        "dbg_mg_get_stats": (C.c_int, [vp, C.POINTER(dbg_stats)]),
+        "dbg_mg_export_kmerset": (C.c_int, [vp, vp, vp]),
+        "dbg_mg_dump_nodes": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(u64)]),
+        "dbg_mg_info": (C.c_int, [vp, vp]),
+        "dbg_mg_last_error": (C.c_char_p, []),
+        "dbg_checkpoint_write": (C.c_int, [C.c_char_p, C.POINTER(dbg_checkpoint_header), vp, vp]),
+        "dbg_checkpoint_read_header": (C.c_int, [C.c_char_p, C.POINTER(dbg_checkpoint_header)]),
+        "dbg_checkpoint_read": (C.c_int, [C.c_char_p, vp, vp]),
         "dbg_reset": (C.c_int, [vp]),
         "dbg_set_stream": (C.c_int, [vp, vp]),
         "dbg_synth_reads_host": (C.c_int, [C.POINTER(dbg_synth_params), u64, u64, vp]),

@@ -94,6 +94,20 @@ extern "C" int dbg_host_alloc(void **p, uint64_t bytes)
     return DBG_OK;
 }
 
+// page-lock memory the caller allocated itself (e.g. a shared-memory table image several ranks export into)
+extern "C" int dbg_host_register(void *p, uint64_t bytes)
+{
+    if (!p) return set_err(DBG_ERR_INVALID, "dbg_host_register: NULL");
+    CU_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return DBG_OK;
+}
+
+extern "C" int dbg_host_unregister(void *p)
+{
+    if (p) CU_TRY(cudaHostUnregister(p));
+    return DBG_OK;
+}
+
 extern "C" int dbg_host_free(void *p)
 {
     if (p) CU_TRY(cudaFreeHost(p));
@@ -127,6 +141,8 @@ struct dbg_ctx {
     uint64_t tail_nodes_cap = 0;
     uint64_t tail_a_own = 0, tail_mt_own = 0, tail_a_in = 0;
     bool tail_exported = false, tail_imported = false, tail_moved = false;
+    uint64_t undo_reads = 0;       // reads counted by the last optimistic exchange scatter (dbg_exchange_scatter_undo)
+    uint64_t guard_total = 0;      // occurrences (upper bound) submitted to the inserts so far: sizes the long-probe budget
     int64_t nodes_delta = 0;       // nodes handed to / adopted from the neighbours (dump_shard counts what is physically here)
     u32 *d_nul_slice = nullptr;    // occupancy words of the laid-out slice (global word positions)
     uint64_t nul_slice_words = 0;
@@ -191,6 +207,7 @@ static TableView view_of(dbg_ctx *c)
     TableView t;
     t.nodes = c->d_nodes; t.P = c->P; t.M = c->M; t.lo = c->shard_lo; t.n_local = c->n_local;
     t.counters = c->d_counters; t.polyA = c->d_polyA;
+    t.guard_budget = (1ull << 20) + c->guard_total;
     return t;
 }
 
@@ -364,7 +381,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
     c->build_ev.clear();
     c->finalized = false; c->reads_total = 0; c->next_read_index = 0; c->polyA_links = 0;
     c->batch_reads = 0; c->batch_bases = 0; c->part_blocks = 0;
-    c->cnt_pending = false;
+    c->cnt_pending = false; c->guard_total = 0;
     c->tail_exported = c->tail_imported = c->tail_moved = false; c->tail_a_own = c->tail_mt_own = c->tail_a_in = 0; c->nodes_delta = 0;
     for (int i = 0; i < 4; i++) c->path_counts[i] = 0;
     c->links_cutoff = INT32_MIN;
@@ -644,6 +661,7 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
                         int n_parts, void *d_tuples, uint64_t bucket_stride, u64 *d_counts)
 {
     if (n_reads == 0 || total_bases == 0) return DBG_OK;
+    c->guard_total += total_bases;
     uint64_t abase = first_base & ~15ull;
     if (((uintptr_t)(d_bases + abase) & 15) != 0) return set_err(DBG_ERR_INVALID, "device base buffer must be 16-byte aligned");
     uint64_t n_chunks = (first_base + total_bases - abase + CB - 1) / CB;
@@ -990,8 +1008,10 @@ static int ensure_opt_buffers(dbg_ctx *c)
     return DBG_OK;
 }
 
+// the source tuples come as n_regions arrays: region r = counts[r] tuples at base + r * stride (tuples)
 template <bool WIDE>
-static int partition_tuples_optimistic(dbg_ctx *c, const void *d_src, uint64_t n, cudaStream_t s, uint32_t *capb_out)
+static int partition_tuples_optimistic(dbg_ctx *c, const void *d_base, uint32_t n_regions, uint64_t stride, const uint64_t *counts, cudaStream_t s,
+                                       uint32_t *capb_out)
 {
     const uint32_t nb = c->n_buckets;
     const size_t st_bytes = StageBuf<WIDE>::bytes(TP_TILE, nb);
@@ -1000,14 +1020,20 @@ static int partition_tuples_optimistic(dbg_ctx *c, const void *d_src, uint64_t n
         capb64 * nb >= (1ull << 32)) return 0;
     const uint32_t capb = (uint32_t)capb64;
     if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
-    const uint64_t n_rows = (n + TP_TILE - 1) / TP_TILE;
     CU_TRY(cudaMemsetAsync(c->d_fill, 0, ((size_t)nb + 1) * sizeof(u32), s));
     if (st_bytes > 48 * 1024)
         CU_TRY(cudaFuncSetAttribute(k_tuple_scatter_staged<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
-    k_tuple_scatter_staged<WIDE, true><<<(unsigned)n_rows, 256, st_bytes, s>>>((const u64 *)d_src, n, view_of(c), c->part_shift, nb, nullptr, c->d_tuples,
-                                                                               c->d_fill, capb, c->d_fill + nb);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
+    const size_t tw = WIDE ? 4 : 2;
+    for (uint32_t r = 0; r < n_regions; r++) {
+        const uint64_t n = counts[r];
+        if (n == 0) continue;
+        const uint64_t n_rows = (n + TP_TILE - 1) / TP_TILE;
+        const u64 *src = static_cast<const u64 *>(d_base) + (size_t)r * stride * tw;
+        k_tuple_scatter_staged<WIDE, true><<<(unsigned)n_rows, 256, st_bytes, s>>>(src, n, view_of(c), c->part_shift, nb, nullptr, c->d_tuples,
+                                                                                   c->d_fill, capb, c->d_fill + nb);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+    }
     CU_TRY(cudaMemcpyAsync(c->h_flag, c->d_fill + nb, sizeof(u32), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     if (*c->h_flag != 0) { c->path_counts[3]++; return 0; }
@@ -1024,6 +1050,7 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     if (!c || (!d_tuples && n)) return set_err(DBG_ERR_INVALID, "dbg_insert_tuples_device: NULL argument");
     if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
     if (n == 0) return DBG_OK;
+    c->guard_total += n;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     // enough tuples per table slice: put them in slice order first, then insert through L2-resident slices
@@ -1037,7 +1064,8 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     if (rc) return rc;
     if (part) {
         uint32_t capb = 0;
-        int opt = c->wide ? partition_tuples_optimistic<true>(c, d_tuples, n, s, &capb) : partition_tuples_optimistic<false>(c, d_tuples, n, s, &capb);
+        const uint64_t one[1] = {n};
+        int opt = c->wide ? partition_tuples_optimistic<true>(c, d_tuples, 1, 0, one, s, &capb) : partition_tuples_optimistic<false>(c, d_tuples, 1, 0, one, s, &capb);
         if (opt < 0) return opt;
         if (!opt) {
             c->path_counts[1]++;
@@ -1070,6 +1098,7 @@ extern "C" int dbg_insert_sliced_device(dbg_ctx *c, const void *d_tuples, uint64
     if (!c || (!d_tuples && n) || !d_slice_offs) return set_err(DBG_ERR_INVALID, "dbg_insert_sliced_device: NULL argument");
     if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
     if (n == 0) return DBG_OK;
+    c->guard_total += n;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     CU_TRY(cudaMemcpyAsync(c->d_boffs, d_slice_offs, ((size_t)c->n_buckets + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
@@ -1082,6 +1111,132 @@ extern "C" int dbg_insert_sliced_device(dbg_ctx *c, const void *d_tuples, uint64
     CU_TRY(cudaEventRecord(ev.b, s));
     c->build_ev.push_back(ev);
     c->part_blocks++;
+    return DBG_OK;
+}
+
+// ---- optimistic peer exchange: ONE extraction pass, no counting pass, no offsets exchanged beforehand -----------------
+// Every owner keeps a fixed region of `cap_pair` tuples for every source rank in its receive buffer.  The scatter pass of
+// the source (k_build<StagedScatterSink<OPT>> with owner buckets) sorts every 2048-tuple batch by owner in shared memory
+// and stores the runs straight into the owners' regions over NVLink peer mappings, reserving space with one atomicAdd per
+// owner and batch on its LOCAL counters d_fill[0..n_parts); d_fill[n_parts] is raised when a region would overflow (the
+// caller then redoes the block with the exact two-pass exchange: nothing of it has been inserted yet).
+extern "C" int dbg_exchange_scatter_opt_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                               uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
+                                               uint64_t region_off, uint32_t cap_pair, uint32_t *d_fill, void *stream)
+{
+    if (!c || !d_dst_ptrs || !d_fill) return set_err(DBG_ERR_INVALID, "dbg_exchange_scatter_opt_device: NULL argument");
+    if (n_parts < 1 || n_parts > 64) return set_err(DBG_ERR_INVALID, "n_parts outside 1..64");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemsetAsync(d_fill, 0, ((size_t)n_parts + 1) * sizeof(u32), s));
+    if (n_reads == 0 || total_bases == 0) return DBG_OK;
+    uint64_t abase = first_base & ~15ull;
+    if (((uintptr_t)(d_bases + abase) & 15) != 0) return set_err(DBG_ERR_INVALID, "device base buffer must be 16-byte aligned");
+    uint64_t n_chunks = (first_base + total_bases - abase + CB - 1) / CB;
+    if (n_chunks > 0x7fffffffull || total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
+    int rc = ensure_chunks(c, n_chunks);
+    if (rc) return rc;
+    const uint32_t cap0 = stage_cap(c, c->wide);
+    if (cap0 == 0) return set_err(DBG_ERR_STATE, "staged scatter disabled (DBG_B200_STAGE_CAP=0)");
+    // the scatter pass counts reads / occurrences / k-mer-0 lanes as it goes: keep what dbg_exchange_scatter_undo restores
+    if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
+    CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    c->undo_reads = n_reads;
+    EvPair ev;
+    rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    unsigned gb = (unsigned)((n_reads + 1 + 255) / 256);
+    k_chunk_first<<<gb, 256, 0, s>>>((const u64 *)d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    BuildArgs a;
+    a.bases = d_bases; a.offs = (const u64 *)d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
+    a.chunk_first = c->d_chunk_first; a.read_index0 = first_read_index; a.K = c->prm.K; a.R = c->prm.max_read_len;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
+    const uint64_t div = (c->P + n_parts - 1) / n_parts;
+    if (c->wide) {
+        StagedScatterSink<true, true> st; st.t = view_of(c); st.shift = 0; st.n_buckets = (uint32_t)n_parts; st.cap = cap0; st.matrix = nullptr; st.tuples = nullptr;
+        st.fill = d_fill; st.capb = cap_pair; st.flag = d_fill + n_parts; st.filled = 0;
+        st.div = div; st.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div); st.dst_ptrs = (u64 *const *)d_dst_ptrs; st.region_off = region_off;
+        rc = launch_build<true>(c, a, st, n_chunks, s, 0, StageBuf<true>::bytes(cap0, (uint32_t)n_parts));
+    } else {
+        StagedScatterSink<false, true> st; st.t = view_of(c); st.shift = 0; st.n_buckets = (uint32_t)n_parts; st.cap = cap0; st.matrix = nullptr; st.tuples = nullptr;
+        st.fill = d_fill; st.capb = cap_pair; st.flag = d_fill + n_parts; st.filled = 0;
+        st.div = div; st.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div); st.dst_ptrs = (u64 *const *)d_dst_ptrs; st.region_off = region_off;
+        rc = launch_build<false>(c, a, st, n_chunks, s, 0, StageBuf<false>::bytes(cap0, (uint32_t)n_parts));
+    }
+    if (rc) return rc;
+    c->reads_total += n_reads;
+    ev.slot = 7;                               // ms[7]: the fused scatter-into-peers kernel alone (NVLink figure of bench.py)
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+// an optimistic scatter overflowed: take back what it added to this context's side counters (reads, occurrences, k-mer-0
+// lanes), so that the exact exchange can redo the block
+extern "C" int dbg_exchange_scatter_undo(dbg_ctx *c, void *stream)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    if (!c->d_snap) return set_err(DBG_ERR_STATE, "no optimistic scatter to undo");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemcpyAsync(c->d_counters, c->d_snap, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->d_polyA, c->d_snap + CNT_N, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    c->reads_total -= c->undo_reads;
+    c->undo_reads = 0;
+    return DBG_OK;
+}
+
+// Owner side of the optimistic exchange: the receive buffer holds one region per source rank (region r = counts[r]
+// tuples at d_base + r * stride_tuples); all of them go through ONE optimistic slice partition and one bucketed insert.
+extern "C" int dbg_insert_tuple_regions_device(dbg_ctx *c, const void *d_base, uint32_t n_regions, uint64_t stride_tuples,
+                                               const uint64_t *counts, void *stream)
+{
+    if (!c || !d_base || !counts || n_regions == 0) return set_err(DBG_ERR_INVALID, "dbg_insert_tuple_regions_device: bad argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
+    uint64_t n = 0;
+    for (uint32_t r = 0; r < n_regions; r++) { if (counts[r] > stride_tuples) return set_err(DBG_ERR_INVALID, "region %u holds more than its stride", r); n += counts[r]; }
+    if (n == 0) return DBG_OK;
+    c->guard_total += n;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    bool part = want_partition(c, n) && c->optimistic;
+    const uint64_t want_cap = n + n / 8 + (uint64_t)c->n_buckets * INS_TILE;
+    if (part && ensure_tuples(c, want_cap) != DBG_OK) part = false;
+    EvPair ev;
+    int rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    int opt = 0;
+    uint32_t capb = 0;
+    if (part) {
+        opt = c->wide ? partition_tuples_optimistic<true>(c, d_base, n_regions, stride_tuples, counts, s, &capb)
+                      : partition_tuples_optimistic<false>(c, d_base, n_regions, stride_tuples, counts, s, &capb);
+        if (opt < 0) return opt;
+    }
+    if (opt) {
+        EvPair ei;
+        rc = ev_begin(c, s, &ei);
+        if (rc) return rc;
+        ei.slot = 6;
+        rc = insert_any(c, c->d_tuples, (uint64_t)capb * c->n_buckets, nullptr, s, true, c->d_fill);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(ei.b, s));
+        c->build_ev.push_back(ei);
+        c->part_blocks++;
+    } else {
+        // few tuples per table slice, or a slice region overflowed (skew): insert the regions as they are
+        const size_t tb = c->wide ? 32 : 16;
+        for (uint32_t r = 0; r < n_regions; r++) {
+            if (counts[r] == 0) continue;
+            rc = insert_any(c, static_cast<const char *>(d_base) + (size_t)r * stride_tuples * tb, counts[r], nullptr, s);
+            if (rc) return rc;
+        }
+        c->path_counts[0]++;
+    }
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
     return DBG_OK;
 }
 
@@ -1233,8 +1388,6 @@ static int run_layout(dbg_ctx *c)
 // sharded context: lay out this rank's window [imported tail | own range minus own tail] (dbg_shard_tail_export /
 // _import came first) into d_out (virtual slot order) and derive the occupancy words of the slice in global positions.
 // The k-mer-0 node is NOT placed here: it goes in last, on the merged table (dbg_host_polyA_insert).
-static uint64_t slice_first_word(const dbg_ctx *c, const LayoutGeom &g) { return ((g.gbase + g.v_begin) % c->P) / 32; }
-
 template <bool WIDE, bool TRACK>
 static int run_layout_sharded(dbg_ctx *c)
 {

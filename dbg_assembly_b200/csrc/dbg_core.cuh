@@ -43,9 +43,11 @@ struct TableView {
     u64 n_local;      // physical slots
     u64 *counters;    // [0] new nodes, [1] probe conflicts, [2] occurrences, [3] kmers_logged, [4] error flag, [5] reads
     u64 *polyA;       // 8 x u64 occurrence counts for the k-mer-0 side node: l lanes A,C,G,T then r lanes
+    u64 guard_budget; // long-probe budget of the build so far (insert_probe): 2^20 + occurrences submitted
 };
 
-enum { CNT_NEW = 0, CNT_CONFLICT = 1, CNT_OCC = 2, CNT_LOGGED = 3, CNT_ERROR = 4, CNT_READS = 5, CNT_N = 8 };
+// [6] k-mer-0 link words (k_polyA_insert), [7] tile counter of k_insert_tuples, [8] 1024-slot crossings of long probes
+enum { CNT_NEW = 0, CNT_CONFLICT = 1, CNT_OCC = 2, CNT_LOGGED = 3, CNT_ERROR = 4, CNT_READS = 5, CNT_GUARD = 8, CNT_N = 16 };
 
 // ---- hashing ----------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 hash_code(u64 kmer)
@@ -210,16 +212,16 @@ __device__ __forceinline__ void bump_counts(NodeT<WIDE> *p, u32 lanes, u32 lb, u
 }
 
 // the reference's link word from four half counts: lane of base b = bits (3-b)*8.., saturating at 255
+// (kmerSet.cpp:56,341).  Two packed-half instructions per pair of lanes: clamp to 255.0, add 1024.0 -- in
+// [1024, 2048) a half's ulp is 1, so the low byte of the sum IS the count -- then one byte permute gathers the four
+// counts with lane A on top.
 __device__ __forceinline__ u32 pack_link(u64 c)
 {
-    u32 w = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        float f = __half2float(__ushort_as_half((unsigned short)(c >> (16 * b))));
-        u32 v = (u32)f;
-        w |= (v > 255u ? 255u : v) << (24 - 8 * b);
-    }
-    return w;
+    const __half2 cap = __floats2half2_rn(255.f, 255.f), magic = __floats2half2_rn(1024.f, 1024.f);
+    u32 lo = (u32)c, hi = (u32)(c >> 32);                    // lo = lanes A,C ; hi = lanes G,T (16 bits each)
+    __half2 a = __hadd2(__hmin2(*reinterpret_cast<__half2 *>(&lo), cap), magic);
+    __half2 b = __hadd2(__hmin2(*reinterpret_cast<__half2 *>(&hi), cap), magic);
+    return __byte_perm(*reinterpret_cast<u32 *>(&a), *reinterpret_cast<u32 *>(&b), 0x0246);   // A<<24 | C<<16 | G<<8 | T
 }
 
 __device__ __forceinline__ bool cas128(void *addr, u64 new_lo, u64 new_hi, u64 &old_lo, u64 &old_hi)

@@ -33,9 +33,6 @@ constexpr int G = 4;           // consecutive occurrences per thread run (rollin
 #define DBG_MIN_CTAS 2
 #endif
 constexpr int MIN_CTAS = DBG_MIN_CTAS;    // register budget of the insert kernels: CTAs (x8 warps) per SM
-// longest probe sequence an insert follows before it gives up and raises CNT_ERROR: a table that is (nearly) full
-// must be reported promptly, not scanned slot by slot (the front end then rebuilds with a larger device table)
-constexpr u32 PROBE_CAP = 16384;
 constexpr u64 EMPTY_PRI = ~0ULL;
 constexpr u64 POLYA_PRI = ~0ULL - 1;
 
@@ -94,15 +91,29 @@ __device__ __forceinline__ void insert_one(const TableView &t, u64 klo, u64 khi,
     insert_probe<WIDE, TRACK>(t, p, n, klo, khi, lb, rb, ord, n_new, n_conf);
 }
 
+// Every 1024 slots of a long probe (free in the common case; out of line so that the hot loop pays no registers for
+// it): long probes draw on a budget of the whole build -- about 1024 probe steps per occurrence submitted so far, far
+// beyond what any table that still has room needs -- so a (nearly) full table is REPORTED within seconds instead of
+// being scanned slot by slot.  Raising the error also poisons the tile counter of k_insert_tuples (counters[7]).
+#ifndef DBG_GUARD
+#define DBG_GUARD 1      // 0: no guard (measurements only), 1: inline, 2: out of line
+#endif
+static __device__ __noinline__ bool probe_guard(u64 *counters, u64 budget)
+{
+    if (atomicAdd(counters + CNT_GUARD, 1ULL) >= budget || __ldcg(counters + CNT_ERROR)) {
+        atomicExch(counters + CNT_ERROR, 1ULL); atomicExch(counters + 7, 1ULL << 62);
+        return true;
+    }
+    return false;
+}
+
 // the probe loop, entered with the home slot's node already loaded (callers may have several loads in flight)
 template <bool WIDE, bool TRACK>
 __device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p, NodeRegs n, u64 klo, u64 khi, u32 lb, u32 rb, u64 ord,
                                              u32 &n_new, u32 &n_conf)
 {
     typedef NodeT<WIDE> Nd;
-    // the probe ends at the end of the shard (+ margin) or after PROBE_CAP slots, whichever comes first
-    Nd *p_end = static_cast<Nd *>(t.nodes) + t.n_local;
-    if (p_end - p > (long long)PROBE_CAP) p_end = p + PROBE_CAP;
+    Nd *const p_end = static_cast<Nd *>(t.nodes) + t.n_local;
     for (;;) {
         if ((n.klo | n.khi) == 0) {
             if (WIDE) {
@@ -128,7 +139,16 @@ __device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p,
         }
         n_conf++;                                       // occupied by another key: next slot (DBGgraph.cpp:201-204)
         p++;
-        if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); return; }
+        if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 62); return; }
+#if DBG_GUARD == 2
+        if ((reinterpret_cast<unsigned long long>(p) & (1024 * sizeof(Nd) - 1)) == 0 && probe_guard(t.counters, t.guard_budget)) return;
+#elif DBG_GUARD == 1
+        if ((reinterpret_cast<unsigned long long>(p) & (1024 * sizeof(Nd) - 1)) == 0) {
+            if (atomicAdd(t.counters + CNT_GUARD, 1ULL) >= t.guard_budget || __ldcg(t.counters + CNT_ERROR)) {
+                atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 62); return;
+            }
+        }
+#endif
         load_node(p, n);
     }
 }
@@ -295,8 +315,11 @@ struct StageBuf {
     // tuples and the batch reserves its run with one atomicAdd per touched bucket on fill[]; a bucket that would
     // overflow raises *flag and its tuples are dropped (the host then redoes the block with the exact two-pass
     // partition).
+    // dst_ptrs != nullptr (optimistic peer exchange): bucket b lives in its own buffer dst_ptrs[b] (the owner's receive
+    // buffer, over NVLink), and this source's region starts at tuple `region_off` of every one of them
     template <bool OPT = false>
-    __device__ __forceinline__ void flush(u64 *dst, u32 *fill = nullptr, u32 capb = 0, u32 *flag = nullptr)
+    __device__ __forceinline__ void flush(u64 *dst, u32 *fill = nullptr, u32 capb = 0, u32 *flag = nullptr, u64 *const *dst_ptrs = nullptr,
+                                          u64 region_off = 0)
     {
         const u32 t = threadIdx.x, nthr = blockDim.x;
         const u32 n = misc[0];
@@ -317,7 +340,7 @@ struct StageBuf {
                     for (int j = 0; j < 4; j++) {
                         const u32 b = c0 + j * nthr + t;
                         const u32 cnt = b < nb ? bh[b] : 0u;
-                        if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = b * capb + rr[j]; }
+                        if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = (dst_ptrs ? 0u : b * capb) + rr[j]; }
                     }
                 }
             }
@@ -340,7 +363,7 @@ struct StageBuf {
             for (int j = 0; j < 4; j++) {
                 const u32 b = j * nthr + t;
                 const u32 cnt = b < nb ? bh[b] : 0u;
-                if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = b * capb + rr[j]; }
+                if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = (dst_ptrs ? 0u : b * capb) + rr[j]; }
             }
         }
         __syncthreads();
@@ -349,8 +372,9 @@ struct StageBuf {
         for (u32 i = t; i < n; i += nthr) {
             const u32 e = idx[i], b = bk[e];
             if (OPT && base[b] == 0xffffffffu) continue;
-            const u64 pos = (u64)base[b] + (i - boff[b]);
+            const u64 pos = (u64)base[b] + (i - boff[b]) + region_off;
             const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(tup);
+            if (OPT && dst_ptrs) dst = dst_ptrs[b];
             if (WIDE) {
                 ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst) + 2 * pos;
                 __stcg(d, q[2 * e]);
@@ -388,6 +412,12 @@ struct StagedScatterSink {
     u32 *fill;         // OPT: tuples stored so far per bucket (global)
     u32 capb;          // OPT: region size per bucket
     u32 *flag;         // OPT: overflow
+    // optimistic PEER exchange (multi-GPU, OPT only): buckets = owner ranks (home / div), bucket b is stored into the
+    // owner's receive buffer dst_ptrs[b] over NVLink, inside the region [region_off, region_off + capb) that owner keeps
+    // for THIS source -- no counting pass, no offsets exchanged beforehand
+    u64 div = 0, div_M = 0;
+    u64 *const *dst_ptrs = nullptr;
+    u64 region_off = 0;
     StageBuf<WIDE> sb;
     u32 filled;
 
@@ -405,7 +435,7 @@ struct StagedScatterSink {
     {
         // `filled` is a block-uniform upper bound of the batch cursor kept in registers (never read the shared
         // cursor to decide: a fast warp may already have bumped it for this round)
-        if (filled + BLOCK * RUN > sb.cap) { __syncthreads(); sb.template flush<OPT>(tuples, fill, capb, flag); filled = 0; }
+        if (filled + BLOCK * RUN > sb.cap) { __syncthreads(); sb.template flush<OPT>(tuples, fill, capb, flag, dst_ptrs, region_off); filled = 0; }
         filled += BLOCK * RUN;
         u32 bkt[RUN];
         u32 mine = 0;
@@ -418,7 +448,9 @@ struct StagedScatterSink {
                     if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
-                    bkt[g] = (u32)((mod_P(hh, t.P, t.M) - t.lo) >> shift);
+                    const u64 home = mod_P(hh, t.P, t.M);
+                    if (OPT && div) { u32 b = (u32)__umul64hi(home, div_M); if ((u64)(b + 1) * div <= home) b++; bkt[g] = b; }
+                    else bkt[g] = (u32)((home - t.lo) >> shift);
                     mine++;
                 }
             }
@@ -439,7 +471,7 @@ struct StagedScatterSink {
     __device__ __forceinline__ void finish()
     {
         __syncthreads();
-        sb.template flush<OPT>(tuples, fill, capb, flag);
+        sb.template flush<OPT>(tuples, fill, capb, flag, dst_ptrs, region_off);
     }
 };
 
@@ -544,7 +576,7 @@ constexpr int PT_CHUNKS = 128;     // chunks per scan tile
 
 static __global__ void k_offsets_to_counts(const u64 *__restrict__ offs, u32 n, u64 *counts)
 {
-    u32 i = threadIdx.x;
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) counts[i] = offs[i + 1] - offs[i];
 }
 
@@ -874,15 +906,15 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
     // the bucket-ordered stream: the window of table slices they touch cannot drift apart (static round-robin
     // let fast CTAs run buckets ahead and the slices fell out of L2).  The counter is read one tile ahead (its
     // round trip hides behind the current tile) and published through a ping-pong slot: one barrier per tile.
+    // (a table already found full: nothing to do; a probe that finds it full poisons the tile counter, see insert_probe)
     u64 next_tile = 0;
-    if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? ~0ULL / INS_TILE : atomicAdd(tile_counter, 1ULL);
+    if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? (1ULL << 40) : atomicAdd(tile_counter, 1ULL);
     for (u32 par = 0;; par ^= 1) {
         if (threadIdx.x == 0) s_tile[par] = next_tile;
         __syncthreads();
         const u64 tile = s_tile[par] * INS_TILE;
         if (tile >= n) break;
-        // (a table found full ends the kernel at the next tile: nothing scans a full table slot by slot)
-        if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? ~0ULL / INS_TILE : atomicAdd(tile_counter, 1ULL);
+        if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
         if (boffs && tile >= b1 && b + 1 < n_buckets) {
             // entered a new bucket (rare path): its region, its tuple count, the prefetch ratio of the next slice
             while (b + 1 < n_buckets && tile >= b1) { b++; b0 = b1; b1 = __ldg(boffs + b + 1); }
@@ -1089,18 +1121,37 @@ __device__ __forceinline__ void cluster_bounds(const u32 *W, int k, bool prev_oc
     }
 }
 
+// index (0 .. LT+LH-1) of the i-th occupied slot of the window: chunk from the per-32 counts, then the n-th set bit
+__device__ __forceinline__ int nth_occupied(const u32 *W, const u32 *wcnt, u32 i)
+{
+    int c = 0;
+    u32 before = 0;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < LW; q++) {
+        const u32 n = wcnt[q];
+        if (!found && before + n <= i) { before += n; c = q + 1; } else found = true;
+    }
+    if (c >= LW) c = LW - 1;                                  // (not reached for i < n_occ)
+    return (c << 5) + (int)(__fns(W[c], 0, (int)(i - before) + 1) & 31u);
+}
+
 template <bool WIDE, bool TRACK>
 __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<WIDE> *__restrict__ nodes, LayoutGeom geo, void *out, u32 *nul32,
                                                         LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
 {
-    // the tile's nodes, loaded coalesced and digested in parallel: key, ordinal, packed link words, home slot;
-    // then EVERY occupied slot's thread replays its own key with priority probing (atomicMin on the ordinal) in
-    // shared memory -- the same algorithm as the global method, but on chip, per tile, with no idle lanes.
+    // One tile = LT slots (+ LH halo).  (1) every thread loads one node (coalesced 256-bit loads), the raw nodes go to
+    // shared memory, empty slots are written out at once; (2) the OCCUPIED slots are renumbered densely, so the
+    // expensive part -- hash -> home slot, cluster bounds, the replay with priority probing (atomicMin on the ordinal,
+    // the same algorithm as the global method, but on chip) -- runs on full warps instead of on the half-empty ones a
+    // table at load 0.5 gives; (3) each key finds its slot and the 16-B image node is written.
     // nul32 == nullptr (sharded windows): the occupancy bitmap is produced afterwards from the image (k_nul_from_image),
     // because a window's 32-slot groups are not aligned with the global bitmap words.
-    __shared__ u64 s_klo[LT + LH], s_khi[WIDE ? LT + LH : 1], s_ord[LT + LH], s_links[LT + LH], s_owner[LT + LH];
-    __shared__ u32 s_home[LT + LH];     // home - tile start (>= 0 for every cluster that starts in the tile)
-    __shared__ u32 s_W[LW];             // occupancy bitmap of the window
+    constexpr int NQ = WIDE ? 3 : 2;     // 16-byte quarters kept per node: {klo,nord|khi} [{nord,-}] {c0,c1}
+    __shared__ ulonglong2 s_raw[NQ * (LT + LH)];
+    __shared__ u64 s_ord[LT + LH], s_owner[LT + LH];
+    __shared__ u32 s_home[LT + LH];     // home - tile start (>= 0 for every cluster that starts in the tile); ~0: not replayed here
+    __shared__ u32 s_W[LW], s_wcnt[LW]; // occupancy bitmap of the window, occupied slots per 32
     __shared__ int s_prev;
     const u64 e_skip = info->e, g_skip = info->g;
     const u64 v_end = geo.v_end;
@@ -1112,25 +1163,30 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
             NodeRegs nd; nd.klo = 0; nd.khi = 0; nd.nord = 0; nd.c0 = 0; nd.c1 = 0;
             if (s < v_end) load_node(nodes + s, nd);
             const bool o = (nd.klo | nd.khi) != 0;
-            s_klo[k] = nd.klo; if (WIDE) s_khi[k] = nd.khi;
+            if (WIDE) { s_raw[3 * k] = make_ulonglong2(nd.klo, nd.khi); s_raw[3 * k + 1] = make_ulonglong2(nd.nord, 0ULL); s_raw[3 * k + 2] = make_ulonglong2(nd.c0, nd.c1); }
+            else { s_raw[2 * k] = make_ulonglong2(nd.klo, nd.nord); s_raw[2 * k + 1] = make_ulonglong2(nd.c0, nd.c1); }
             s_owner[k] = EMPTY_PRI;
-            if (o) {
-                s_home[k] = (u32)(home_virtual(geo, nd.klo, nd.khi, WIDE) - i0);
-                s_ord[k] = TRACK ? ~nd.nord : s;
-                s_links[k] = (u64)pack_link(nd.c0) | ((u64)pack_link(nd.c1) << 32);
-            }
             const u32 bal = __ballot_sync(0xffffffffu, o);
             if (lane == 0) {
-                s_W[k >> 5] = bal;
+                s_W[k >> 5] = bal; s_wcnt[k >> 5] = __popc(bal);
                 if (nul32 && k < LT && s < v_end) nul32[s >> 5] = __byte_perm(__brev(bal), 0, 0x0123);   // MSB-first bitmap word of 32 slots
             }
             if (k < LT && s < v_end && !o) write_image<WIDE>(out, s, 0, 0, 0);
         }
         if (t == 0) s_prev = (i0 > geo.v_begin) && slot_occupied<WIDE>(nodes, i0 - 1);
         __syncthreads();
-        bool mine[2] = {false, false};
-        for (int r = 0, k = t; k < LT + LH; k += LT, r++) {
-            if (!((s_W[k >> 5] >> (k & 31)) & 1u)) continue;
+        u32 n_occ = 0;
+#pragma unroll
+        for (int q = 0; q < LW; q++) n_occ += s_wcnt[q];
+        for (u32 i = t; i < n_occ; i += LT) {
+            const int k = nth_occupied(s_W, s_wcnt, i);
+            u64 klo, khi = 0, nord;
+            if (WIDE) { const ulonglong2 a = s_raw[3 * k]; klo = a.x; khi = a.y; nord = s_raw[3 * k + 1].x; }
+            else { const ulonglong2 a = s_raw[2 * k]; klo = a.x; nord = a.y; }
+            u64 cur = TRACK ? ~nord : i0 + k;
+            u32 pos = (u32)(home_virtual(geo, klo, khi, WIDE) - i0);
+            s_ord[k] = cur;
+            s_home[k] = 0xffffffffu;
             int start, end;
             cluster_bounds(s_W, k, s_prev != 0, start, end);
             if (start < 0 || start >= LT) continue;                   // belongs to the previous / next tile
@@ -1148,9 +1204,7 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
                 }
                 continue;
             }
-            mine[r] = true;
-            u64 cur = s_ord[k];
-            u32 pos = s_home[k];
+            s_home[k] = pos;
             for (;;) {
                 u64 old = atomicMin(&s_owner[pos], cur);
                 if (old == EMPTY_PRI) break;
@@ -1159,12 +1213,14 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
             }
         }
         __syncthreads();
-        for (int r = 0, k = t; k < LT + LH; k += LT, r++) {
-            if (!mine[r]) continue;
-            const u64 pri = s_ord[k];
+        for (u32 i = t; i < n_occ; i += LT) {
+            const int k = nth_occupied(s_W, s_wcnt, i);
             u32 pos = s_home[k];
+            if (pos == 0xffffffffu) continue;
+            const u64 pri = s_ord[k];
             while (s_owner[pos] != pri) pos++;
-            write_image<WIDE>(out, i0 + pos, s_klo[k], WIDE ? s_khi[k] : 0ULL, s_links[k]);
+            const ulonglong2 a = s_raw[NQ * k], cc = s_raw[NQ * k + NQ - 1];
+            write_image<WIDE>(out, i0 + pos, a.x, WIDE ? a.y : 0ULL, (u64)pack_link(cc.x) | ((u64)pack_link(cc.y) << 32));
         }
         __syncthreads();
     }

@@ -145,6 +145,20 @@ class DBGBuilder:
                                                       int(first_read_index), int(n_parts), int(bool(by_slice)), d_dst_ptrs_ptr,
                                                       d_dst_base_ptr, stream), "dbg_exchange_scatter_device")
 
+    def exchange_scatter_opt_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index, n_parts,
+                                    d_dst_ptrs_ptr, region_off, cap_pair, d_fill_ptr, stream=None):
+        capi.check(self.L.dbg_exchange_scatter_opt_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
+                                                          int(first_read_index), int(n_parts), d_dst_ptrs_ptr, int(region_off),
+                                                          int(cap_pair), d_fill_ptr, stream), "dbg_exchange_scatter_opt_device")
+
+    def exchange_scatter_undo(self, stream=None):
+        capi.check(self.L.dbg_exchange_scatter_undo(self.h, stream), "dbg_exchange_scatter_undo")
+
+    def insert_tuple_regions_device(self, d_base_ptr, stride_tuples, counts, stream=None):
+        a = np.ascontiguousarray(counts, dtype=np.uint64)
+        capi.check(self.L.dbg_insert_tuple_regions_device(self.h, d_base_ptr, len(a), int(stride_tuples), a.ctypes.data, stream),
+                   "dbg_insert_tuple_regions_device")
+
     def insert_sliced_device(self, d_tuples_ptr, n, d_slice_offs_ptr, stream=None):
         capi.check(self.L.dbg_insert_sliced_device(self.h, d_tuples_ptr, int(n), d_slice_offs_ptr, stream), "dbg_insert_sliced_device")
 
@@ -270,7 +284,7 @@ class DBGBuilder:
         ms = np.zeros(8, dtype=np.float32)
         capi.check(self.L.dbg_get_timings(self.h, ms.ctypes.data), "dbg_get_timings")
         return dict(clear_ms=float(ms[0]), build_ms=float(ms[1]), layout_ms=float(ms[2]), links_ms=float(ms[3]),
-                    h2d_ms=float(ms[4]), d2h_ms=float(ms[5]), insert_ms=float(ms[6]))
+                    h2d_ms=float(ms[4]), d2h_ms=float(ms[5]), insert_ms=float(ms[6]), scatter_ms=float(ms[7]))
 
     @property
     def launches(self):
@@ -281,6 +295,75 @@ class DBGBuilder:
         c = np.zeros(4, dtype=np.uint64)
         capi.check(self.L.dbg_path_counts(self.h, c.ctypes.data), "dbg_path_counts")
         return dict(direct=int(c[0]), exact=int(c[1]), optimistic=int(c[2]), overflows=int(c[3]))
+
+
+class MultiGpuBuilder:
+    """dbg_mg_*: ONE process driving several GPUs behind the calls of a single-GPU build (include/dbg_b200.h)."""
+
+    def __init__(self, n_gpus, K=31, max_read_len=250, init_slots=None, init_g=None, load_factor=0.7, devices=None, track_order=True,
+                 force_wide=False):
+        self.L = capi.load()
+        if init_slots is None:
+            init_slots = init_slots_from_g(1.0 if init_g is None else init_g)
+        p = capi.dbg_params()
+        p.K, p.max_read_len, p.init_slots = int(K), int(max_read_len), int(init_slots)
+        p.load_factor, p.track_order, p.force_wide = float(load_factor), int(bool(track_order)), int(bool(force_wide))
+        self.h = C.c_void_p()
+        dev = (C.c_int32 * n_gpus)(*devices) if devices is not None else None
+        rc = self.L.dbg_mg_create(C.byref(self.h), C.byref(p), int(n_gpus), dev)
+        if rc != capi.DBG_OK:
+            msg = self.L.dbg_mg_last_error().decode()
+            if self.h:
+                self.L.dbg_mg_destroy(self.h)
+                self.h = C.c_void_p()
+            raise capi.DbgError(rc, "dbg_mg_create", msg)
+        self.wide = int(K) > 31 or bool(force_wide)
+        self.stats = None
+
+    def _check(self, rc, where):
+        if rc != capi.DBG_OK:
+            raise capi.DbgError(rc, where, self.L.dbg_mg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dbg_mg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def submit(self, bases, offs):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = len(offs) - 1
+        if n > 0:
+            self._check(self.L.dbg_mg_submit_reads(self.h, bases.ctypes.data if bases.size else None, offs.ctypes.data, n), "dbg_mg_submit_reads")
+
+    def submit_ptr(self, bases_ptr, offs_ptr, n_reads):
+        self._check(self.L.dbg_mg_submit_reads(self.h, bases_ptr, offs_ptr, int(n_reads)), "dbg_mg_submit_reads")
+
+    def finalize(self):
+        st = capi.dbg_stats()
+        self._check(self.L.dbg_mg_finalize(self.h, C.byref(st)), "dbg_mg_finalize")
+        self.stats = st.as_dict()
+        return self.stats
+
+    def export_kmerset(self, array=None, nul_flag=None):
+        P = self.stats["array_size"]
+        if array is None:
+            array = np.zeros(P, dtype=NODE32 if self.wide else NODE16)
+        if nul_flag is None:
+            nul_flag = np.zeros(P // 8 + 1, dtype=np.uint8)
+        self._check(self.L.dbg_mg_export_kmerset(self.h, array.ctypes.data, nul_flag.ctypes.data), "dbg_mg_export_kmerset")
+        return array, nul_flag
+
+    def info(self):
+        a = np.zeros(4, dtype=np.uint64)
+        self._check(self.L.dbg_mg_info(self.h, a.ctypes.data), "dbg_mg_info")
+        return dict(rounds=int(a[0]), regrows=int(a[1]), fallback=bool(a[2]), cap_pair=int(a[3]))
 
 
 def replay_growth(nodes, reads_per_file, init_slots, load_factor=0.7, max_double_times=10, buffer_reads=10000,

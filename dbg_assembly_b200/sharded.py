@@ -95,7 +95,7 @@ class LocalShards:
     tests run on a single device, and what a single-process front end would run on several."""
 
     def __init__(self, n, K, max_read_len, init_slots, load_factor=0.7, devices=None, track_order=True, force_wide=False,
-                 by_slice=False):
+                 by_slice=False, optimistic=False, cap_pair=None):
         import torch
         from .graph import DBGBuilder
         self.n = n
@@ -107,15 +107,56 @@ class LocalShards:
         self.torch = torch
         self.P_request, self.load_factor = init_slots, load_factor
         self.blobs = None
+        self.optimistic, self.cap_pair = optimistic, cap_pair
+        self.overflows = 0
 
     def close(self):
         for b in self.b:
             b.close()
 
+    def _add_blocks_opt(self, blocks):
+        """one round of the OPTIMISTIC exchange: every source scatters straight into its region of every owner's buffer
+        (dbg_exchange_scatter_opt_device), the owners take the regions (dbg_insert_tuple_regions_device); a region that
+        would overflow makes the whole round fall back to the exact exchange (nothing was inserted yet)"""
+        torch, n = self.torch, self.n
+        biggest = max([blk[4] for blk in blocks if blk is not None] + [1])
+        cap_pair = self.cap_pair or int(biggest / n * 1.25) + 4096
+        recv = [torch.zeros(n * cap_pair * (self.tb // 8), dtype=torch.int64, device=torch.device("cuda", self.devices[q])) for q in range(n)]
+        fills = []
+        for r, blk in enumerate(blocks):
+            dev = torch.device("cuda", self.devices[r])
+            fill = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+            if blk is not None:
+                db, do, nr, fb, tbases, fri = blk
+                d_ptrs = torch.tensor([t.data_ptr() for t in recv], dtype=torch.int64, device=dev)
+                self.b[r].exchange_scatter_opt_device(db.data_ptr(), do.data_ptr(), nr, fb, tbases, fri, n, d_ptrs.data_ptr(), r * cap_pair,
+                                                      cap_pair, fill.data_ptr())
+                torch.cuda.synchronize(self.devices[r])
+            fills.append(fill.cpu())
+        allf = torch.stack(fills)                                       # [source][owner | flag]
+        if int(allf[:, n].sum()) != 0:
+            self.overflows += 1
+            for r, blk in enumerate(blocks):
+                if blk is not None:
+                    self.b[r].exchange_scatter_undo()
+                    torch.cuda.synchronize(self.devices[r])
+            return None
+        for q in range(n):
+            counts = allf[:, q].numpy().astype(np.uint64)
+            if counts.sum():
+                self.b[q].insert_tuple_regions_device(recv[q].data_ptr(), cap_pair, counts)
+                torch.cuda.synchronize(self.devices[q])
+        return allf[:, :n].sum(dim=0).tolist()
+
     def add_blocks(self, blocks):
         """blocks[r] = (d_bases tensor, d_offs tensor, n_reads, first_base, total_bases, first_read_index): the reads rank r
         contributes to this round (None = nothing).  One exchange round: count on every rank, offsets, scatter, insert."""
         torch, n = self.torch, self.n
+        if self.optimistic:
+            got = self._add_blocks_opt(blocks)
+            if got is not None:
+                return got
+            # a region would have overflowed (skewed input): the side counters were restored, redo the round exactly
         nbl = self.b[0].partition_info()[0] if self.by_slice else 1
         nbt = n * nbl
         counts = []
@@ -226,7 +267,7 @@ class ShardedBuilder:
     """The per-rank driver.  `reads` are this rank's own contiguous block of the global read sequence."""
 
     def __init__(self, K, max_read_len, init_slots, load_factor=0.7, device=0, track_order=True, group=None,
-                 slack=None, exchange="peer"):
+                 slack=None, exchange="peer", sub_blocks=4):
         from .graph import DBGBuilder
         self.ex = Exchange(group)
         self.n, self.rank = self.ex.world, self.ex.rank
@@ -236,9 +277,15 @@ class ShardedBuilder:
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
         self._send = self._counts = None
         self.exchange_bytes = 0
-        # "peer": the scatter pass stores tuples straight into the owners' receive buffers over NVLink peer
-        # mappings (exchange fused into the kernel); "nccl": pack locally, then grouped send/recv
+        # "peer" (default): OPTIMISTIC fused exchange -- one extraction pass stores tuples straight into fixed regions of
+        #     the owners' receive buffers over NVLink peer mappings, in sub-blocks, the scatter of sub-block k+1 overlapping
+        #     the owners' partition + insert of sub-block k; a region overflow (skew) redoes that sub-block exactly;
+        # "peer_exact": count pass + all-gathered exact offsets + scatter pass (no overlap);
+        # "peer_sliced": exact, (owner x slice) buckets;  "nccl": pack locally, then grouped send/recv
         self.exchange = exchange if self.n > 1 else "nccl"
+        self.sub_blocks = max(1, int(sub_blocks))
+        self.opt_fallbacks = 0
+        self._sA = self._sB = None
         self._recv_ptr = None
         self._recv_cap = 0
         self._peer_ptrs = None
@@ -277,6 +324,74 @@ class ShardedBuilder:
         self._peer_ptrs = [self._recv_ptr if q == self.rank else self.b.peer_open(handles[q]) for q in range(self.n)]
         self._d_ptrs = torch.tensor(self._peer_ptrs, dtype=torch.int64, device=self.device)
         dist.barrier(group=self.ex.group)
+
+    def _add_reads_peer_opt(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index):
+        """optimistic fused exchange, pipelined over sub-blocks (see __init__).  Streams: A = scatter + the small
+        all-gather of the fill counters (which doubles as the cross-rank barrier), B = owner-side partition + insert."""
+        n, dev, rank, S = self.n, self.device, self.rank, self.sub_blocks
+        tb = self.width * 8
+        if self._sA is None:
+            self._sA, self._sB = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        sA, sB = self._sA, self._sB
+        cur = torch.cuda.current_stream(dev)
+        S = max(1, min(S, n_reads))
+        cuts = [n_reads * k // S for k in range(S + 1)]
+        offs_h = d_offs[torch.tensor(cuts, device=dev)].cpu().tolist()
+        sub_bases = max(offs_h[k + 1] - offs_h[k] for k in range(S))
+        want = torch.tensor([int(sub_bases / n * 1.25) + 4096], dtype=torch.int64, device=dev)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=self.ex.group)
+        cap_pair = int(want.item())
+        self._ensure_peers(2 * n * cap_pair)
+        d_ptrs = self._d_ptrs
+        fills = [torch.zeros(n + 1, dtype=torch.int32, device=dev) for _ in range(S)]
+        allfill = [torch.empty(n * (n + 1), dtype=torch.int32, device=dev) for _ in range(S)]
+        sA.wait_stream(cur); sB.wait_stream(cur)
+
+        def scatter(k):
+            r0, r1 = cuts[k], cuts[k + 1]
+            with torch.cuda.stream(sA):
+                self.b.exchange_scatter_opt_device(d_bases.data_ptr(), d_offs.data_ptr() + 8 * r0, r1 - r0, offs_h[k], offs_h[k + 1] - offs_h[k],
+                                                   first_read_index + r0, n, d_ptrs.data_ptr(), ((k & 1) * n + rank) * cap_pair, cap_pair,
+                                                   fills[k].data_ptr(), stream=sA.cuda_stream)
+
+        def gather(k):
+            with torch.cuda.stream(sA):
+                dist.all_gather_into_tensor(allfill[k], fills[k], group=self.ex.group)
+                return allfill[k].view(n, n + 1).cpu()                 # host waits for A: scatter(k) everywhere, insert(k-1) here
+
+        recv_total = 0
+        scatter(0)
+        counts = gather(0)
+        for k in range(S):
+            overflow = bool(counts[:, n].any())
+            if k + 1 < S and not overflow:
+                scatter(k + 1)                                          # runs while the owners work on sub-block k
+            if overflow:
+                # some region was too small (skewed input): nothing of sub-block k was inserted; everybody redoes it exactly
+                self.opt_fallbacks += 1
+                self.b.exchange_scatter_undo(stream=sA.cuda_stream)
+                torch.cuda.synchronize(dev)
+                r0, r1 = cuts[k], cuts[k + 1]
+                with torch.cuda.stream(sB):
+                    recv_total += self._add_reads_peer(d_bases, d_offs[r0:], r1 - r0, offs_h[k], offs_h[k + 1] - offs_h[k], first_read_index + r0)
+                torch.cuda.synchronize(dev)
+                self._ensure_peers(2 * n * cap_pair)
+                d_ptrs = self._d_ptrs
+                if k + 1 < S:
+                    scatter(k + 1)
+            else:
+                mine = counts[:, rank].numpy().astype(np.uint64)
+                recv_total += int(mine.sum())
+                self.exchange_bytes += int(counts[rank, :n].sum() - counts[rank, rank]) * tb
+                # (the host has already waited for the all-gather of sub-block k: every rank's stores into this rank's
+                #  regions have landed; B must NOT wait for A here, scatter(k+1) is running there)
+                with torch.cuda.stream(sB):
+                    self.b.insert_tuple_regions_device(self._recv_ptr + (k & 1) * n * cap_pair * tb, cap_pair, mine, stream=sB.cuda_stream)
+            if k + 1 < S:
+                sA.wait_stream(sB)                                      # set (k+1)&1 ... is free again only after everybody's insert(k): gate the next barrier
+                counts = gather(k + 1)
+        cur.wait_stream(sA); cur.wait_stream(sB)
+        return recv_total
 
     def _add_reads_peer(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index):
         """fused exchange.  "peer": exchange buckets = owners; stores of one CTA go to n streams, so NVLink sees long
@@ -332,7 +447,9 @@ class ShardedBuilder:
                          first_read_index, n_occ_upper=None):
         """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
         total_bases bounds the tuple count)"""
-        if self.exchange in ("peer", "peer_sliced"):
+        if self.exchange == "peer":
+            return self._add_reads_peer_opt(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
+        if self.exchange in ("peer_exact", "peer_sliced"):
             return self._add_reads_peer(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
         from .graph import torch_stream_handle
         stream = torch_stream_handle(self.device)

@@ -88,6 +88,8 @@ int  dbg_device_count(void);                            /* 0 when no CUDA device
 /* pinned host memory for read buffers (front ends read/decode straight into it) */
 int  dbg_host_alloc(void **p, uint64_t bytes);
 int  dbg_host_free(void *p);
+int  dbg_host_register(void *p, uint64_t bytes);        /* page-lock caller-allocated memory (shared table image) */
+int  dbg_host_unregister(void *p);
 
 /* ---- life cycle ------------------------------------------------------------------------------- */
 /* init_kmerset_parallel + the globals of build_debruijn_graph (DBGgraph.cpp:371-402) */
@@ -140,6 +142,20 @@ int  dbg_exchange_scatter_device(dbg_ctx *ctx, const char *d_bases, const uint64
                                  uint64_t first_base, uint64_t total_bases, uint64_t first_read_index, int32_t n_parts,
                                  int32_t by_slice, void *const *d_dst_ptrs, const uint64_t *d_dst_base, void *stream);
 int  dbg_insert_sliced_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, const uint64_t *d_slice_offs, void *stream);
+/* OPTIMISTIC fused exchange (the default of the multi-GPU driver): ONE extraction pass.  Every owner keeps a fixed region
+ * of cap_pair tuples for every source rank in its receive buffer; the source's scatter pass sorts every 2048-tuple batch
+ * by owner in shared memory and stores the runs into its region of each owner's buffer over NVLink (d_dst_ptrs[q] = base
+ * of owner q's buffer, region_off = first tuple of this source's region inside it), reserving space with atomics on its
+ * LOCAL counters d_fill[0..n_parts).  d_fill[n_parts] != 0 afterwards: a region would have overflowed (skewed input) --
+ * nothing was inserted, redo the block with dbg_exchange_count/scatter_device.  The owners then take the regions with
+ * dbg_insert_tuple_regions_device (region r = counts[r] tuples at d_base + r * stride_tuples; counts are HOST values:
+ * the all-gathered d_fill). */
+int  dbg_exchange_scatter_opt_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                     uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
+                                     uint64_t region_off, uint32_t cap_pair, uint32_t *d_fill, void *stream);
+int  dbg_exchange_scatter_undo(dbg_ctx *ctx, void *stream);     /* after an overflow: restore the side counters of the scatter */
+int  dbg_insert_tuple_regions_device(dbg_ctx *ctx, const void *d_base, uint32_t n_regions, uint64_t stride_tuples,
+                                     const uint64_t *counts, void *stream);
 int  dbg_partition_info(const dbg_ctx *ctx, uint32_t *n_slices, int32_t *slice_shift);
 /* Insert n tuples (all owned by this context's shard) produced by dbg_extract_tuples_device. */
 int  dbg_insert_tuples_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, void *stream);
@@ -172,6 +188,27 @@ int  dbg_shard_slice_info(dbg_ctx *ctx, uint64_t *g_first, uint64_t *n_slots, vo
 int  dbg_export_shard_slice(dbg_ctx *ctx, void *array, uint8_t *nul_flag, uint64_t edge_slots[4]);
 int  dbg_host_fix_nul_bytes(const void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, const uint64_t *slots, uint64_t n);
 int  dbg_host_polyA_insert(void *array, uint8_t *nul_flag, uint64_t P, int32_t wide, uint32_t l_link, uint32_t r_link, uint64_t *slot_out);
+
+/* ---- ONE process, several GPUs: the same five calls a front end makes for one GPU ------------------------------------
+ * dbg_mg_* drives n sharded contexts (devices[r], NULL = 0..n-1; peer access is enabled between them) from one host
+ * process: reads of a block are dealt to the GPUs, exchanged with the optimistic fused scatter over NVLink, inserted by
+ * their owners; dbg_mg_finalize hands the boundary clusters around the ring and lays out every slice;
+ * dbg_mg_export_kmerset assembles the reference's KmerSet (kmerSet.h:88-99: array[P] + nul_flag, k-mer-0 node last) in
+ * the caller's memory -- what build_debruijn_graph hands to build_contig_sequence (main.cpp:204-207).  params->device,
+ * shard_rank and shard_count are ignored.  dbg_mg_dump_nodes lists every node with its first-occurrence ordinal (input
+ * of dbg_replay_growth, like dbg_dump_shard).  info = {exchange rounds, region regrows, dump-merge fallback used, region
+ * size in tuples}. */
+typedef struct dbg_mg dbg_mg;
+int  dbg_mg_create(dbg_mg **mg, const dbg_params *params, int32_t n_gpus, const int32_t *devices);
+void dbg_mg_destroy(dbg_mg *mg);
+int  dbg_mg_submit_reads(dbg_mg *mg, const char *bases, const uint64_t *offs, uint64_t n_reads);
+int  dbg_mg_finalize(dbg_mg *mg, dbg_stats *stats);
+int  dbg_mg_get_stats(dbg_mg *mg, dbg_stats *stats);
+int  dbg_mg_export_kmerset(dbg_mg *mg, void *array, uint8_t *nul_flag);
+int  dbg_mg_dump_nodes(dbg_mg *mg, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *l_link, uint32_t *r_link,
+                       uint64_t *first_ordinal, uint64_t *n);
+int  dbg_mg_info(const dbg_mg *mg, uint64_t info[4]);
+const char *dbg_mg_last_error(void);
 
 /* ---- results ---------------------------------------------------------------------------------- */
 /* Tail of build_debruijn_graph: waits for all blocks, builds the reference-layout image on the device
@@ -207,7 +244,8 @@ int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
 
 /* per-phase device time of the most recent calls, milliseconds (CUDA events on the ctx stream):
  * [0] table clear, [1] build kernels (sum over blocks), [2] layout+polyA (finalize), [3] links pass,
- * [4] H2D copies, [5] D2H export, [6] the bucketed insert kernel alone (partitioned path; part of [1]) */
+ * [4] H2D copies, [5] D2H export, [6] the bucketed insert kernel alone (partitioned path; part of [1]),
+ * [7] the scatter kernel of the optimistic peer exchange alone (multi-GPU) */
 int  dbg_get_timings(dbg_ctx *ctx, float ms[8]);
 /* number of kernel launches issued by this context so far */
 uint64_t dbg_launch_count(const dbg_ctx *ctx);
@@ -262,6 +300,19 @@ int  dbg_replay_growth(const dbg_growth_params *g, const uint64_t *reads_per_fil
                        const uint64_t *kmer_lo, const uint64_t *kmer_hi, const uint32_t *l_link, const uint32_t *r_link,
                        const uint64_t *first_ordinal, uint64_t n_nodes, uint32_t polyA_l, uint32_t polyA_r,
                        dbg_growth_result *res, void *array, uint8_t *nul_flag);
+
+/* ---- on-disk checkpoint of the finished graph (host code, plain file I/O) --------------------------
+ * The KmerSet build_debruijn_graph hands to the traversal (kmerSet.h:88-99), stored as its filled slots in slot order
+ * {slot, kmer[, kmer_hi], l_link, r_link} + a checksum: a front end can re-run the traversal with other cut-offs without
+ * reading the reads again (integration/DBGgraph_b200.cpp: DBG_B200_CHECKPOINT=<file>).  magic / version / records are
+ * filled in by the writer. */
+typedef struct {
+    uint64_t magic; uint32_t version; uint32_t K; uint32_t wide; float load_factor;
+    uint64_t size, max_cutoff, count, count_conflict, reads, kmers_logged, records;
+} dbg_checkpoint_header;
+int  dbg_checkpoint_write(const char *path, const dbg_checkpoint_header *hdr, const void *array, const uint8_t *nul_flag);
+int  dbg_checkpoint_read_header(const char *path, dbg_checkpoint_header *hdr);
+int  dbg_checkpoint_read(const char *path, void *array, uint8_t *nul_flag);
 
 /* ---- K-mer frequency table for correct_error ---------------------------------
  * What the external `kmerfreq` program writes and correct_error loads (correct_error/main_parallel_senior.cpp:

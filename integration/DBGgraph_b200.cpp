@@ -57,6 +57,10 @@ KmerNode *PolyA;
 clock_t time_start;
 clock_t time_end;
 
+// The context outlives build_debruijn_graph() when the table the traversal got IS the device image (no growth replay):
+// calculate_kmer_links (below) then takes the link pass from the GPU instead of scanning P slots.
+static dbg_ctx *g_links_ctx = NULL;
+
 static void die(const char *where, int rc)
 {
     cerr << "libdbgb200: " << where << " failed: " << dbg_strerror(rc) << " -- " << dbg_last_error() << endl;
@@ -71,10 +75,25 @@ static const uint64_t BLOCK_BASES = 128ull << 20;
 static const uint64_t BLOCK_READS = 2ull << 20;
 static const size_t MAX_AHEAD = 4;          // files being decoded at the same time
 
+// The build runs on one GPU (dbg_*) or, with DBG_B200_GPUS=n in the environment (DBG_B200_DEVICES=0,1,... picks them), on
+// several from this one process (dbg_mg_*: reads dealt to the GPUs, k-mers exchanged over NVLink by owner slot range, the
+// table slices merged back into the one KmerSet the traversal consumes).  Same calls, same results.
+struct Build {
+    dbg_ctx *one = NULL;
+    dbg_mg *many = NULL;
+    int submit(const char *bases, const uint64_t *offs, uint64_t n) { return many ? dbg_mg_submit_reads(many, bases, offs, n) : dbg_submit_reads(one, bases, offs, n); }
+    int get_stats(dbg_stats *st) { return many ? dbg_mg_get_stats(many, st) : dbg_get_stats(one, st); }
+    int finalize(dbg_stats *st) { return many ? dbg_mg_finalize(many, st) : dbg_finalize(one, st); }
+    int dump(uint64_t *k, uint32_t *l, uint32_t *r, uint64_t *o, uint64_t *n) { return many ? dbg_mg_dump_nodes(many, k, NULL, l, r, o, n) : dbg_dump_shard(one, k, NULL, l, r, o, n); }
+    int export_kmerset(void *array, uint8_t *nul) { return many ? dbg_mg_export_kmerset(many, array, nul) : dbg_export_kmerset(one, array, nul); }
+    void destroy() { if (many) dbg_mg_destroy(many); if (one) dbg_destroy(one); many = NULL; one = NULL; }
+    const char *err() { return many && dbg_mg_last_error()[0] ? dbg_mg_last_error() : dbg_last_error(); }
+};
+
 // returns false when the device table turned out to be too small for the input (the caller rebuilds with a larger one).
 // `limit`: use at most this many reads of the file (the reference stops reading a file when -e is exhausted,
 // DBGgraph.cpp:346-350); UINT64_MAX = the whole file.  *cut is set when reads were left unread.
-static bool consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod, bool quiet, uint64_t limit, bool *cut)
+static bool consume_file(Build &ctx, dbgio::FileProducer &prod, bool quiet, uint64_t limit, bool *cut)
 {
     uint64_t in_block = 0, taken = 0;
     bool full = false, stop = false;
@@ -86,9 +105,9 @@ static bool consume_file(dbg_ctx *ctx, dbgio::FileProducer &prod, bool quiet, ui
         uint64_t use = b->n_reads;
         if (taken + use >= limit) { if (taken + use > limit || !b->last) *cut = true; use = limit - taken; stop = true; }
         if (use) {
-            int rc = dbg_submit_reads(ctx, b->bases, b->offs, use);
+            int rc = ctx.submit(b->bases, b->offs, use);
             if (rc == DBG_ERR_TABLE_FULL) full = true;
-            else if (rc) die("dbg_submit_reads", rc);
+            else if (rc) { cerr << ctx.err() << endl; die("dbg_submit_reads", rc); }
         }
         taken += use;
         if (full) { prod.recycle(b); return false; }      // the producer is cancelled by its owner
@@ -132,15 +151,15 @@ struct GrowthInput {
     uint64_t n = 0;
 };
 
-static void fetch_nodes(dbg_ctx *ctx, GrowthInput &g)
+static void fetch_nodes(Build &ctx, GrowthInput &g)
 {
     int rc;
     uint64_t n = 0;
-    if ((rc = dbg_dump_shard(ctx, NULL, NULL, NULL, NULL, NULL, &n))) die("dbg_dump_shard", rc);
+    if ((rc = ctx.dump(NULL, NULL, NULL, NULL, &n))) die("dbg_dump_shard", rc);
     g.kmer.resize(n + 1); g.ord.resize(n + 1); g.l.resize(n + 1); g.r.resize(n + 1);
     uint64_t cap = n + 1;
-    if ((rc = dbg_dump_shard(ctx, g.kmer.data(), NULL, g.l.data(), g.r.data(), g.ord.data(), &cap))) die("dbg_dump_shard", rc);
-    g.n = n;
+    if ((rc = ctx.dump(g.kmer.data(), g.l.data(), g.r.data(), g.ord.data(), &cap))) die("dbg_dump_shard", rc);
+    g.n = cap;
 }
 
 static void replay(const GrowthInput &g, uint64_t ref_init_slots, const std::vector<uint64_t> &reads_per_file, const dbg_stats &st,
@@ -153,6 +172,39 @@ static void replay(const GrowthInput &g, uint64_t ref_init_slots, const std::vec
     int rc = dbg_replay_growth(&gp, reads_per_file.data(), (uint32_t)reads_per_file.size(), g.kmer.data(), NULL, g.l.data(), g.r.data(),
                                g.ord.data(), g.n, (uint32_t)st.polyA_l, (uint32_t)st.polyA_r, grow, array, nul_flag);
     if (rc) die("dbg_replay_growth", rc);
+}
+
+// DBG_B200_CHECKPOINT=<file>: the finished KmerSet is kept on disk (dbg_checkpoint_write); a later run with the same -k
+// finds it and goes straight to the traversal -- other cut-offs (-D -T -I -P -W -C -G -B -U -L -E -M) without reading
+// the reads again.  The reference has no such restart point.
+static bool load_checkpoint(const char *path)
+{
+    dbg_checkpoint_header h;
+    if (dbg_checkpoint_read_header(path, &h) != DBG_OK) return false;
+    if ((int)h.K != KmerSize || h.wide) { cerr << "libdbgb200: checkpoint " << path << " was built with -k " << h.K << ": ignored" << endl; return false; }
+    kset = new KmerSet;
+    kset->e_size = sizeof(KmerNode);
+    kset->size = h.size; kset->count = h.count; kset->count_conflict = h.count_conflict; kset->load_factor = h.load_factor;
+    kset->max = h.max_cutoff; kset->iter_ptr = 0;
+    kset->array = (KmerNode *)malloc((kset->size + 1) * kset->e_size);
+    kset->nul_flag = (uint8_t *)malloc(kset->size / 8 + 1);
+    kset->del_flag = (uint8_t *)calloc(kset->size / 8 + 1, 1);
+    if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
+    memset(kset->array + kset->size, 0, sizeof(KmerNode));
+    if (dbg_checkpoint_read(path, kset->array, kset->nul_flag) != DBG_OK) { cerr << "libdbgb200: checkpoint " << path << " is damaged: rebuilding" << endl; return false; }
+    Total_reads_num = h.reads; Kmer_total_num = h.kmers_logged;
+    cerr << "libdbgb200: graph of " << h.count << " nodes loaded from checkpoint " << path << " (no reads were parsed)" << endl;
+    return true;
+}
+
+static void save_checkpoint(const char *path)
+{
+    dbg_checkpoint_header h;
+    memset(&h, 0, sizeof(h));
+    h.K = (uint32_t)KmerSize; h.wide = 0; h.load_factor = kset->load_factor; h.size = kset->size; h.max_cutoff = kset->max; h.count = kset->count;
+    h.count_conflict = kset->count_conflict; h.reads = Total_reads_num; h.kmers_logged = Kmer_total_num;
+    if (dbg_checkpoint_write(path, &h, kset->array, kset->nul_flag) != DBG_OK) cerr << "libdbgb200: WARNING: could not write checkpoint " << path << endl;
+    else cerr << "libdbgb200: checkpoint written to " << path << endl;
 }
 
 void build_debruijn_graph(vector<string> &reads_files)
@@ -169,6 +221,9 @@ void build_debruijn_graph(vector<string> &reads_files)
     KmerNumInRead = maxReadLen - KmerSize + 1;
 
     if (KmerSize > 31) { cerr << "debruijn_contig: -k max 31 for the 64-bit host traversal" << endl; exit(1); }
+
+    const char *ckpt = getenv("DBG_B200_CHECKPOINT");
+    if (ckpt && *ckpt && load_checkpoint(ckpt)) { print_kmerset_parameter(kset); return; }
 
     cerr << "Start to initialize the kmerset hash" << endl;
     dbg_params prm;
@@ -201,7 +256,16 @@ void build_debruijn_graph(vector<string> &reads_files)
     // The same loop reproduces "-e exhausted" (DBGgraph.cpp:346-350: the reference stops reading the current file, and
     // every later file after its first block): the replay of the full build tells where the reference stopped, and the
     // build is redone on exactly the reads the reference used (`limits`).
-    dbg_ctx *ctx = NULL;
+    Build ctx;
+    int n_gpus = getenv("DBG_B200_GPUS") ? atoi(getenv("DBG_B200_GPUS")) : 1;
+    std::vector<int32_t> gpu_list;
+    if (const char *e = getenv("DBG_B200_DEVICES")) {
+        for (const char *q = e; *q;) { gpu_list.push_back((int32_t)strtol(q, (char **)&q, 10)); if (*q == ',') q++; else break; }
+        if (!getenv("DBG_B200_GPUS")) n_gpus = (int)gpu_list.size();
+    }
+    if (n_gpus < 1) n_gpus = 1;
+    if (!gpu_list.empty() && (int)gpu_list.size() != n_gpus) { cerr << "libdbgb200: DBG_B200_DEVICES lists " << gpu_list.size() << " devices, DBG_B200_GPUS=" << n_gpus << endl; exit(1); }
+    if (n_gpus > 1) cerr << "libdbgb200: building on " << n_gpus << " GPUs" << endl;
     int rc = 0;
     dbg_stats st;
     std::vector<uint64_t> reads_per_file, limits;
@@ -209,7 +273,8 @@ void build_debruijn_graph(vector<string> &reads_files)
     GrowthInput gin;
     double w1 = 0, w2 = 0;
     for (int attempt = 0;; attempt++) {
-        rc = dbg_create(&ctx, &prm);
+        if (n_gpus > 1) { rc = dbg_mg_create(&ctx.many, &prm, n_gpus, gpu_list.empty() ? NULL : gpu_list.data()); if (rc) cerr << dbg_mg_last_error() << endl; }
+        else rc = dbg_create(&ctx.one, &prm);
         if (rc) die("dbg_create", rc);
         if (attempt == 0) {
             time_end = clock();
@@ -241,7 +306,7 @@ void build_debruijn_graph(vector<string> &reads_files)
                 }
                 prod[i].reset();
                 if (fits) {
-                    rc = dbg_get_stats(ctx, &st);
+                    rc = ctx.get_stats(&st);
                     if (rc == DBG_ERR_TABLE_FULL) fits = false;
                     else if (rc) die("dbg_get_stats", rc);
                 }
@@ -257,13 +322,12 @@ void build_debruijn_graph(vector<string> &reads_files)
         // add polyA and polyT [kmer: 0] to the kmerset (DBGgraph.cpp:418) happens inside dbg_finalize
         w2 = wall_now();
         if (fits) {
-            rc = dbg_finalize(ctx, &st);
+            rc = ctx.finalize(&st);
             if (rc == DBG_ERR_TABLE_FULL) fits = false;
-            else if (rc) die("dbg_finalize", rc);
+            else if (rc) { cerr << ctx.err() << endl; die("dbg_finalize", rc); }
         }
         if (!fits) {
-            dbg_destroy(ctx);
-            ctx = NULL;
+            ctx.destroy();
             if (attempt >= 24) { cerr << "libdbgb200: the input does not fit a device table of " << prm.init_slots << " slots" << endl; exit(1); }
             prm.init_slots = prm.init_slots < 1024 ? 2048 : prm.init_slots * 2;
             cerr << "libdbgb200: -i " << initHashSize << " cannot hold this input; rebuilding with a device table of " << prm.init_slots
@@ -292,8 +356,7 @@ void build_debruijn_graph(vector<string> &reads_files)
                 }
                 cerr << "\nlibdbgb200: -e " << maxDoubleHashTimes << " is exhausted inside file " << grow.truncated_file
                      << ": the CPU program ignores the rest of it; rebuilding on exactly the reads it used" << endl;
-                dbg_destroy(ctx);
-                ctx = NULL;
+                ctx.destroy();
                 prm.init_slots = ref_init_slots;       // the reduced read set starts over from the reference's -i
                 continue;
             }
@@ -335,12 +398,59 @@ void build_debruijn_graph(vector<string> &reads_files)
     if (!kset->array || !kset->nul_flag || !kset->del_flag) { cerr << "out of host memory for the kmerset" << endl; exit(1); }
     const double w3 = wall_now();
     if (grown) replay(gin, ref_init_slots, reads_per_file, st, &grow, kset->array, kset->nul_flag);
-    else if ((rc = dbg_export_kmerset(ctx, kset->array, kset->nul_flag))) die("dbg_export_kmerset", rc);
+    else if ((rc = ctx.export_kmerset(kset->array, kset->nul_flag))) { cerr << ctx.err() << endl; die("dbg_export_kmerset", rc); }
     const double w4 = wall_now();
+    if (ckpt && *ckpt) save_checkpoint(ckpt);
     cerr << "libdbgb200 wall clock (s): init " << w1 - w0 << ", read files + submit " << w2 - w1 << ", finalize (GPU build + layout) "
          << w3 - w2 << ", export kmerset " << w4 - w3 << endl;
 
-    dbg_destroy(ctx);
+#ifdef DBG_B200_GPU_LINKS
+    if (!grown && ctx.one && !getenv("DBG_B200_CPU_LINKS")) { g_links_ctx = ctx.one; ctx.one = NULL; }   // calculate_kmer_links() below finishes with it
+#endif
+    ctx.destroy();
 
     print_kmerset_parameter(kset);
 }
+
+#ifdef DBG_B200_GPU_LINKS
+// ---- first pass of the traversal on the GPU (contig.cpp:107-205) ----------------------------------------------------
+// Compiled in when the build recipe (oracle/Makefile, target b200) renamed contig.cpp's own calculate_kmer_links to
+// calculate_kmer_links_cpu in a generated copy: build_contig_sequence() (contig.cpp:62) then calls THIS function.  klink,
+// del_flag, the depth histogram and the slot-ordered tip / branch lists come from dbg_export_links (k_links_classify +
+// ordered compaction on the table image that is still resident on the device) instead of a host scan over P slots; the
+// .contig.kmer.freq file and the log lines are written exactly like the original.  When the table was laid out by the
+// host-side growth replay the device image is not the table the traversal holds: the original runs.
+#include "contig.h"
+#include <fstream>
+void calculate_kmer_links_cpu(KmerSet *kset, KmerLink *klink, vector<uint64_t> &tip_nodes, vector<uint64_t> &branch_nodes);
+
+void calculate_kmer_links(KmerSet *kset, KmerLink *klink, vector<uint64_t> &tip_nodes, vector<uint64_t> &branch_nodes)
+{
+    if (!g_links_ctx) { calculate_kmer_links_cpu(kset, klink, tip_nodes, branch_nodes); return; }
+    static_assert(sizeof(KmerLink) == 2, "KmerLink is the 2-byte bit-field struct of contig.h:31-42");
+    int64_t DepthStat[256], stats3[3] = {0, 0, 0};
+    uint64_t nt = 0, nb = 0;
+    int rc = dbg_export_links(g_links_ctx, KmerFreqCutoff, (uint8_t *)klink, kset->del_flag, DepthStat, NULL, &nt, NULL, &nb, stats3);
+    if (rc) die("dbg_export_links", rc);
+    tip_nodes.resize(nt); branch_nodes.resize(nb);
+    uint64_t ct = nt ? nt : 1, cb = nb ? nb : 1;
+    uint64_t dummy = 0;
+    rc = dbg_export_links(g_links_ctx, KmerFreqCutoff, NULL, NULL, NULL, nt ? tip_nodes.data() : &dummy, &ct, nb ? branch_nodes.data() : &dummy, &cb, NULL);
+    if (rc) die("dbg_export_links (lists)", rc);
+    dbg_destroy(g_links_ctx);
+    g_links_ctx = NULL;
+    const int64_t total_kmer_speceis_num = stats3[0], deleted_lowFreq_kmer_num = stats3[1], linear_kmer_node_num = stats3[2];
+
+    string kmer_depth_file = Output_prefix + ".contig.kmer.freq";                       // contig.cpp:186-203
+    ofstream depthFile(kmer_depth_file.c_str());
+    if (!depthFile) cerr << "fail to open file " << kmer_depth_file << endl;
+    cerr << "\nTotal kmer nodes number:    " << total_kmer_speceis_num << endl;
+    cerr << "Deleted lowfreq kmer nodes: " << deleted_lowFreq_kmer_num << "\t" << (double)deleted_lowFreq_kmer_num / total_kmer_speceis_num << endl;
+    cerr << "Used linear kmer nodes:     " << linear_kmer_node_num << "\t" << (double)linear_kmer_node_num / total_kmer_speceis_num << endl;
+    cerr << "Used tip kmer nodes:        " << tip_nodes.size() << "\t" << (double)tip_nodes.size() / total_kmer_speceis_num << endl;
+    cerr << "Used branching kmer nodes:  " << branch_nodes.size() << "\t" << (double)branch_nodes.size() / total_kmer_speceis_num << endl;
+    depthFile << "Kmer_depth\tAppear_times\n";
+    for (int i = 1; i <= 255; i++) depthFile << i << "\t" << DepthStat[i] << endl;
+    depthFile.close();
+}
+#endif

@@ -124,3 +124,26 @@ def test_front_end_gzip_fastq_input(mock_front_end, oracle_mod, tmp_path):
         outs[tag] = {s: open(pre + s, "rb").read() for s in SUF}
         assert "Total number of reads loaded into memory: 2500" in r.stderr.decode()
     assert outs["ref"] == outs["b200"] and len(outs["ref"][".contig.seq.fa"]) > 1000
+
+
+def test_front_end_checkpoint_restart(mock_front_end, reads_lib, tmp_path):
+    """DBG_B200_CHECKPOINT: the first run writes the finished KmerSet, the second one loads it, parses no reads, and still
+    writes the reference's files -- also with another traversal cut-off (-D), where it must equal the reference run with
+    that cut-off"""
+    ck = str(tmp_path / "graph.ckpt")
+    env = dict(os.environ, DBG_B200_CHECKPOINT=ck)
+    extra = ["-i", "0.0005"]
+
+    def run_env(pre, more, e):
+        r = subprocess.run([mock_front_end, "-k", "25", "-r", "100", "-f", "2", "-t", "1", "-M", "100", "-o", pre, reads_lib] + extra + more,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120, env=e)
+        return r.returncode, {s: open(pre + s, "rb").read() for s in SUF if os.path.exists(pre + s)}, r.stderr.decode()
+    rc1, f1, log1 = run_env(str(tmp_path / "a"), [], env)
+    assert rc1 == 0 and "checkpoint written" in log1 and os.path.getsize(ck) > 1000
+    rc2, f2, log2 = run_env(str(tmp_path / "b"), [], env)
+    assert rc2 == 0 and "loaded from checkpoint" in log2 and "Start to parse reads file" not in log2
+    assert f1 == f2 and len(f1) == len(SUF)
+    rc3, f3, log3 = run_env(str(tmp_path / "c"), ["-D", "4"], env)
+    rc_r, f_r, _ = run(REF_BIN, reads_lib, str(tmp_path / "ref"), extra + ["-D", "4"])
+    assert rc3 == 0 and rc_r == 0 and "loaded from checkpoint" in log3
+    assert f3 == f_r and f3 != f1

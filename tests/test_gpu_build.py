@@ -324,8 +324,8 @@ def test_table_full_is_reported_not_hung(dbg):
     reads = random_reads(61, 3000, 100, 150, genome_len=100000, err=0.05)
     bases, offs = reads_to_arrays(reads)
     with dbg.DBGBuilder(K=31, max_read_len=150, init_slots=5000) as b:   # ~3e5 distinct k-mers into 5003 slots (+margin)
-        b.submit(bases, offs)
-        with pytest.raises(dbg.capi.DbgError) as ei:
+        with pytest.raises(dbg.capi.DbgError) as ei:      # reported by the submit that follows the overfull batch, or by finalize
+            b.submit(bases, offs)
             b.finalize()
         assert ei.value.code == dbg.capi.DBG_ERR_TABLE_FULL
 

@@ -42,7 +42,8 @@ def deal_blocks(torch, bases, offs, n, rounds=1):
     return out, (db, do)
 
 
-def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, rounds=1, load=0.7):
+def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, rounds=1, load=0.7, optimistic=False, cap_pair=None,
+                info=None):
     import torch
     from dbg_assembly_b200.sharded import LocalShards
     bases = np.concatenate([f[0] for f in files]) if files else np.zeros(0, np.uint8)
@@ -50,7 +51,7 @@ def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, ro
     for b, o in files:
         offs.append(o[1:] + offs[-1][-1])
     offs = np.concatenate(offs)
-    ls = LocalShards(n, K, R, P_req, load_factor=load, force_wide=force_wide, by_slice=by_slice)
+    ls = LocalShards(n, K, R, P_req, load_factor=load, force_wide=force_wide, by_slice=by_slice, optimistic=optimistic, cap_pair=cap_pair)
     try:
         rds, keep = deal_blocks(torch, bases, offs, n, rounds)
         for blocks in rds:
@@ -65,6 +66,10 @@ def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, ro
             arr, nul, _ = ls.export_kmerset_fallback()
             used_fallback = True
         counts = sum(b.get_stats()["count"] for b in ls.b)
+        if info is not None:
+            info["overflows"] = ls.overflows
+            info["occurrences"] = sum(b.get_stats()["occurrences"] for b in ls.b)
+            info["reads"] = sum(b.get_stats()["reads"] for b in ls.b)
         return arr, nul, counts, used_fallback
     finally:
         ls.close()
@@ -78,17 +83,26 @@ def check_against_oracle(o, arr, nul, wide):
 
 
 @pytest.mark.parametrize("n", [2, 3, 8])
-@pytest.mark.parametrize("by_slice", [False, True])
+@pytest.mark.parametrize("mode", ["optimistic", "optimistic_overflow", "exact", "exact_sliced"])
 @pytest.mark.parametrize("K,wide", [(31, False), (31, True), (63, True)])
-def test_sharded_build_merges_into_the_reference_table(dbg, oracle_mod, monkeypatch, n, by_slice, K, wide):
+def test_sharded_build_merges_into_the_reference_table(dbg, oracle_mod, monkeypatch, n, mode, K, wide):
+    """exchange modes: optimistic = ONE extraction pass into fixed per-source regions (dbg_exchange_scatter_opt_device +
+    dbg_insert_tuple_regions_device; the default of the multi-GPU driver); optimistic_overflow = regions forced too small:
+    the side counters are rolled back and the round is redone exactly; exact = count + offsets + scatter
+    (dbg_exchange_count/scatter_device, PeerStagedSink); exact_sliced = (owner x slice) buckets + dbg_insert_sliced_device"""
     monkeypatch.setenv("DBG_B200_PART_SHIFT", "10")        # many table slices per shard at test size
     reads = random_reads(171 + n, 5000, 40, 150, genome_len=25000) + [b"A" * 70] * 30 + [b"T" * 64] * 7
     bases, offs = reads_to_arrays(reads)
     P_req = 400_000
     o = oracle_build(oracle_mod, [(bases, offs)], K, 150, P_req, wide=wide)
-    arr, nul, counts, fb = run_sharded(dbg, [(bases, offs)], K, 150, P_req, n, by_slice=by_slice, force_wide=wide and K <= 31, rounds=2)
+    info = {}
+    arr, nul, counts, fb = run_sharded(dbg, [(bases, offs)], K, 150, P_req, n, by_slice=mode == "exact_sliced", force_wide=wide and K <= 31,
+                                       rounds=2, optimistic=mode.startswith("optimistic"), cap_pair=512 if mode == "optimistic_overflow" else None,
+                                       info=info)
     assert not fb, "the windowed layout must handle an ordinary table"
     assert counts + 1 == o.count
+    assert info["occurrences"] == o.occurrences and info["reads"] == len(reads)
+    assert info["overflows"] == (2 if mode == "optimistic_overflow" else 0)
     check_against_oracle(o, arr, nul, wide)
     o.close()
 
@@ -121,5 +135,49 @@ def test_sharded_layout_on_dense_and_tiny_tables(dbg, oracle_mod, n, P_req, n_re
 def test_sharded_layout_of_an_empty_build(dbg, oracle_mod):
     o = oracle_build(oracle_mod, [], 31, 100, 50_000)
     arr, nul, counts, fb = run_sharded(dbg, [], 31, 100, 50_000, 2)
+    check_against_oracle(o, arr, nul, False)
+    o.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# dbg_mg_*: one process, several GPUs (here: several contexts on device 0), behind the single-GPU calls
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("variant", ["plain", "regrow", "small_rounds"])
+@pytest.mark.parametrize("K,wide", [(31, False), (55, True)])
+def test_multi_gpu_driver_builds_the_reference_table(dbg, oracle_mod, monkeypatch, n, variant, K, wide):
+    """dbg_mg_create / submit_reads / finalize / export_kmerset == the oracle's table (nodes, links, slot layout, k-mer-0
+    node), with exchange regions forced too small (they are doubled and the round redone) and with many small rounds"""
+    if variant == "regrow":
+        monkeypatch.setenv("DBG_B200_MG_CAP_PAIR", "256")
+    if variant == "small_rounds":
+        monkeypatch.setenv("DBG_B200_MG_ROUND_BASES", "60000")
+    reads = random_reads(300 + n, 4000, 40, 150, genome_len=20000) + [b"A" * 70] * 20
+    files = [reads_to_arrays(reads[:2500]), reads_to_arrays(reads[2500:])]
+    P_req = 300_000
+    o = oracle_build(oracle_mod, files, K, 150, P_req, wide=wide)
+    with dbg.MultiGpuBuilder(n, K=K, max_read_len=150, init_slots=P_req, devices=[0] * n) as b:
+        for bases, offs in files:
+            b.submit(bases, offs)
+        st = b.finalize()
+        arr, nul = b.export_kmerset()
+        info = b.info()
+    assert (st["count"], st["occurrences"], st["reads"], st["kmers_logged"]) == (o.count, o.occurrences, o.total_reads, o.kmers_logged)
+    assert not info["fallback"]
+    assert (info["regrows"] > 0) == (variant == "regrow")
+    assert info["rounds"] > (2 if variant != "small_rounds" else 10) - 1
+    check_against_oracle(o, arr, nul, wide)
+    o.close()
+
+
+def test_multi_gpu_driver_on_a_tiny_table_uses_the_dump_merge(dbg, oracle_mod):
+    reads = random_reads(977, 60, 60, 100, genome_len=3000, err=0.03)
+    files = [reads_to_arrays(reads)]
+    o = oracle_build(oracle_mod, files, 21, 100, 3000)
+    with dbg.MultiGpuBuilder(4, K=21, max_read_len=100, init_slots=3000, devices=[0] * 4) as b:
+        b.submit(*files[0])
+        st = b.finalize()
+        arr, nul = b.export_kmerset()
+    assert st["count"] == o.count
     check_against_oracle(o, arr, nul, False)
     o.close()
