@@ -237,36 +237,24 @@ def short_workload(args, wname, local, dev, torch, dbg, synth, steps=3, warmup=2
 
 
 def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, st, rank, world, dev, dist, torch):
-    import mmap
     import dbg_assembly_b200 as dbg
+    from dbg_assembly_b200.sharded import SharedImage
     Lb = dbg.capi.load()
     P = st["array_size"]
     wide = K > 31
     nb = 32 if wide else 16
-    img_bytes, nul_bytes = P * nb, P // 8 + 1
-    total = (img_bytes + 4095) // 4096 * 4096 + (nul_bytes + 4095) // 4096 * 4096
     path = [f"/dev/shm/dbg_b200_e2e_{os.getpid()}.img"] if rank == 0 else [None]
     dist.broadcast_object_list(path, src=0)
     path = path[0]
-    ok = torch.tensor([1], device=dev)
-    if rank == 0:
-        try:
-            sv = os.statvfs("/dev/shm")
-            if sv.f_bavail * sv.f_frsize < total + (1 << 30):
-                raise OSError("not enough room in /dev/shm")
-            with open(path, "wb") as f:
-                f.truncate(total)
-        except Exception:
-            ok[0] = 0
+    ok = torch.tensor([1 if (rank != 0 or SharedImage.room_for(P, wide)) else 0], device=dev)
     dist.broadcast(ok, src=0)
     if int(ok.item()) == 0:
-        raise RuntimeError(f"/dev/shm cannot hold the {total / 1e9:.1f} GB shared table image")
-    f = open(path, "r+b")
-    mm = mmap.mmap(f.fileno(), total)
-    base = np.frombuffer(mm, dtype=np.uint8)
-    base_ptr = base.ctypes.data
-    nul_off = (img_bytes + 4095) // 4096 * 4096
-    # page-lock only what this rank writes: its slice of the image (it may wrap) and its nul_flag bytes
+        raise RuntimeError(f"/dev/shm cannot hold the {P * nb / 1e9:.1f} GB shared table image")
+    img = SharedImage(path, P, wide, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        img = SharedImage(path, P, wide, create=False)
+    # page-lock only what this rank writes: its slice of the image (it may wrap past slot P-1)
     g_first, n_slots, _ = sb.b.shard_slice_info()
     regs = []
 
@@ -274,9 +262,9 @@ def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, s
         if ln <= 0:
             return
         a0 = off // 4096 * 4096
-        a1 = min(total, (off + ln + 4095) // 4096 * 4096)
-        dbg.capi.check(Lb.dbg_host_register(base_ptr + a0, a1 - a0), "dbg_host_register")
-        regs.append(base_ptr + a0)
+        a1 = min(img.total, (off + ln + 4095) // 4096 * 4096)
+        dbg.capi.check(Lb.dbg_host_register(img.base_ptr + a0, a1 - a0), "dbg_host_register")
+        regs.append(img.base_ptr + a0)
     first_len = min(n_slots, P - g_first)
     reg(g_first * nb, first_len * nb)
     if first_len < n_slots:
@@ -285,9 +273,6 @@ def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, s
     h_offs = (torch.arange(n + 1, dtype=torch.int64) * L).pin_memory()
     h_bases.copy_(d_bases.cpu())
     d_b2, d_o2 = torch.empty_like(d_bases), torch.empty_like(d_offs)
-    arr_ptr, nul_ptr = base_ptr, base_ptr + nul_off
-    arr = np.frombuffer(mm, dtype=dbg.NODE32 if wide else dbg.NODE16, count=P)
-    nul = np.frombuffer(mm, dtype=np.uint8, count=nul_bytes, offset=nul_off)
 
     def e2e_step():
         d_b2.copy_(h_bases, non_blocking=True)
@@ -295,18 +280,7 @@ def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, s
         sb.b.reset()
         sb.add_reads_device(d_b2, d_o2, n, 0, n * L, first_read, occ_rank)
         s = sb.finalize(layout=True)
-        edges = sb.b.export_shard_slice(arr_ptr, nul_ptr)
-        torch.cuda.synchronize()
-        e = torch.full((4,), -1, dtype=torch.int64, device=dev)
-        for i, x in enumerate(edges):
-            e[i] = x
-        alle = torch.empty(4 * world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(alle, e)               # also the barrier: every slice is in the shared image
-        if rank == 0:
-            ed = [int(x) for x in alle.cpu().tolist() if x >= 0]
-            dbg.capi.host_fix_nul_bytes(arr, nul, P, wide, ed)
-            dbg.capi.host_polyA_insert(arr, nul, P, wide, s["polyA_l"], s["polyA_r"])
-        dist.barrier()
+        sb.export_into(img, s)
         return s
     e2e_step()
     torch.cuda.synchronize(); dist.barrier()
@@ -319,26 +293,21 @@ def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, s
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    filled = int(np.unpackbits(nul[: min(nul_bytes, 1 << 20)]).sum()) if rank == 0 else 0
+    # cheap integrity figure of the merged image (rank 0): filled slots in the first 8 Mi slots vs the bitmap's count
+    chk = None
+    if rank == 0:
+        m = min(P, 8 << 20)
+        chk = {"slots_checked": int(m), "nonzero_kmers": int(np.count_nonzero(img.arr["kmer"][:m])),
+               "nul_bits": int(np.unpackbits(img.nul[: (m + 7) // 8])[:m].sum())}
     out = {"value": s2["global_occurrences"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * L + (n + 1) * 8) * world,
-           "d2h_bytes_per_step": int(img_bytes + nul_bytes), "ms_per_step": dt * 1e3, "steps": e_steps,
+           "d2h_bytes_per_step": int(img.img_bytes + img.nul_bytes), "ms_per_step": dt * 1e3, "steps": e_steps,
            "what": "per rank: pinned host reads -> H2D -> fused exchange -> insert -> cross-shard hand-off -> layout -> D2H of the rank's slice into ONE "
                    "shared host table image (/dev/shm); rank 0 fixes the shared nul_flag bytes and adds the k-mer-0 node; wall clock, max over ranks",
-           "merged_image_slots": int(P), "nul_bits_set_in_first_MiB": filled}
+           "merged_image_slots": int(P), "merged_image_check": chk}
     for r in regs:
         Lb.dbg_host_unregister(r)
-    del arr, nul, base
-    try:
-        mm.close()
-    except BufferError:
-        pass
-    f.close()
     dist.barrier()
-    if rank == 0:
-        try:
-            os.unlink(path)
-        except OSError:
-            pass
+    img.close(unlink=rank == 0)
     return out
 
 

@@ -207,7 +207,7 @@ static TableView view_of(dbg_ctx *c)
     TableView t;
     t.nodes = c->d_nodes; t.P = c->P; t.M = c->M; t.lo = c->shard_lo; t.n_local = c->n_local;
     t.counters = c->d_counters; t.polyA = c->d_polyA;
-    t.guard_budget = (1ull << 20) + c->guard_total;
+    t.guard_budget = (1ull << 12) + c->guard_total / 16;      // in units of 16384 probe steps (insert_probe)
     return t;
 }
 

@@ -91,21 +91,24 @@ __device__ __forceinline__ void insert_one(const TableView &t, u64 klo, u64 khi,
     insert_probe<WIDE, TRACK>(t, p, n, klo, khi, lb, rb, ord, n_new, n_conf);
 }
 
-// Every 1024 slots of a long probe (free in the common case; out of line so that the hot loop pays no registers for
-// it): long probes draw on a budget of the whole build -- about 1024 probe steps per occurrence submitted so far, far
-// beyond what any table that still has room needs -- so a (nearly) full table is REPORTED within seconds instead of
-// being scanned slot by slot.  Raising the error also poisons the tile counter of k_insert_tuples (counters[7]).
+// A (nearly) full table must be REPORTED, not scanned slot by slot to its end (the front end then rebuilds with a larger
+// device table).  DBG_GUARD picks how (measured on C2, profiles/README.md): 1-3 = a budget of long probe steps checked inside
+// the probe loop -- correct, but the extra code spills at the insert kernel's 32-register budget and costs 9 % of it;
+// 4 (default) = the probe length is capped through the loop's own end pointer, which costs nothing.
 #ifndef DBG_GUARD
-#define DBG_GUARD 1      // 0: no guard (measurements only), 1: inline, 2: out of line
+#define DBG_GUARD 4
 #endif
+constexpr long long PROBE_CAP = 1ll << 22;      // slots a probe may walk from its home slot (longest legitimate clusters: ~1e5)
+#if DBG_GUARD == 2
 static __device__ __noinline__ bool probe_guard(u64 *counters, u64 budget)
 {
     if (atomicAdd(counters + CNT_GUARD, 1ULL) >= budget || __ldcg(counters + CNT_ERROR)) {
-        atomicExch(counters + CNT_ERROR, 1ULL); atomicExch(counters + 7, 1ULL << 62);
+        atomicExch(counters + CNT_ERROR, 1ULL); atomicExch(counters + 7, 1ULL << 40);
         return true;
     }
     return false;
 }
+#endif
 
 // the probe loop, entered with the home slot's node already loaded (callers may have several loads in flight)
 template <bool WIDE, bool TRACK>
@@ -113,7 +116,16 @@ __device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p,
                                              u32 &n_new, u32 &n_conf)
 {
     typedef NodeT<WIDE> Nd;
+#if DBG_GUARD == 4
+    // a probe ends at the end of the shard (+ margin) or PROBE_CAP slots from home, whichever comes first: the check is
+    // the one the loop has anyway, so a (nearly) full table is REPORTED -- the first probe that runs out raises the error
+    // and poisons the tile counter of k_insert_tuples (counters[7]), the probes in flight end within PROBE_CAP slots --
+    // instead of being scanned slot by slot to its end
+    Nd *p_end = static_cast<Nd *>(t.nodes) + t.n_local;
+    if (p_end - p > (long long)PROBE_CAP) p_end = p + PROBE_CAP;
+#else
     Nd *const p_end = static_cast<Nd *>(t.nodes) + t.n_local;
+#endif
     for (;;) {
         if ((n.klo | n.khi) == 0) {
             if (WIDE) {
@@ -139,13 +151,21 @@ __device__ __forceinline__ void insert_probe(const TableView &t, NodeT<WIDE> *p,
         }
         n_conf++;                                       // occupied by another key: next slot (DBGgraph.cpp:201-204)
         p++;
-        if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 62); return; }
-#if DBG_GUARD == 2
+        if (p >= p_end) { atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 40); return; }
+#if DBG_GUARD == 3
+        // every 16384 probe steps of this thread (its running conflict counter is live anyway: no extra register): long
+        // probes draw on a budget of the whole build (see probe_guard)
+        if ((n_conf & 0x3FFFu) == 0) {
+            if (atomicAdd(t.counters + CNT_GUARD, 1ULL) >= t.guard_budget || __ldcg(t.counters + CNT_ERROR)) {
+                atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 40); return;
+            }
+        }
+#elif DBG_GUARD == 2
         if ((reinterpret_cast<unsigned long long>(p) & (1024 * sizeof(Nd) - 1)) == 0 && probe_guard(t.counters, t.guard_budget)) return;
 #elif DBG_GUARD == 1
         if ((reinterpret_cast<unsigned long long>(p) & (1024 * sizeof(Nd) - 1)) == 0) {
             if (atomicAdd(t.counters + CNT_GUARD, 1ULL) >= t.guard_budget || __ldcg(t.counters + CNT_ERROR)) {
-                atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 62); return;
+                atomicExch(t.counters + CNT_ERROR, 1ULL); atomicExch(t.counters + 7, 1ULL << 40); return;
             }
         }
 #endif
@@ -403,7 +423,10 @@ struct StageBuf {
 template <bool WIDE, bool OPT = false>
 struct StagedScatterSink {
     static constexpr int RUN = G;
-    static constexpr int MIN_BLOCKS = 3;           // <= 85 registers: three CTAs per SM next to a 2048-tuple batch
+#ifndef DBG_SCATTER_MIN_BLOCKS
+#define DBG_SCATTER_MIN_BLOCKS 3
+#endif
+    static constexpr int MIN_BLOCKS = DBG_SCATTER_MIN_BLOCKS;   // 3: <= 85 registers, three CTAs per SM next to a 2048-tuple batch
     TableView t;
     int shift;
     u32 n_buckets, cap;
@@ -1133,7 +1156,14 @@ __device__ __forceinline__ int nth_occupied(const u32 *W, const u32 *wcnt, u32 i
         if (!found && before + n <= i) { before += n; c = q + 1; } else found = true;
     }
     if (c >= LW) c = LW - 1;                                  // (not reached for i < n_occ)
-    return (c << 5) + (int)(__fns(W[c], 0, (int)(i - before) + 1) & 31u);
+    // position of the r-th (0-based) set bit of W[c]: binary search on population counts
+    u32 w = W[c], r = i - before, pos = 0, t;
+    t = __popc(w & 0xFFFFu); if (r >= t) { pos += 16; r -= t; w >>= 16; }
+    t = __popc(w & 0xFFu);   if (r >= t) { pos += 8;  r -= t; w >>= 8; }
+    t = __popc(w & 0xFu);    if (r >= t) { pos += 4;  r -= t; w >>= 4; }
+    t = __popc(w & 0x3u);    if (r >= t) { pos += 2;  r -= t; w >>= 2; }
+    t = w & 1u;              if (r >= t) { pos += 1; }
+    return (c << 5) + (int)(pos & 31u);
 }
 
 template <bool WIDE, bool TRACK>
@@ -1202,6 +1232,13 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
                     if (rr >= MAX_REGIONS || off + len > scratch_cap) info->overflow = 1;
                     else { regions[rr].a = cs; regions[rr].n = len; regions[rr].off = off; regions[rr].wrap = 0; }
                 }
+                continue;
+            }
+            if (end - start == 1) {
+                // a key alone between two empty slots sits at its home slot (probing never crosses an empty slot): nothing
+                // to replay -- about a third of the keys of a table at load 0.5 -- write its image node at once
+                const ulonglong2 cc = s_raw[NQ * k + NQ - 1];
+                write_image<WIDE>(out, i0 + k, klo, khi, (u64)pack_link(cc.x) | ((u64)pack_link(cc.y) << 32));
                 continue;
             }
             s_home[k] = pos;

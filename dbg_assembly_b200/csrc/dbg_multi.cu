@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -31,7 +32,10 @@ thread_local char g_mg_err[512] = "";
 
 int mg_fail(int code, const char *what)
 {
-    snprintf(g_mg_err, sizeof(g_mg_err), "%s: %s", what, dbg_last_error());
+    // a worker thread may already have left its (thread-local) message here: keep it, add the call's name
+    char prev[sizeof(g_mg_err)];
+    snprintf(prev, sizeof(prev), "%s", g_mg_err[0] && strncmp(g_mg_err, "GPU ", 4) == 0 ? g_mg_err : dbg_last_error());
+    snprintf(g_mg_err, sizeof(g_mg_err), "%.60s: %.440s", what, prev);
     return code;
 }
 
@@ -61,11 +65,14 @@ struct dbg_mg {
 static void run_per_gpu(dbg_mg *m, const std::function<int(int)> &f, std::vector<int> &rc)
 {
     rc.assign(m->n, 0);
+    std::vector<std::string> msg(m->n);                      // dbg_last_error() is thread-local: fetch it in the worker
     std::vector<std::thread> th;
-    for (int r = 1; r < m->n; r++) th.emplace_back([&, r]() { cudaSetDevice(m->dev[r]); rc[r] = f(r); });
+    for (int r = 1; r < m->n; r++) th.emplace_back([&, r]() { cudaSetDevice(m->dev[r]); rc[r] = f(r); if (rc[r]) msg[r] = dbg_last_error(); });
     cudaSetDevice(m->dev[0]);
     rc[0] = f(0);
     for (auto &t : th) t.join();
+    for (int r = 1; r < m->n; r++)
+        if (rc[r] && rc[0] == DBG_OK) { snprintf(g_mg_err, sizeof(g_mg_err), "GPU %d: %s", m->dev[r], msg[r].c_str()); break; }
 }
 
 static int first_error(const std::vector<int> &rc)

@@ -11,6 +11,8 @@ extract/insert callables.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -61,11 +63,15 @@ def merge_dumps_host(dumps, P_request, load_factor, wide, polyA_l, polyA_r):
     return arr, nul, plan
 
 
-def ring_layout(builders):
+def ring_layout(builders, blobs_out=None):
     """single process, all ranks at hand (tests, one process driving several GPUs): tail hand-off around the ring, then
-    every rank lays out its window.  Returns (list of stats, blobs)."""
+    every rank lays out its window.  Returns (list of stats, blobs).  blobs_out (a list) receives every blob as soon as
+    it exists: a rank that refuses (DBG_ERR_STATE) leaves the caller with what the others already handed over -- their
+    overflow nodes now live ONLY in those blobs -- for the dump-merging fallback."""
     n = len(builders)
-    blobs = [b.shard_tail_export() for b in builders]
+    blobs = blobs_out if blobs_out is not None else []
+    for b in builders:
+        blobs.append(b.shard_tail_export())
     for r, b in enumerate(builders):
         b.shard_tail_import(blobs[(r - 1) % n])
     return [b.finalize() for b in builders], blobs
@@ -203,7 +209,8 @@ class LocalShards:
             b.set_polyA_counts(polyA)
         if not layout:
             return [b.finalize() for b in self.b]
-        stats, self.blobs = ring_layout(self.b)
+        self.blobs = []
+        stats, _ = ring_layout(self.b, self.blobs)
         return stats
 
     def export_kmerset(self, stats):
@@ -217,6 +224,58 @@ class LocalShards:
         polyA = self.b[0].get_polyA_counts()
         cl = lambda q: sum(int(min(int(q[i]), 255)) << (24 - 8 * i) for i in range(4))
         return merge_dumps_host(dumps, self.P_request, self.load_factor, self.b[0].wide, cl(polyA[:4]), cl(polyA[4:]))
+
+
+class LayoutNeedsMerge(RuntimeError):
+    """the windowed cross-shard layout refused on some rank (boundary cluster longer than the hand-off porch, a hand-off
+    that cascades through a whole shard, a shard too dense for the cluster scratch: tables of a few thousand slots or
+    pathologically dense ones).  Raised on EVERY rank together; merge the shard dumps instead (same table)."""
+
+
+class SharedImage:
+    """ONE host table image (array[P] + nul_flag[P/8+1], the reference's KmerSet, kmerSet.h:88-99) that the ranks of a
+    one-process-per-GPU build export their slices into: a file mapping in /dev/shm (rank 0 creates it, everybody maps it).
+    A single consumer process -- the reference's traversal -- would map the same file."""
+
+    def __init__(self, path, P, wide, create):
+        import mmap
+        from .graph import NODE16, NODE32
+        self.path, self.P, self.wide = path, int(P), bool(wide)
+        nb = 32 if wide else 16
+        self.img_bytes, self.nul_bytes = self.P * nb, self.P // 8 + 1
+        self.nul_off = (self.img_bytes + 4095) // 4096 * 4096
+        self.total = self.nul_off + (self.nul_bytes + 4095) // 4096 * 4096
+        if create:
+            with open(path, "wb") as f:
+                f.truncate(self.total)
+        self.f = open(path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), self.total)
+        self.base = np.frombuffer(self.mm, dtype=np.uint8)
+        self.base_ptr = self.base.ctypes.data
+        self.arr = np.frombuffer(self.mm, dtype=NODE32 if wide else NODE16, count=self.P)
+        self.nul = np.frombuffer(self.mm, dtype=np.uint8, count=self.nul_bytes, offset=self.nul_off)
+        self.arr_ptr, self.nul_ptr = self.base_ptr, self.base_ptr + self.nul_off
+
+    @staticmethod
+    def room_for(P, wide, where="/dev/shm"):
+        try:
+            sv = os.statvfs(where)
+            return sv.f_bavail * sv.f_frsize > P * (32 if wide else 16) + P // 8 + (1 << 30)
+        except OSError:
+            return False
+
+    def close(self, unlink=False):
+        self.arr = self.nul = self.base = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        self.f.close()
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
 
 
 class Exchange:
@@ -274,6 +333,7 @@ class ShardedBuilder:
         self.b = DBGBuilder(K=K, max_read_len=max_read_len, init_slots=init_slots, load_factor=load_factor, device=device,
                             track_order=track_order, shard_rank=self.rank, shard_count=self.n)
         self.device = torch.device("cuda", device)
+        self.P_request, self.load_factor = init_slots, load_factor
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
         self._send = self._counts = None
         self.exchange_bytes = 0
@@ -472,6 +532,23 @@ class ShardedBuilder:
         self._keep = recv    # keep alive until the insert kernel ran
         return total
 
+    def merged_table_from_dumps(self):
+        """fallback after LayoutNeedsMerge (collective): every rank's nodes (+ the overflow nodes it had already handed
+        over, which live only in its tail blob) are gathered on rank 0, which replays them in first-occurrence order on
+        the host -- the reference's layout by construction.  Returns (array, nul_flag) on rank 0, (None, None) elsewhere."""
+        d = self.b.dump_shard()
+        blob = getattr(self, "_tail_blob", None)
+        extra = blob_margin_nodes(blob) if blob else None
+        polyA = self.b.get_polyA_counts()
+        gathered = [None] * self.n
+        dist.all_gather_object(gathered, (d, extra), group=self.ex.group)
+        if self.rank != 0:
+            return None, None
+        dumps = [g[0] for g in gathered] + [g[1] for g in gathered if g[1] is not None]
+        cl = lambda q: sum(int(min(int(q[i]), 255)) << (24 - 8 * i) for i in range(4))
+        arr, nul, _ = merge_dumps_host(dumps, self.P_request, self.load_factor, self.b.wide, cl(polyA[:4]), cl(polyA[4:]))
+        return arr, nul
+
     def _ring_blobs(self, blob: bytes) -> bytes:
         """every rank's tail blob goes to the rank on its right (sizes first, then one padded all-gather: blobs are
         a few hundred bytes)"""
@@ -488,6 +565,23 @@ class ShardedBuilder:
         left = (self.rank - 1) % n
         return bytes(allb[left * mx: left * mx + sizes[left]].cpu().numpy().tobytes())
 
+    def export_into(self, img: "SharedImage", st):
+        """after finalize(layout=True): this rank's slice goes into the shared table image; once every slice is in, rank 0
+        fixes the nul_flag bytes shared between neighbours and appends the k-mer-0 node (DBGgraph.cpp:418).  Collective."""
+        from . import capi
+        edges = self.b.export_shard_slice(img.arr_ptr, img.nul_ptr)
+        torch.cuda.synchronize(self.device)
+        e = torch.full((4,), -1, dtype=torch.int64, device=self.device)
+        for i, x in enumerate(edges):
+            e[i] = x
+        alle = torch.empty(4 * self.n, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(alle, e, group=self.ex.group)          # also the barrier: every slice is in the image
+        if self.rank == 0:
+            ed = [int(x) for x in alle.cpu().tolist() if x >= 0]
+            capi.host_fix_nul_bytes(img.arr, img.nul, img.P, img.wide, ed)
+            capi.host_polyA_insert(img.arr, img.nul, img.P, img.wide, st["polyA_l"], st["polyA_r"])
+        dist.barrier(group=self.ex.group)
+
     def finalize(self, layout=False):
         """layout=True: cross-shard hand-off of the boundary clusters, then every rank lays out its slice of the
         reference's table (dbg_export_shard_slice / export_slice copies it out)"""
@@ -495,8 +589,32 @@ class ShardedBuilder:
         polyA = self.ex.allreduce_sum_u64(self.b.get_polyA_counts(), self.device)
         self.b.set_polyA_counts(polyA)
         if layout and self.n > 1:
-            self.b.shard_tail_import(self._ring_blobs(self.b.shard_tail_export()))
-        st = self.b.finalize()
+            from . import capi
+
+            def together(fn):
+                """run a step that may refuse with DBG_ERR_STATE; all ranks learn whether anybody refused"""
+                out, ok = None, 1
+                try:
+                    out = fn()
+                except capi.DbgError as e:
+                    if e.code != capi.DBG_ERR_STATE:
+                        raise
+                    ok = 0
+                t = torch.tensor([ok], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.ex.group)
+                return out, bool(t.item())
+            self._tail_blob, ok = together(self.b.shard_tail_export)
+            if not ok:
+                raise LayoutNeedsMerge("dbg_shard_tail_export refused on some rank")
+            incoming = self._ring_blobs(self._tail_blob)
+            _, ok = together(lambda: self.b.shard_tail_import(incoming))
+            if not ok:
+                raise LayoutNeedsMerge("dbg_shard_tail_import refused on some rank")
+            st, ok = together(self.b.finalize)
+            if not ok:
+                raise LayoutNeedsMerge("the windowed layout refused on some rank")
+        else:
+            st = self.b.finalize()
         tot = self.ex.allreduce_sum_u64(np.array([st["count"], st["occurrences"]], dtype=np.uint64), self.device)
         st["global_count"] = int(tot[0]) + 1          # + the k-mer-0 node
         st["global_occurrences"] = int(tot[1])

@@ -22,6 +22,7 @@ REF_DRIVER = os.path.join(REF_DIR, "ref_build_driver")
 REF_CONTIG = os.path.join(REF_DIR, "debruijn_contig_ref")
 REF_ELF = os.path.join(REF_DIR, "debruijn_contig_elf")
 B200_CONTIG = os.path.join(REF_DIR, "debruijn_contig_b200")
+KMER_TABLE_DRIVER = os.path.join(REF_DIR, "ref_kmer_table_driver")   # reference's construct_ref_kmer_table
 CORRECT_ELF = os.path.join(REF_DIR, "correct_error_reads_elf")   # shipped consumer of the .cz table
 
 _lib = None
@@ -80,6 +81,16 @@ def kfreq_count(bases, offs, K):
     counts = np.zeros(1 << (2 * K), dtype=np.uint32)
     lib().orc_kfreq_count(bases.ctypes.data, offs.ctypes.data, len(offs) - 1, K, counts.ctypes.data)
     return counts
+
+
+def ref_kmer_table(genome_fasta, K):
+    """the reference's own both-strand 1-bit table of a genome FASTA (correct_error/simulate_lowfreq_kmer.cpp:189-260
+    through oracle/_ref/ref_kmer_table_driver) -> bit array (uint8 0/1) of 4^K entries, MSB-first bytes unpacked"""
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "t.bits")
+        subprocess.run([KMER_TABLE_DRIVER, str(K), genome_fasta, out], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        raw = np.fromfile(out, dtype=np.uint8)
+    return np.unpackbits(raw)[: 1 << (2 * K)]
 
 
 def load_cz_1bit(prefix, K):

@@ -1,16 +1,22 @@
-"""Multi-GPU parity check (not collected by pytest: needs N GPUs and torchrun).
+"""Multi-GPU parity check on real GPUs (not collected by pytest: needs N GPUs and torchrun; the same flow runs on ONE
+device inside pytest, tests/test_gpu_sharded_layout.py).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multigpu_check.py [--reads 200000] [--K 31]
+        tests/multigpu_check.py [--reads 200000] [--K 31] [--exchange peer|peer_exact|peer_sliced|nccl] [--front-end]
 
-Every rank extracts + exchanges + inserts its block of C2-shaped synthetic reads (ShardedBuilder); the union
-of the shard dumps must equal the oracle's node multiset bit for bit, every node must sit on its owner, and
-replaying the keys in first-occurrence order must reproduce the oracle's slot layout.  Prints one JSON line.
+Every rank extracts + exchanges + inserts its block of C2-shaped synthetic reads (ShardedBuilder, two calls so that the
+exchange repeats), the boundary clusters are handed around the ring, every rank lays out its slice and exports it into
+ONE shared host table image; rank 0 compares that image with the oracle's table (== the reference with -t 1): filled
+slots, k-mers, link words, slot layout, k-mer-0 node -- bit for bit.  --front-end additionally runs the relinked reference
+front end (oracle/_ref/debruijn_contig_b200) with DBG_B200_GPUS=N on the same reads and compares its output files with
+the single-GPU run's and, where the reference binary is present, the reference's.  Prints one JSON line.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
+import tempfile
 
 import numpy as np
 import torch
@@ -19,17 +25,49 @@ import torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
+SUF = (".contig.seq.fa", ".contig.small.fa", ".contig.kmer.freq", ".contig.tip.fa", ".contig.bubble.fa", ".contig.lowedge.fa",
+       ".contig.seq.depth", ".contig.small.depth")
+
+
+def front_end_check(world, hb, ho, K, L):
+    """the drop-in binary on N GPUs from ONE process (dbg_mg_*) vs on one GPU vs the reference program"""
+    from oracle import oracle as orc
+    exe = os.path.join(REPO, "oracle", "_ref", "debruijn_contig_b200")
+    ref = os.path.join(REPO, "oracle", "_ref", "debruijn_contig_ref")
+    if not os.access(exe, os.X_OK):
+        return {"skipped": "oracle/_ref/debruijn_contig_b200 not present"}
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "reads.fa"); orc.write_fasta(fa, hb, ho)
+        lib = os.path.join(td, "reads.lib"); open(lib, "w").write(fa + "\n")
+        files = {}
+        for tag, binary, env in (("gpus1", exe, {}), (f"gpus{world}", exe, {"DBG_B200_GPUS": str(world)}), ("reference", ref, {})):
+            if not os.access(binary, os.X_OK):
+                continue
+            pre = os.path.join(td, tag)
+            r = subprocess.run([binary, "-k", str(K), "-r", str(L), "-f", "2", "-t", "1", "-i", "0.012", "-M", "100", "-o", pre, lib],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=dict(os.environ, **env))
+            if r.returncode != 0:
+                return {"error": f"{tag}: rc {r.returncode}: {r.stderr.decode()[-400:]}"}
+            files[tag] = {s: open(pre + s, "rb").read() for s in SUF}
+        out["multi_equals_single"] = files[f"gpus{world}"] == files["gpus1"]
+        if "reference" in files:
+            out["multi_equals_reference"] = files[f"gpus{world}"] == files["reference"]
+        out["contig_bytes"] = len(files["gpus1"][".contig.seq.fa"])
+    return out
+
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=200_000)
     ap.add_argument("--K", type=int, default=31)
     ap.add_argument("--slots", type=int, default=12_000_000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_sliced", "nccl"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_exact", "peer_sliced", "nccl"])
+    ap.add_argument("--front-end", action="store_true")
     a = ap.parse_args()
     import dbg_assembly_b200 as dbg
     from dbg_assembly_b200 import synth
-    from dbg_assembly_b200.sharded import ShardedBuilder, shard_size
+    from dbg_assembly_b200.sharded import ShardedBuilder, SharedImage
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -42,67 +80,54 @@ def main():
     synth.reads_device(p, first, per, d_bases.data_ptr(), device=local)
     d_offs = torch.arange(per + 1, dtype=torch.int64, device=dev) * L
     torch.cuda.synchronize()
-    sb = ShardedBuilder(K=a.K, max_read_len=L, init_slots=a.slots, device=local, exchange=a.exchange)
+    sb = ShardedBuilder(K=a.K, max_read_len=L, init_slots=a.slots, device=local, exchange=a.exchange, sub_blocks=3)
     from dbg_assembly_b200.graph import torch_stream_handle
     sb.b.set_stream(torch_stream_handle(dev))
-    # two blocks per rank, to exercise repeated exchanges
     half = per // 2
     occ_upper = per * L
     sb.add_reads_device(d_bases, d_offs, half, 0, half * L, first, occ_upper)
     sb.add_reads_device(d_bases, d_offs[half:], per - half, half * L, (per - half) * L, first + half, occ_upper)
-    st = sb.finalize()
-    shard = sb.b.dump_shard()
-    polyA = sb.b.get_polyA_counts()
-    P = st["array_size"]
-    # every node sits on its owner
-    homes = np.array([dbg.capi.hash_code(int(k)) % P for k in shard["kmer"][:2000]]) if a.K <= 31 else None
-    if homes is not None:
-        ss = shard_size(P, world)
-        assert ((homes // ss) == rank).all(), "node stored on the wrong shard"
-    gathered = [None] * world
-    dist.all_gather_object(gathered, {k: v for k, v in shard.items()})
-    ok = True
-    msg = ""
+    st = sb.finalize(layout=True)
+    P, wide = st["array_size"], a.K > 31
+    path = [f"/dev/shm/dbg_b200_mgcheck_{os.getpid()}.img"] if rank == 0 else [None]
+    dist.broadcast_object_list(path, src=0)
+    img = SharedImage(path[0], P, wide, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        img = SharedImage(path[0], P, wide, create=False)
+    sb.export_into(img, st)
+    ok, msg, fe = True, "", None
     if rank == 0:
         from oracle import oracle as orc
         hb, ho = synth.reads_host(p, 0, per * world)
-        o = orc.OracleGraph(a.K, L, a.slots, 0.7, 10, 1 << 40, wide=a.K > 31)
+        o = orc.OracleGraph(a.K, L, a.slots, 0.7, 10, 1 << 40, wide=wide)
         o.add_file(hb, ho); o.finish()
         e = o.dump()
-        nz = (e["kmer"] != 0) | (e["kmer_hi"] != 0)
-        kk = np.concatenate([g["kmer"] for g in gathered]); kh = np.concatenate([g["kmer_hi"] for g in gathered])
-        ll = np.concatenate([g["l"] for g in gathered]); rr = np.concatenate([g["r"] for g in gathered]); oo = np.concatenate([g["ord"] for g in gathered])
-        so = np.lexsort((kk, kh)); eo = np.lexsort((e["kmer"][nz], e["kmer_hi"][nz]))
         try:
-            assert len(kk) == int(nz.sum()) == st["global_count"] - 1, (len(kk), int(nz.sum()), st["global_count"])
-            assert np.array_equal(kk[so], e["kmer"][nz][eo]) and np.array_equal(kh[so], e["kmer_hi"][nz][eo])
-            assert np.array_equal(ll[so], e["l"][nz][eo]) and np.array_equal(rr[so], e["r"][nz][eo])
-            assert st["global_occurrences"] == o.occurrences
-            pa = np.minimum(polyA, 255).astype(np.uint64)
-            assert int(e["l"][~nz][0]) == (int(pa[0]) << 24 | int(pa[1]) << 16 | int(pa[2]) << 8 | int(pa[3]))
-            assert int(e["r"][~nz][0]) == (int(pa[4]) << 24 | int(pa[5]) << 16 | int(pa[6]) << 8 | int(pa[7]))
-            # first-occurrence order == oracle insertion order: the oracle's slot of a key is increasing in
-            # "ordinal" only within a probe cluster, so check through a replay on a sample-free full pass
-            order = np.argsort(oo)
-            seq_lo, seq_hi = kk[order], kh[order]
-            Pn = o.size
-            occ = np.zeros(Pn, dtype=bool)
-            slot_of = np.empty(len(seq_lo), dtype=np.int64)
-            hh = [dbg.capi.hash_code_wide(int(x), int(y)) % Pn if a.K > 31 else dbg.capi.hash_code(int(x)) % Pn for x, y in zip(seq_lo.tolist(), seq_hi.tolist())]
-            for i, h in enumerate(hh):
-                while occ[h]:
-                    h = h + 1 if h + 1 < Pn else 0
-                occ[h] = True; slot_of[i] = h
-            exp_slot = dict(zip(zip(e["kmer"][nz].tolist(), e["kmer_hi"][nz].tolist()), e["slot"][nz].tolist()))
-            got_slot = [exp_slot[(x, y)] for x, y in zip(seq_lo.tolist(), seq_hi.tolist())]
-            assert np.array_equal(slot_of, np.array(got_slot)), "ordinals do not reproduce the reference layout"
+            bits = np.unpackbits(img.nul)[:P]
+            slot = np.nonzero(bits)[0].astype(np.uint64)
+            sel = slot.astype(np.int64)
+            assert st["global_count"] == o.count and st["global_occurrences"] == o.occurrences, (st["global_count"], o.count)
+            assert np.array_equal(slot, e["slot"]), "slot layout differs from the oracle"
+            assert np.array_equal(img.arr["kmer"][sel], e["kmer"]), "k-mers differ"
+            if wide:
+                assert np.array_equal(img.arr["kmer_hi"][sel], e["kmer_hi"])
+            assert np.array_equal(img.arr["l_link"][sel], e["l"]) and np.array_equal(img.arr["r_link"][sel], e["r"]), "link words differ"
+            mask = np.ones(P, dtype=bool); mask[sel] = False
+            assert not img.arr["kmer"][mask].any() and not img.arr["l_link"][mask].any(), "unfilled slots are not zero"
         except AssertionError as ex:
             ok, msg = False, str(ex)
+        if a.front_end and a.K <= 31:
+            fe = front_end_check(world, hb, ho, a.K, L)
+            if fe.get("error") or fe.get("multi_equals_single") is False or fe.get("multi_equals_reference") is False:
+                ok = False
         print(json.dumps({"multigpu_check": "ok" if ok else "FAILED", "n_gpus": world, "K": a.K, "reads": per * world,
-                          "nodes": int(len(kk)) + 1, "occurrences": st["global_occurrences"], "detail": msg,
-                          "exchange_bytes_rank0": sb.exchange_bytes, "exchange": sb.exchange}))
+                          "nodes": int(st["global_count"]), "occurrences": st["global_occurrences"], "detail": msg,
+                          "exchange_bytes_rank0": sb.exchange_bytes, "exchange": sb.exchange, "optimistic_fallbacks": sb.opt_fallbacks,
+                          "front_end": fe}))
         o.close()
     dist.barrier()
+    img.close(unlink=rank == 0)
     sb.close()
     dist.destroy_process_group()
     return 0 if ok else 1

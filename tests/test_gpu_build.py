@@ -651,3 +651,41 @@ def test_python_mirror_reproduces_the_enlarged_reference_table(dbg, build_path):
     slot2 = ks2.filled_slots()
     assert np.array_equal(slot2, g2["slot"]) and np.array_equal(ks2.array["kmer"][slot2.astype(np.int64)], g2["kmer"])
     assert np.array_equal(ks2.array["l_link"][slot2.astype(np.int64)], g2["l"]) and np.array_equal(ks2.array["r_link"][slot2.astype(np.int64)], g2["r"])
+
+
+@pytest.mark.skipif(not os.access(B200_CONTIG, os.X_OK), reason="oracle/_ref/debruijn_contig_b200 not built (needs /root/reference at build time)")
+def test_full_size_C2_contig_files_byte_identical_to_reference(dbg, build_path, tmp_path):
+    """the configuration the metric is quoted on, at FULL size, through files: the reference program (-t 1: its
+    deterministic slot layout) and the front end relinked to libdbgb200 on the same 460 MB FASTA (C2: 4.6 Mb genome,
+    3 066 666 x 150 bp reads, 1 % errors, K=31, -i 0.2) -- all eight output files byte for byte.  About a minute, most
+    of it the reference's CPU build."""
+    if build_path != "direct":
+        pytest.skip("front-end binaries: the build path is chosen by the library")
+    from dbg_assembly_b200 import synth
+    ref = os.path.join(REPO, "oracle", "_ref", "debruijn_contig_ref")
+    gen = os.path.join(REPO, "oracle", "_bin", "synth_fasta")
+    if not (os.access(ref, os.X_OK) and os.access(gen, os.X_OK)):
+        pytest.skip("oracle/_ref/debruijn_contig_ref or oracle/_bin/synth_fasta not present")
+    c = synth.CONFIGS["C2"]
+    p = synth.make_params(c["seed"], c["genome_len"], c["read_len"], c["insert"], c["err"], c["n_rate"])
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > (2 << 30) else str(tmp_path)
+    fa = os.path.join(d, f"c2_full_{os.getpid()}.fa")
+    try:
+        subprocess.run([gen, str(p.seed), str(p.genome_len), str(p.read_len), str(p.insert), str(p.err_per_2p24), str(p.n_per_2p24), "0",
+                        str(c["n_reads"]), fa], check=True, timeout=600)
+        lib = str(tmp_path / "c2.lib"); open(lib, "w").write(fa + "\n")
+        outs = {}
+        for tag, exe in (("b200", B200_CONTIG), ("ref", ref)):
+            pre = str(tmp_path / tag)
+            rr = subprocess.run([exe, "-k", "31", "-r", "150", "-f", "2", "-t", "1", "-i", "0.2", "-M", "100", "-o", pre, lib],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1500)
+            assert rr.returncode == 0, rr.stderr.decode()[-2000:]
+            outs[tag] = {suf: open(pre + suf, "rb").read() for suf in OUT_SUFFIXES}
+            if tag == "b200":
+                assert "count:\t100611066" in rr.stderr.decode()
+        for suf in OUT_SUFFIXES:
+            assert outs["ref"][suf] == outs["b200"][suf], suf
+        assert len(outs["ref"][".contig.seq.fa"]) > 4_000_000
+    finally:
+        if os.path.exists(fa):
+            os.unlink(fa)

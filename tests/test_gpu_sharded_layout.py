@@ -22,6 +22,19 @@ def dbg():
     return m
 
 
+def distinct_kmers_upper_bound(reads, K):
+    """distinct canonical K-mers (case / N folded the way alphabet[] does; canonical = the smaller of a k-mer and its
+    reverse complement in ACGT order, like the 2-bit comparison): the number of nodes the build will hold"""
+    tr, comp = bytes.maketrans(b"acgtnN", b"ACGTAA"), bytes.maketrans(b"ACGT", b"TGCA")
+    seen = set()
+    for r in reads:
+        r = r.translate(tr)
+        for j in range(len(r) - K + 1):
+            k = r[j:j + K]
+            seen.add(min(k, k.translate(comp)[::-1]))
+    return len(seen)
+
+
 def deal_blocks(torch, bases, offs, n, rounds=1):
     """contiguous blocks of the read sequence dealt to n ranks, `rounds` exchange rounds"""
     db = torch.from_numpy(bases).cuda() if len(bases) else torch.zeros(16, dtype=torch.uint8, device="cuda")
@@ -83,13 +96,14 @@ def check_against_oracle(o, arr, nul, wide):
 
 
 @pytest.mark.parametrize("n", [2, 3, 8])
-@pytest.mark.parametrize("mode", ["optimistic", "optimistic_overflow", "exact", "exact_sliced"])
+@pytest.mark.parametrize("mode", ["optimistic", "optimistic_overflow", "exact"])
 @pytest.mark.parametrize("K,wide", [(31, False), (31, True), (63, True)])
 def test_sharded_build_merges_into_the_reference_table(dbg, oracle_mod, monkeypatch, n, mode, K, wide):
     """exchange modes: optimistic = ONE extraction pass into fixed per-source regions (dbg_exchange_scatter_opt_device +
     dbg_insert_tuple_regions_device; the default of the multi-GPU driver); optimistic_overflow = regions forced too small:
     the side counters are rolled back and the round is redone exactly; exact = count + offsets + scatter
-    (dbg_exchange_count/scatter_device, PeerStagedSink); exact_sliced = (owner x slice) buckets + dbg_insert_sliced_device"""
+    (dbg_exchange_count/scatter_device, PeerStagedSink).  (The experimental (owner x slice) bucket mode, exchange=
+    "peer_sliced", is not part of this harness: it was measured slower in round 1 and is kept for experiments only.)"""
     monkeypatch.setenv("DBG_B200_PART_SHIFT", "10")        # many table slices per shard at test size
     reads = random_reads(171 + n, 5000, 40, 150, genome_len=25000) + [b"A" * 70] * 30 + [b"T" * 64] * 7
     bases, offs = reads_to_arrays(reads)
@@ -119,12 +133,13 @@ def test_sharded_build_reproduces_the_golden_reference_tables(dbg, name, n):
         assert np.array_equal(d[k], g[gk]), (name, n, k, fb)
 
 
-@pytest.mark.parametrize("n,P_req,n_reads", [(2, 40_000, 600), (4, 9_000, 150), (8, 5_003, 90), (3, 2_000, 40)])
+@pytest.mark.parametrize("n,P_req,n_reads", [(2, 40_000, 600), (4, 9_000, 150), (8, 5_003, 90), (3, 2_000, 24)])
 def test_sharded_layout_on_dense_and_tiny_tables(dbg, oracle_mod, n, P_req, n_reads):
     """boundary clusters that are long, that cascade, shards of a few hundred slots: the windowed layout either handles
     them or refuses (DBG_ERR_STATE) and the dump-merging fallback produces the same table"""
     reads = random_reads(900 + n, n_reads, 60, 100, genome_len=4000, err=0.03)
     bases, offs = reads_to_arrays(reads)
+    assert distinct_kmers_upper_bound(reads, 21) < 0.97 * P_req      # (an overfull table makes the oracle, like the reference, probe forever)
     o = oracle_build(oracle_mod, [(bases, offs)], 21, 100, P_req)
     assert o.count < o.size
     arr, nul, counts, fb = run_sharded(dbg, [(bases, offs)], 21, 100, P_req, n)
@@ -171,8 +186,9 @@ def test_multi_gpu_driver_builds_the_reference_table(dbg, oracle_mod, monkeypatc
 
 
 def test_multi_gpu_driver_on_a_tiny_table_uses_the_dump_merge(dbg, oracle_mod):
-    reads = random_reads(977, 60, 60, 100, genome_len=3000, err=0.03)
+    reads = random_reads(977, 36, 60, 100, genome_len=3000, err=0.03)
     files = [reads_to_arrays(reads)]
+    assert distinct_kmers_upper_bound(reads, 21) < 0.97 * 3000
     o = oracle_build(oracle_mod, files, 21, 100, 3000)
     with dbg.MultiGpuBuilder(4, K=21, max_read_len=100, init_slots=3000, devices=[0] * 4) as b:
         b.submit(*files[0])

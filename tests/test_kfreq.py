@@ -119,6 +119,59 @@ def test_cz_format_is_what_the_reference_consumer_loads(oracle_mod, tmp_path):
     assert corrected_bad != corrected
 
 
+def _genome_fasta(path, seed, n_chr, lo, hi, wrap=60):
+    """multi-line FASTA, a few chromosomes (ACGT only: construct_ref_kmer_table has no N handling, seqKmer.cpp:34-41)"""
+    rng = np.random.default_rng(seed)
+    chrs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(lo, hi)))) for _ in range(n_chr)]
+    with open(path, "wb") as f:
+        for i, c in enumerate(chrs):
+            f.write(b">chr%d some text\n" % i)
+            for j in range(0, len(c), wrap):
+                f.write(c[j:j + wrap] + b"\n")
+    return chrs
+
+
+@pytest.mark.parametrize("K", [5, 9, 12])
+def test_oracle_bit_table_equals_the_reference_table_builder(oracle_mod, tmp_path, K):
+    """SURVEY 8 a-15, CPU: the reference's own in-tree builder (construct_ref_kmer_table,
+    correct_error/simulate_lowfreq_kmer.cpp:189-260, compiled in place) on a genome FASTA vs the oracle's canonical
+    counter + the loader's reverse-complement rule: same bits, MSB-first layout included"""
+    import os
+    if not os.access(oracle_mod.KMER_TABLE_DRIVER, os.X_OK):
+        pytest.skip("oracle/_ref/ref_kmer_table_driver not built (needs /root/reference)")
+    fa = str(tmp_path / "genome.fa")
+    chrs = _genome_fasta(fa, 40 + K, 4, 300, 5000)
+    ref_bits = oracle_mod.ref_kmer_table(fa, K)
+    bases, offs = reads_to_arrays(chrs)
+    counts = oracle_mod.kfreq_count(bases, offs, K)
+    assert np.array_equal(both_strand_bits(counts, K, 0, oracle_mod), ref_bits)
+    assert int(ref_bits.sum()) > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [9, 13])
+def test_gpu_bit_table_equals_the_reference_table_builder(oracle_mod, tmp_path, K):
+    """SURVEY 8 a-15, GPU: kfreq_export(bits=1, cutoff 0) of the chromosomes + the loader's reverse-complement OR ==
+    the table construct_ref_kmer_table builds from the same genome FASTA (the reference's own code, compiled in place)"""
+    import os
+    from dbg_assembly_b200.kfreq import KmerFreq
+    if not os.access(oracle_mod.KMER_TABLE_DRIVER, os.X_OK):
+        pytest.skip("oracle/_ref/ref_kmer_table_driver not built (needs /root/reference)")
+    fa = str(tmp_path / "genome.fa")
+    chrs = _genome_fasta(fa, 70 + K, 5, 2000, 60000)
+    ref_bits = oracle_mod.ref_kmer_table(fa, K)
+    bases, offs = reads_to_arrays(chrs)
+    with KmerFreq(K=K) as kf:
+        kf.submit(bases, offs)
+        kf.finalize()
+        canon = np.unpackbits(kf.export(bits=1, cutoff=0))[: 1 << (2 * K)]
+    both = canon.copy()
+    L = oracle_mod.lib()
+    for i in np.nonzero(canon)[0].tolist():
+        both[L.orc_rev_com_kbit(int(i), K)] = 1
+    assert np.array_equal(both, ref_bits)
+
+
 @pytest.mark.gpu
 def test_gpu_table_drives_the_reference_consumer_identically(oracle_mod, tmp_path):
     """SURVEY 8c round trip: the table written by the GPU library is loaded by the shipped correct_error_reads and
