@@ -107,11 +107,11 @@ def write_workload_fasta(cfg, n_reads, path, raw=False):
     subprocess.run(cmd, check=True)
 
 
-def scratch_dir():
+def scratch_dir(need_bytes=0):
     """tmpfs when it has room (the reference reads the file through the page cache either way)"""
     for d in ("/dev/shm", None):
         try:
-            if d is None or (os.path.isdir(d) and os.statvfs(d).f_bavail * os.statvfs(d).f_frsize > (4 << 30)):
+            if d is None or (os.path.isdir(d) and os.statvfs(d).f_bavail * os.statvfs(d).f_frsize > need_bytes + (2 << 30)):
                 return tempfile.TemporaryDirectory(dir=d)
         except Exception:
             pass
@@ -129,7 +129,7 @@ def cpu_reference_run(cfg, n_reads, threads, steps, warmup, name, budget_s=None)
     init_g = cfg["init_g"] * frac             # == cfg["init_g"] for the whole workload
     vals = []
     t_start = time.perf_counter()
-    with scratch_dir() as td:
+    with scratch_dir(n_reads * (cfg["read_len"] + 14)) as td:
         if orc.have_reference():
             kind = "reference"
             path = os.path.join(td, "reads.fa")
@@ -173,13 +173,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = workload(args.workload, 1, args.scale)
+    # the same configuration as the B200 arm at this N: weak scaling, so at --gpus N the reference builds the N-GPU
+    # workload (N x genome, N x reads, N x table) -- on the host cores, it has no other way to use the box
+    n_g = max(1, args.gpus)
+    cfg_n = workload(args.workload, n_g, args.scale)
+    cfg = dict(cfg_n, genome_len=cfg_n["genome_len_total"], n_reads=cfg_n["n_reads_total"], init_g=cfg_n["init_g_total"])
     threads = os.cpu_count() or 1
     n_reads = cfg["n_reads"] if args.ref_sample_reads <= 0 else min(cfg["n_reads"], args.ref_sample_reads)
     vals, info = cpu_reference_run(cfg, n_reads, threads, args.steps, args.warmup, args.workload, budget_s=args.ref_budget_s)
     v = float(np.mean(vals))
     occ = n_reads * (cfg["read_len"] - cfg["K"] + 1)
-    cd = config_dict(args, cfg, 1)
+    cd = config_dict(args, cfg_n, n_g)
     if n_reads != cfg["n_reads"]:
         cd["reference_sample_reads"] = n_reads
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -418,6 +422,7 @@ def run_b200(args):
         nodes_total = st["global_count"]
         extra["exchange_bytes_per_step_rank0"] = sb.exchange_bytes // (args.steps + args.warmup)
         extra["optimistic_exchange_fallbacks"] = sb.opt_fallbacks
+        extra["sub_blocks_used"] = sb.sub_blocks_used
         sc_ms = float(np.mean(scatter_ms))
         if sc_ms > 0:
             # NVLink figure of the fused scatter kernel(s): bytes this rank stored into its peers' buffers / kernel time

@@ -796,7 +796,11 @@ __global__ void __launch_bounds__(BLOCK, Sink::MIN_BLOCKS) k_build(BuildArgs a, 
 // owner side of the multi-GPU exchange: received tuples arrive in source order; the same exact, atomic-free
 // radix partition (count rows -> column scan -> scatter) puts them in table-slice order for the bucketed insert
 // ---------------------------------------------------------------------------------------------------
-constexpr int TP_TILE = 4096;     // tuples per CTA
+#ifndef DBG_TP_TILE
+#define DBG_TP_TILE 2048
+#endif
+constexpr int TP_TILE = DBG_TP_TILE;     // tuples per CTA (2048: 50 KB of staging, four CTAs per SM; 4096 left only two resident)
+constexpr int TP_CTAS = TP_TILE <= 2048 ? 4 : 2;
 
 // after an optimistic scatter that did not overflow: bucket b occupies [b*capb, b*capb + fill[b]); publish the
 // strided bucket offsets the insert kernel walks and zero the keys behind the last tuple of every region (the insert
@@ -820,7 +824,7 @@ __global__ void __launch_bounds__(256) k_opt_finish(u64 *tuples, const u32 *__re
 
 // scatter pass of the tuple partition through the shared-memory staging (one batch = the CTA's tile of TP_TILE tuples)
 template <bool WIDE, bool OPT>
-__global__ void __launch_bounds__(256) k_tuple_scatter_staged(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
+__global__ void __launch_bounds__(256, TP_CTAS) k_tuple_scatter_staged(const u64 *__restrict__ src, u64 n, TableView t, int shift, u32 nb,
                                                               const u32 *__restrict__ matrix, u64 *dst, u32 *fill, u32 capb, u32 *flag)
 {
     extern __shared__ u32 tp_smem[];

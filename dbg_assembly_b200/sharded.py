@@ -345,6 +345,7 @@ class ShardedBuilder:
         self.exchange = exchange if self.n > 1 else "nccl"
         self.sub_blocks = max(1, int(sub_blocks))
         self.opt_fallbacks = 0
+        self.sub_blocks_used = None
         self._sA = self._sB = None
         self._recv_ptr = None
         self._recv_cap = 0
@@ -385,7 +386,7 @@ class ShardedBuilder:
         self._d_ptrs = torch.tensor(self._peer_ptrs, dtype=torch.int64, device=self.device)
         dist.barrier(group=self.ex.group)
 
-    def _add_reads_peer_opt(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index):
+    def _add_reads_peer_opt(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ=None):
         """optimistic fused exchange, pipelined over sub-blocks (see __init__).  Streams: A = scatter + the small
         all-gather of the fill counters (which doubles as the cross-rank barrier), B = owner-side partition + insert."""
         n, dev, rank, S = self.n, self.device, self.rank, self.sub_blocks
@@ -394,7 +395,15 @@ class ShardedBuilder:
             self._sA, self._sB = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         sA, sB = self._sA, self._sB
         cur = torch.cuda.current_stream(dev)
-        S = max(1, min(S, n_reads))
+        # a sub-block must still carry enough tuples per table slice for the owners' partitioned insert to pay (the library's
+        # path selection: tuples x 80 B (150 B with 128-bit keys) against the bytes of the shard's table); fewer, larger
+        # sub-blocks when the table is large relative to the block (K = 63: 64-B nodes)
+        from . import capi
+        P = capi.find_next_prime(max(3, int(self.P_request)))
+        table_bytes = (P + n - 1) // n * (64 if self.b.wide else 32)
+        est_tuples = int(n_occ) if n_occ else int(total_bases) * 0.8
+        S = max(1, min(S, n_reads, int(est_tuples * (150 if self.b.wide else 80) / (1.25 * table_bytes))))
+        self.sub_blocks_used = S
         cuts = [n_reads * k // S for k in range(S + 1)]
         offs_h = d_offs[torch.tensor(cuts, device=dev)].cpu().tolist()
         sub_bases = max(offs_h[k + 1] - offs_h[k] for k in range(S))
@@ -508,7 +517,7 @@ class ShardedBuilder:
         """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
         total_bases bounds the tuple count)"""
         if self.exchange == "peer":
-            return self._add_reads_peer_opt(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
+            return self._add_reads_peer_opt(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ_upper)
         if self.exchange in ("peer_exact", "peer_sliced"):
             return self._add_reads_peer(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
         from .graph import torch_stream_handle

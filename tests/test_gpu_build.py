@@ -674,15 +674,23 @@ def test_full_size_C2_contig_files_byte_identical_to_reference(dbg, build_path, 
         subprocess.run([gen, str(p.seed), str(p.genome_len), str(p.read_len), str(p.insert), str(p.err_per_2p24), str(p.n_per_2p24), "0",
                         str(c["n_reads"]), fa], check=True, timeout=600)
         lib = str(tmp_path / "c2.lib"); open(lib, "w").write(fa + "\n")
-        outs = {}
+        import json
+        import time
+        outs, wall = {}, {}
         for tag, exe in (("b200", B200_CONTIG), ("ref", ref)):
             pre = str(tmp_path / tag)
+            t0 = time.perf_counter()
             rr = subprocess.run([exe, "-k", "31", "-r", "150", "-f", "2", "-t", "1", "-i", "0.2", "-M", "100", "-o", pre, lib],
                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1500)
+            wall[tag] = round(time.perf_counter() - t0, 2)
             assert rr.returncode == 0, rr.stderr.decode()[-2000:]
             outs[tag] = {suf: open(pre + suf, "rb").read() for suf in OUT_SUFFIXES}
             if tag == "b200":
                 assert "count:\t100611066" in rr.stderr.decode()
+                wall["b200_phases"] = [l for l in rr.stderr.decode().splitlines() if l.startswith("libdbgb200 wall clock")]
+        out_dir = os.path.join(REPO, "gpurun_out")        # whole-program wall clocks, for profiles/ (scratch dir of the GPU runs)
+        if os.path.isdir(out_dir):
+            json.dump(wall, open(os.path.join(out_dir, "dropin_full_C2_wall.json"), "w"))
         for suf in OUT_SUFFIXES:
             assert outs["ref"][suf] == outs["b200"][suf], suf
         assert len(outs["ref"][".contig.seq.fa"]) > 4_000_000

@@ -166,7 +166,7 @@ def test_multi_gpu_driver_builds_the_reference_table(dbg, oracle_mod, monkeypatc
     if variant == "regrow":
         monkeypatch.setenv("DBG_B200_MG_CAP_PAIR", "256")
     if variant == "small_rounds":
-        monkeypatch.setenv("DBG_B200_MG_ROUND_BASES", "60000")
+        monkeypatch.setenv("DBG_B200_MG_ROUND_BASES", "8000")        # a round holds n x 4000 bases: >= 7 rounds per file even at n = 8
     reads = random_reads(300 + n, 4000, 40, 150, genome_len=20000) + [b"A" * 70] * 20
     files = [reads_to_arrays(reads[:2500]), reads_to_arrays(reads[2500:])]
     P_req = 300_000
@@ -180,7 +180,7 @@ def test_multi_gpu_driver_builds_the_reference_table(dbg, oracle_mod, monkeypatc
     assert (st["count"], st["occurrences"], st["reads"], st["kmers_logged"]) == (o.count, o.occurrences, o.total_reads, o.kmers_logged)
     assert not info["fallback"]
     assert (info["regrows"] > 0) == (variant == "regrow")
-    assert info["rounds"] > (2 if variant != "small_rounds" else 10) - 1
+    assert info["rounds"] >= (2 if variant != "small_rounds" else 12)
     check_against_oracle(o, arr, nul, wide)
     o.close()
 

@@ -125,3 +125,47 @@ def test_replay_matches_a_live_reference_run_that_enlarges(oracle_mod, tmp_path)
     # -e 1: the reference drops reads -> the replay refuses
     plan1, arr1, _ = replay_growth(nodes, rpf, int(init_g * 1e9), 0.7, 1, B, polyA[0], polyA[1])
     assert plan1["truncated"] == 1 and plan1["truncated_first_read"] == 300 and arr1 is None
+
+
+@pytest.mark.parametrize("name", ["contig_k31", "ragged_k31", "even_k16_two_files"])
+def test_shard_dump_merge_rebuilds_the_reference_table(oracle_mod, name):
+    """fallback of the cross-shard layout (sharded.merge_dumps_host / dbg_mg_export_kmerset): the nodes of a build dealt
+    to 3 "shards" by owner slot range -- with some overflow nodes listed twice (adopted by the neighbour AND present in the
+    tail blob), one shard's overflow nodes only inside a raw tail blob (32-byte build nodes: key, ~ordinal, eight half-float
+    counters) -- merged by replaying first occurrences on the host == the reference's table (golden fixture), k-mer-0 node
+    included.  CPU only: pins the host-side merge and the blob decoder."""
+    from dbg_assembly_b200 import capi
+    from dbg_assembly_b200.sharded import blob_margin_nodes, merge_dumps_host
+    g = load_golden(name)
+    nodes, _, polyA = full_build_nodes(oracle_mod, g)
+    P = g["size"]
+    n = 3
+    home = np.array([capi.hash_code(int(k)) % P for k in nodes["kmer"].tolist()], dtype=np.int64)
+    owner = home // ((P + n - 1) // n)
+    dumps = []
+    for r in range(n):
+        sel = owner == r
+        dumps.append({k: v[sel] for k, v in nodes.items()})
+    # shard 0 hands its last 5 nodes over as a tail blob (raw build nodes), and 2 of them also show up adopted in shard 1
+    take = 5
+    d0 = dumps[0]
+    moved = {k: v[-take:] for k, v in d0.items()}
+    dumps[0] = {k: v[:-take] for k, v in d0.items()}
+    dumps[1] = {k: np.concatenate([dumps[1][k], moved[k][:2]]) for k in dumps[1]}
+    blob = bytearray(np.array([0, take, 32, 0], dtype=np.uint64).tobytes())
+    for i in range(take):
+        cnt = np.zeros(8, dtype=np.float16)
+        for s, w in enumerate((int(moved["l"][i]), int(moved["r"][i]))):
+            for b in range(4):
+                c = (w >> (24 - 8 * b)) & 0xFF
+                cnt[4 * s + b] = 300.0 if c == 255 else float(c)          # a saturated lane holds "255 or more"
+        blob += np.array([moved["kmer"][i], ~moved["ord"][i]], dtype=np.uint64).tobytes() + cnt.tobytes()
+    extra = blob_margin_nodes(bytes(blob))
+    for k in ("kmer", "l", "r", "ord"):
+        assert np.array_equal(extra[k], moved[k]), k
+    arr, nul, plan = merge_dumps_host(dumps + [extra], g["init_slots"], g["load"], False, polyA[0], polyA[1])
+    assert plan["final_size"] == P and plan["count"] == g["count"]
+    slot = np.nonzero(np.unpackbits(nul)[:P])[0].astype(np.uint64)
+    sel = slot.astype(np.int64)
+    assert np.array_equal(slot, g["slot"]) and np.array_equal(arr["kmer"][sel], g["kmer"])
+    assert np.array_equal(arr["l_link"][sel], g["l"]) and np.array_equal(arr["r_link"][sel], g["r"])
