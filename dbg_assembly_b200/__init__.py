@@ -7,5 +7,6 @@ include/dbg_b200.h.  Everything computes on the GPU; there is no CPU fallback.
 """
 from .graph import DBGBuilder, MultiGpuBuilder, KmerSet, build_debruijn_graph, read_reads_file, NODE16, NODE32  # noqa: F401
 from . import capi, synth  # noqa: F401
+from .seedidx import SeedIndex  # noqa: F401
 
-__all__ = ["DBGBuilder", "MultiGpuBuilder", "KmerSet", "build_debruijn_graph", "read_reads_file", "capi", "synth", "NODE16", "NODE32"]
+__all__ = ["DBGBuilder", "MultiGpuBuilder", "KmerSet", "build_debruijn_graph", "read_reads_file", "capi", "synth", "NODE16", "NODE32", "SeedIndex"]

@@ -25,7 +25,7 @@ class dbg_params(C.Structure):
     _fields_ = [("K", C.c_int32), ("max_read_len", C.c_int32), ("init_slots", C.c_uint64),
                 ("load_factor", C.c_float), ("device", C.c_int32), ("track_order", C.c_int32),
                 ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("force_wide", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("payload_mode", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class dbg_stats(C.Structure):
@@ -86,6 +86,8 @@ SYMBOLS = [
     "dbg_reset", "dbg_set_stream", "dbg_synth_reads_host", "dbg_synth_reads_device", "dbg_measure_random_rmw",
     "kfreq_create", "kfreq_destroy", "kfreq_submit_reads", "kfreq_submit_reads_device", "kfreq_finalize",
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
+    "dbg_device_build_table", "seedidx_create", "seedidx_destroy", "seedidx_add_contigs", "seedidx_finalize", "seedidx_export",
+    "seedidx_align_reads", "seedidx_launch_count", "seedidx_last_error",
 ]
 
 _lib = None
@@ -179,6 +181,15 @@ def load(build_if_missing: bool = True):
         "kfreq_export": (C.c_int, [vp, i32, i32, vp]),
         "kfreq_write_cz": (C.c_int, [vp, C.c_char_p, i32, i32]),
         "kfreq_last_error": (C.c_char_p, []),
+        "dbg_device_build_table": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]),
+        "seedidx_create": (C.c_int, [C.POINTER(vp), i32, u64, C.c_float, i32]),
+        "seedidx_destroy": (None, [vp]),
+        "seedidx_add_contigs": (C.c_int, [vp, vp, vp, u64]),
+        "seedidx_finalize": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "seedidx_export": (C.c_int, [vp, vp, vp]),
+        "seedidx_align_reads": (C.c_int, [vp, vp, vp, u64, vp, i32, vp]),
+        "seedidx_launch_count": (u64, [vp]),
+        "seedidx_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdbgb200.so")
-SOURCES = ["dbg_build.cu", "dbg_multi.cu", "synth.cu", "kfreq.cu", "growth_host.cu", "checkpoint_host.cu"]
+SOURCES = ["dbg_build.cu", "dbg_multi.cu", "synth.cu", "kfreq.cu", "seedidx.cu", "growth_host.cu", "checkpoint_host.cu"]
 HEADERS = ["dbg_core.cuh", "dbg_kernels.cuh", "synth_core.h", os.path.join(REPO, "include", "dbg_b200.h")]
 
 NVCC_FLAGS = [

@@ -290,6 +290,9 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (p->K < 1 || p->K > 63) return set_err(DBG_ERR_INVALID, "K=%d outside 1..63", p->K);
     if (p->max_read_len < 1 || p->max_read_len > 65535) return set_err(DBG_ERR_INVALID, "max_read_len=%d outside 1..65535", p->max_read_len);
     int n_shards = p->shard_count > 1 ? p->shard_count : 1;
+    if (p->payload_mode != 0 && p->payload_mode != 1) return set_err(DBG_ERR_INVALID, "payload_mode=%d", p->payload_mode);
+    if (p->payload_mode == 1 && (p->K > 31 || p->force_wide || n_shards > 1 || !p->track_order))
+        return set_err(DBG_ERR_INVALID, "the seed index needs K <= 31, one shard and track_order");
     if (p->shard_rank < 0 || p->shard_rank >= n_shards) return set_err(DBG_ERR_INVALID, "shard_rank %d / %d", p->shard_rank, n_shards);
     int ndev = dbg_device_count();
     if (ndev == 0) return set_err(DBG_ERR_CUDA, "no CUDA device visible: libdbgb200 has no CPU fallback");
@@ -687,7 +690,7 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     BuildArgs a;
     a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
     a.chunk_first = c->d_chunk_first; a.read_index0 = read_index0; a.K = c->prm.K; a.R = c->prm.max_read_len;
-    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1; a.seed = c->prm.payload_mode == 1;
 
     if (part) {
         rc = c->wide ? run_partitioned<true>(c, a, n_chunks, total_bases, s) : run_partitioned<false>(c, a, n_chunks, total_bases, s);
@@ -890,7 +893,7 @@ static int rank_phase(dbg_ctx *c, int phase, const char *d_bases, const u64 *d_o
     BuildArgs a;
     a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
     a.chunk_first = c->d_chunk_first; a.read_index0 = read_index0; a.K = c->prm.K; a.R = c->prm.max_read_len;
-    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1; a.seed = c->prm.payload_mode == 1;
     if (phase == 1) {
         unsigned gb = (unsigned)((n_reads + 1 + 255) / 256);
         k_chunk_first<<<gb, 256, 0, s>>>(d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
@@ -1153,7 +1156,7 @@ extern "C" int dbg_exchange_scatter_opt_device(dbg_ctx *c, const char *d_bases, 
     BuildArgs a;
     a.bases = d_bases; a.offs = (const u64 *)d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
     a.chunk_first = c->d_chunk_first; a.read_index0 = first_read_index; a.K = c->prm.K; a.R = c->prm.max_read_len;
-    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1; a.seed = c->prm.payload_mode == 1;
     const uint64_t div = (c->P + n_parts - 1) / n_parts;
     if (c->wide) {
         StagedScatterSink<true, true> st; st.t = view_of(c); st.shift = 0; st.n_buckets = (uint32_t)n_parts; st.cap = cap0; st.matrix = nullptr; st.tuples = nullptr;
@@ -1277,7 +1280,7 @@ static int fill_stats(dbg_ctx *c, const u64 *cnt)
 {
     dbg_stats &s = c->st;
     s.array_size = c->P; s.max_cutoff = c->max_cutoff; s.load_factor = c->lf; s.wide = c->wide;
-    s.count = cnt[CNT_NEW] + (c->finalized && (c->n_shards <= 1) ? 1 : 0);
+    s.count = cnt[CNT_NEW] + (c->finalized && (c->n_shards <= 1) && c->prm.payload_mode != 1 ? 1 : 0);
     s.conflict = cnt[CNT_CONFLICT]; s.reads = c->reads_total; s.kmers_logged = cnt[CNT_LOGGED]; s.occurrences = cnt[CNT_OCC];
     s.polyA_l = (uint32_t)c->polyA_links; s.polyA_r = (uint32_t)(c->polyA_links >> 32);
     s.shard_lo = c->shard_lo; s.shard_hi = c->shard_hi;
@@ -1379,9 +1382,12 @@ static int run_layout(dbg_ctx *c)
         if (rc) return rc;
         c->layout_regions = UINT32_MAX;
     }
-    k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
+    // (seed index, payload_mode 1: k-mer 0 is an ordinary key there -- csrc/seedidx.cu places it by its first occurrence)
+    if (c->prm.payload_mode != 1) {
+        k_polyA_insert<WIDE><<<1, 32, 0, c->stream>>>(c->P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+    }
     return DBG_OK;
 }
 
@@ -1694,6 +1700,15 @@ extern "C" int dbg_device_image(dbg_ctx *c, void **d_array, void **d_nul_flag)
     if (!c->finalized || !c->d_out || c->n_shards > 1) return set_err(DBG_ERR_STATE, "no finalized image (unsharded contexts only; sharded: dbg_shard_slice_info)");
     if (d_array) *d_array = c->d_out;
     if (d_nul_flag) *d_nul_flag = c->d_nul32;
+    return DBG_OK;
+}
+
+extern "C" int dbg_device_build_table(dbg_ctx *c, void **d_nodes, uint64_t *n_local, uint64_t **d_polyA)
+{
+    if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    if (d_nodes) *d_nodes = c->d_nodes;
+    if (n_local) *n_local = c->n_local;
+    if (d_polyA) *d_polyA = (uint64_t *)c->d_polyA;
     return DBG_OK;
 }
 

@@ -53,7 +53,22 @@ struct BuildArgs {
     int K, R;
     u32 stage_words;          // packed words staged per chunk (incl. slack)
     int count_stats;          // add this launch's reads/occurrences to the context counters
+    int seed;                 // 1: contig seed index (link_scaffold/map_func.cpp:119-172): occurrences carry no neighbour bases but
+                              // the strand of the k-mer (ordinal << 1 | direct) and count into lane 0; tie -> direct 0
 };
+
+// seed-index occurrences (BuildArgs::seed): lb = 0 (the occurrence count lives in l lane A), rb = RB_SEED: "no right
+// neighbour" for every insert path (rb >= 4), and the mark by which the k-mer-0 side node also keeps its first ordinal
+constexpr u32 RB_SEED = 5;
+
+// the k-mer-0 side node (DBGgraph.cpp:153-164): counts above 255 change nothing after clamping, so stop adding once a
+// lane is saturated (bounds contention).  Seed index: polyA[0] counts the occurrences, polyA[7] keeps ~(first ordinal).
+__device__ __forceinline__ void polyA_bump(u64 *polyA, u32 lb, u32 rb, u64 ord)
+{
+    if (lb < 4 && __ldcg(polyA + lb) < 255) atomicAdd(polyA + lb, 1ULL);
+    if (rb < 4 && __ldcg(polyA + 4 + rb) < 255) atomicAdd(polyA + 4 + rb, 1ULL);
+    if (rb == RB_SEED && ~ord > __ldcg(polyA + 7)) atomicMax(polyA + 7, ~ord);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // chunk index: chunk_first[c] = first read whose start offset lies in chunk >= c
@@ -185,10 +200,8 @@ struct InsertSink {
 
     __device__ __forceinline__ void polyA(const Occ &o)
     {
-        // k-mer 0 never enters the table during the build (DBGgraph.cpp:153-164).  Counts above 255
-        // change nothing after clamping, so stop adding once a lane is saturated (bounds contention).
-        if (o.lb < 4 && __ldcg(t.polyA + o.lb) < 255) atomicAdd(t.polyA + o.lb, 1ULL);
-        if (o.rb < 4 && __ldcg(t.polyA + 4 + o.rb) < 255) atomicAdd(t.polyA + 4 + o.rb, 1ULL);
+        // k-mer 0 never enters the table during the build (DBGgraph.cpp:153-164)
+        polyA_bump(t.polyA, o.lb, o.rb, o.ord);
     }
 
     __device__ __forceinline__ void consume(const Occ (&o)[G], int nv)
@@ -260,8 +273,7 @@ struct PartitionSink {
             if (g < nv) {
                 if ((o[g].klo | o[g].khi) == 0) {
                     if (MODE == 1) {   // the k-mer-0 side node is accumulated once, in the scatter pass
-                        if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
-                        if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                        polyA_bump(t.polyA, o[g].lb, o[g].rb, o[g].ord);
                     }
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
@@ -467,8 +479,7 @@ struct StagedScatterSink {
             bkt[g] = 0xffffffffu;
             if (g < nv) {
                 if ((o[g].klo | o[g].khi) == 0) {
-                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
-                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                    polyA_bump(t.polyA, o[g].lb, o[g].rb, o[g].ord);
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
                     const u64 home = mod_P(hh, t.P, t.M);
@@ -542,8 +553,7 @@ struct PeerStagedSink {
             bkt[g] = 0xffffffffu; rank[g] = 0;
             if (g < nv) {
                 if ((o[g].klo | o[g].khi) == 0) {     // the k-mer-0 side node is accumulated here, once
-                    if (o[g].lb < 4 && __ldcg(t.polyA + o[g].lb) < 255) atomicAdd(t.polyA + o[g].lb, 1ULL);
-                    if (o[g].rb < 4 && __ldcg(t.polyA + 4 + o[g].rb) < 255) atomicAdd(t.polyA + 4 + o[g].rb, 1ULL);
+                    polyA_bump(t.polyA, o[g].lb, o[g].rb, o[g].ord);
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
                     u64 home = mod_P(hh, t.P, t.M);
@@ -774,6 +784,11 @@ __global__ void __launch_bounds__(BLOCK, Sink::MIN_BLOCKS) k_build(BuildArgs a, 
                         q.lb = (right < 4) ? 3 - right : 4u;
                     }
                     q.ord = ((a.read_index0 + rb + i) << 16) | j;
+                    if (a.seed) {
+                        // chop_contig_to_kmerset, map_func.cpp:154-163: direct = 1 only for kbit < rc_kbit (a tie is direct 0)
+                        const bool direct = WIDE ? (fhi < rhi || (fhi == rhi && flo < rlo)) : (flo < rlo);
+                        q.lb = 0; q.rb = RB_SEED; q.ord = (q.ord << 1) | (direct ? 1u : 0u);
+                    }
                     j++; nv = g + 1;
                 }
             }

@@ -186,7 +186,7 @@ static int kfreq_count_device(kfreq_ctx *c, const char *d_bases, const u64 *d_of
     a.bases = d_bases; a.offs = d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
     a.chunk_first = c->d_chunk_first; a.read_index0 = 0; a.K = c->K; a.R = c->max_read_len;
     a.stage_words = (uint32_t)(((CB + ((a.R + 15) / 16) * 16) / 16 + 8 + 1) & ~1);
-    a.count_stats = 1;
+    a.count_stats = 1; a.seed = 0;
     FreqSink sk;
     sk.t.nodes = nullptr; sk.t.P = 1; sk.t.M = 0; sk.t.lo = 0; sk.t.n_local = 0; sk.t.counters = c->d_counters; sk.t.polyA = nullptr;
     sk.table = c->d_table; sk.lo = c->lo; sk.hi = c->hi;

@@ -334,6 +334,7 @@ class ShardedBuilder:
                             track_order=track_order, shard_rank=self.rank, shard_count=self.n)
         self.device = torch.device("cuda", device)
         self.P_request, self.load_factor = init_slots, load_factor
+        self.K, self.max_read_len = int(K), int(max_read_len)
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
         self._send = self._counts = None
         self.exchange_bytes = 0
@@ -406,11 +407,18 @@ class ShardedBuilder:
         self.sub_blocks_used = S
         cuts = [n_reads * k // S for k in range(S + 1)]
         offs_h = d_offs[torch.tensor(cuts, device=dev)].cpu().tolist()
-        sub_bases = max(offs_h[k + 1] - offs_h[k] for k in range(S))
-        want = torch.tensor([int(sub_bases / n * 1.25) + 4096], dtype=torch.int64, device=dev)
+        # region size: the sub-block's OCCURRENCES (sum of min(len, -r) - K + 1 over its reads, counted on the device), not its
+        # bases (100-bp reads at K = 63 carry 38 occurrences per 100 bases: sizing by bases took 96 GB of receive buffers on
+        # C3); a region that is too small is detected and the sub-block redone exactly, so the estimate only has to be good
+        lens = (d_offs[1:n_reads + 1] - d_offs[:n_reads]).clamp(max=int(self.max_read_len))
+        occ_cum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), (lens - (self.K - 1)).clamp(min=0).cumsum(0)])
+        occ_h = occ_cum[torch.tensor(cuts, device=dev)].cpu().tolist()
+        sub_occ = max(occ_h[k + 1] - occ_h[k] for k in range(S))
+        want = torch.tensor([int(sub_occ / n * 1.25) + 4096], dtype=torch.int64, device=dev)
         dist.all_reduce(want, op=dist.ReduceOp.MAX, group=self.ex.group)
         cap_pair = int(want.item())
-        self._ensure_peers(2 * n * cap_pair)
+        n_sets = 2 if S > 1 else 1                                  # double buffering only when there is something to overlap
+        self._ensure_peers(n_sets * n * cap_pair)
         d_ptrs = self._d_ptrs
         fills = [torch.zeros(n + 1, dtype=torch.int32, device=dev) for _ in range(S)]
         allfill = [torch.empty(n * (n + 1), dtype=torch.int32, device=dev) for _ in range(S)]
@@ -444,7 +452,7 @@ class ShardedBuilder:
                 with torch.cuda.stream(sB):
                     recv_total += self._add_reads_peer(d_bases, d_offs[r0:], r1 - r0, offs_h[k], offs_h[k + 1] - offs_h[k], first_read_index + r0)
                 torch.cuda.synchronize(dev)
-                self._ensure_peers(2 * n * cap_pair)
+                self._ensure_peers(n_sets * n * cap_pair)
                 d_ptrs = self._d_ptrs
                 if k + 1 < S:
                     scatter(k + 1)

@@ -58,7 +58,9 @@ typedef struct {
     int32_t  shard_rank;     /* multi-GPU: this context owns home slots [rank*ceil(P/n), ...) of the P-slot  */
     int32_t  shard_count;    /* table; 0/1 = unsharded                                                       */
     int32_t  force_wide;     /* 1: use the 128-bit path even for K <= 31 (tests pin it against the 64-bit)   */
-    int32_t  reserved[5];
+    int32_t  payload_mode;   /* 0: De Bruijn graph nodes (link lanes); 1: contig seed index (seedidx_* below use it):
+                                occurrences carry their strand instead of neighbour bases, k-mer 0 is an ordinary key  */
+    int32_t  reserved[4];
 } dbg_params;
 
 typedef struct {
@@ -241,6 +243,9 @@ int  dbg_dump_shard(dbg_ctx *ctx, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32
 
 /* device pointers of the finalized image, for callers that stay on the GPU (bench, multi-GPU gather) */
 int  dbg_device_image(dbg_ctx *ctx, void **d_array, void **d_nul_flag);
+/* the BUILD table behind it (n_local nodes of 32 B {kmer, ~first ordinal, 8 half-float counts}, 64 B on the wide path) and the
+ * 8 side counters of the k-mer-0 node; any pointer may be NULL */
+int  dbg_device_build_table(dbg_ctx *ctx, void **d_nodes, uint64_t *n_local, uint64_t **d_polyA);
 
 /* per-phase device time of the most recent calls, milliseconds (CUDA events on the ctx stream):
  * [0] table clear, [1] build kernels (sum over blocks), [2] layout+polyA (finalize), [3] links pass,
@@ -336,6 +341,31 @@ int  kfreq_export(kfreq_ctx *ctx, int32_t bits, int32_t cutoff, uint8_t *out);
 /* <prefix>.kmer.freq.cz, <prefix>.kmer.freq.cz.len, and (when the context owns all of 4^K) <prefix>.kmer.freq.stat */
 int  kfreq_write_cz(kfreq_ctx *ctx, const char *prefix, int32_t bits, int32_t cutoff);
 const char *kfreq_last_error(void);
+
+/* ---- contig seed index of link_scaffold (csrc/seedidx.cu) -----------------------------------------
+ * The k-mer -> {contig id, position, unique?, strand} hash that map_pair / map_reads build from the contigs
+ * (link_scaffold/map_pair.cpp:122-125: init_kmerset(3 x contig length, 0.5) + chop_contig_to_kmerset, map_func.cpp:119-172,
+ * kmerSet.cpp:82-107,168-210) and probe with read k-mers (get_align_seed, map_func.cpp:181-237).  The exported table is the
+ * reference's KmerSet byte for byte (same size, same slots): nodes {u64 kmer; u64 id:32, pos:30, freq:1, direct:1}
+ * (kmerSet.h:53-60, GCC bit-field layout: value = id | pos << 32 | freq << 62 | direct << 63) + nul_flag[size/8+1], MSB first.
+ * K <= 31.  Contigs are ASCII [ACGTNacgtn]; runs of upper-case 'N' separate blocks (scaffold_to_contig), blocks shorter than
+ * K are skipped (the reference's loop is undefined there).  A table that the reference would enlarge (count >= size *
+ * load_factor) is refused with DBG_ERR_TABLE_FULL. */
+typedef struct seedidx_ctx seedidx_ctx;
+typedef struct { uint64_t kmer; uint64_t value; } seed_node16;
+int  seedidx_create(seedidx_ctx **ctx, int32_t K, uint64_t init_slots, float load_factor, int32_t device);
+void seedidx_destroy(seedidx_ctx *ctx);
+/* contigs seqs[offs[i] .. offs[i+1]); contig ids continue across calls; an empty sequence keeps its id (map_pair.cpp:100-110) */
+int  seedidx_add_contigs(seedidx_ctx *ctx, const char *seqs, const uint64_t *offs, uint64_t n_contigs);
+int  seedidx_finalize(seedidx_ctx *ctx, uint64_t *size, uint64_t *count, uint64_t *max_cutoff);
+int  seedidx_export(seedidx_ctx *ctx, void *array, uint8_t *nul_flag);
+/* get_align_seed(read, search_start[i] (NULL: 1), read length) for a batch of reads (each <= 65535 bases):
+ * out[6 i ..] = {contig_id_index, seed_contig_start, seed_contig_end, seed_read_start, seed_read_end, 'F' | 'R' | 'N'},
+ * the first five -1 when no seed is found */
+int  seedidx_align_reads(seedidx_ctx *ctx, const char *bases, const uint64_t *offs, uint64_t n_reads, const int32_t *search_start,
+                         int32_t seed_kmer_num, int32_t *out);
+uint64_t seedidx_launch_count(const seedidx_ctx *ctx);
+const char *seedidx_last_error(void);
 
 /* ---- roofline denominators measured on the spot (bench.py) --------------------------------------- */
 /* uniformly random 32-B sector read-modify-writes over `bytes` of device memory, `n_ops` operations;

@@ -290,3 +290,114 @@ def run_ref_build(files, K, max_read_len, init_g, threads=1, load=0.7, max_doubl
             d = dict(size=size, count=count, slot=rec["slot"].copy(), kmer=rec["kmer"].copy(),
                      l=rec["l"].copy(), r=rec["r"].copy())
         return stats, d
+
+
+# ---------------------------------------------------------------------------------------------------
+# f-4: contig seed index of link_scaffold (oracle/seed_oracle.c; reference through oracle/_ref/ref_seed_driver)
+# ---------------------------------------------------------------------------------------------------
+SEED_DRIVER = os.path.join(REF_DIR, "ref_seed_driver")
+SEED_NODE = np.dtype([("kmer", "<u8"), ("value", "<u8")])     # value = id | pos << 32 | freq << 62 | direct << 63
+
+
+def _seed_lib():
+    L = lib()
+    if not hasattr(L, "_seed_ready"):
+        u64 = C.c_uint64
+        L.orc_seed_create.restype = C.c_void_p; L.orc_seed_create.argtypes = [C.c_int, u64, C.c_float]
+        L.orc_seed_destroy.restype = None; L.orc_seed_destroy.argtypes = [C.c_void_p]
+        L.orc_seed_add_contigs.restype = C.c_int; L.orc_seed_add_contigs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64, u64]
+        for name in ("size", "count", "max", "conflict"):
+            f = getattr(L, "orc_seed_" + name); f.restype = u64; f.argtypes = [C.c_void_p]
+        L.orc_seed_array.restype = C.c_void_p; L.orc_seed_array.argtypes = [C.c_void_p]
+        L.orc_seed_nul_flag.restype = C.c_void_p; L.orc_seed_nul_flag.argtypes = [C.c_void_p]
+        L.orc_seed_align.restype = None
+        L.orc_seed_align.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L._seed_ready = True
+    return L
+
+
+def seqs_to_arrays(seqs):
+    """list of bytes -> (uint8 bases, uint64 offsets)"""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+    bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(0, dtype=np.uint8)
+    return bases, offs
+
+
+class SeedOracle:
+    """init_kmerset + chop_contig_to_kmerset + get_align_seed, sequential (link_scaffold/map_func.cpp, kmerSet.cpp)"""
+
+    def __init__(self, K, init_size, load_factor=0.5):
+        self.L = _seed_lib()
+        self.K = K
+        self.h = self.L.orc_seed_create(K, int(init_size), float(load_factor))
+
+    def add_contigs(self, seqs, id0=0):
+        bases, offs = seqs_to_arrays(seqs)
+        if bases.size == 0:
+            bases = np.zeros(1, dtype=np.uint8)
+        return int(self.L.orc_seed_add_contigs(self.h, bases.ctypes.data, offs.ctypes.data, len(seqs), int(id0)))
+
+    def __getattr__(self, name):
+        if name in ("size", "count", "max", "conflict"):
+            return int(getattr(self.L, "orc_seed_" + name)(self.h))
+        raise AttributeError(name)
+
+    def array(self):
+        n = self.size
+        buf = (C.c_uint8 * (n * 16)).from_address(self.L.orc_seed_array(self.h))
+        return np.frombuffer(buf, dtype=SEED_NODE, count=n).copy()
+
+    def nul_flag(self):
+        n = self.size // 8 + 1
+        buf = (C.c_uint8 * n).from_address(self.L.orc_seed_nul_flag(self.h))
+        return np.frombuffer(buf, dtype=np.uint8, count=n).copy()
+
+    def align(self, reads, seed_kmer_num=5):
+        """get_align_seed(read, 1, len) for every read long enough (map_pair.cpp:284) -> int32 [n, 6]"""
+        out = np.full((len(reads), 6), -1, dtype=np.int32)
+        out[:, 5] = ord("N")
+        rec = np.zeros(6, dtype=np.int32)
+        for i, r in enumerate(reads):
+            if len(r) >= self.K + seed_kmer_num:
+                self.L.orc_seed_align(self.h, r, len(r), 1, len(r), int(seed_kmer_num), rec.ctypes.data)
+                out[i] = rec
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.orc_seed_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def have_seed_reference() -> bool:
+    return os.access(SEED_DRIVER, os.X_OK)
+
+
+def run_ref_seed(contig_names, contig_seqs, reads, K, min_ctg_len, seed_kmer_num=5, hash_size=None, timeout=600):
+    """the reference's own seed index (oracle/_ref/ref_seed_driver) -> dict(size, count, max, conflict, array, nul, seeds)"""
+    with tempfile.TemporaryDirectory() as td:
+        fa, rd, out = os.path.join(td, "c.fa"), os.path.join(td, "r.txt"), os.path.join(td, "o")
+        with open(fa, "wb") as f:
+            for n, s in zip(contig_names, contig_seqs):
+                f.write(b">" + n + b"\n" + s + b"\n")
+        with open(rd, "wb") as f:
+            for r in reads:
+                f.write(r + b"\n")
+        cmd = [SEED_DRIVER, str(K), str(min_ctg_len), str(seed_kmer_num), fa, rd, out]
+        if hash_size is not None:
+            cmd.append(str(int(hash_size)))
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
+        raw = open(out + ".table", "rb").read()
+        size, count, mx, conflict = struct.unpack("<QQQQ", raw[:32])
+        array = np.frombuffer(raw, dtype=SEED_NODE, offset=32, count=size).copy()
+        nul = np.frombuffer(raw, dtype=np.uint8, offset=32 + 16 * size, count=size // 8 + 1).copy()
+        seeds = np.fromfile(out + ".seeds", dtype=np.int32).reshape(-1, 6)
+    return dict(size=size, count=count, max=mx, conflict=conflict, array=array, nul=nul, seeds=seeds)

@@ -21,7 +21,7 @@ def capi():
 def header_symbols():
     txt = open(os.path.join(REPO, "include", "dbg_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    names = re.findall(r"\b((?:dbg|kfreq)_[a-z0-9_A-Z]+)\s*\(", txt)
+    names = re.findall(r"\b((?:dbg|kfreq|seedidx)_[a-z0-9_A-Z]+)\s*\(", txt)
     return sorted(set(names))
 
 
