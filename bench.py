@@ -518,10 +518,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / e_steps
         tm = b2.timings()
+        xi = b2.export_info()
         line["e2e"] = {"value": s2["occurrences"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * L + (n + 1) * 8),
-                       "d2h_bytes_per_step": int(P * nbytes_node + P // 8 + 1), "ms_per_step": dt * 1e3, "steps": e_steps,
+                       "d2h_bytes_per_step": int(xi["link_bytes"]), "ms_per_step": dt * 1e3, "steps": e_steps,
                        "h2d_ms": tm["h2d_ms"], "d2h_ms": tm["d2h_ms"], "build_ms": tm["build_ms"], "layout_ms": tm["layout_ms"],
-                       "what": "dbg_submit_reads (pinned host reads) -> dbg_finalize -> dbg_export_kmerset (KmerSet image into pinned host memory); wall clock"}
+                       "result_bytes_on_host": int(P * nbytes_node + P // 8 + 1), "export": xi,
+                       "what": "dbg_submit_reads (pinned host reads) -> dbg_finalize -> dbg_export_kmerset (the whole P-slot KmerSet image + nul_flag "
+                               "land in pinned host memory; occupied nodes travel compact and host threads of the library expand them, "
+                               "chunks the host cannot absorb travel as plain image bytes: export.chunks_compact / chunks_plain); wall clock"}
         b2.close()
         for hb in (h_bases, h_offs, h_arr, h_nul):
             hb.close()

@@ -88,6 +88,7 @@ SYMBOLS = [
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
     "dbg_device_build_table", "seedidx_create", "seedidx_destroy", "seedidx_add_contigs", "seedidx_finalize", "seedidx_export",
     "seedidx_align_reads", "seedidx_launch_count", "seedidx_last_error",
+    "dbg_export_info", "dbg_host_expand_nodes",
 ]
 
 _lib = None
@@ -190,6 +191,8 @@ def load(build_if_missing: bool = True):
         "seedidx_align_reads": (C.c_int, [vp, vp, vp, u64, vp, i32, vp]),
         "seedidx_launch_count": (u64, [vp]),
         "seedidx_last_error": (C.c_char_p, []),
+        "dbg_export_info": (C.c_int, [vp, vp]),
+        "dbg_host_expand_nodes": (u64, [vp, u64, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -233,6 +236,11 @@ def host_polyA_insert(array: np.ndarray, nul_flag: np.ndarray, P: int, wide: boo
     check(load().dbg_host_polyA_insert(array.ctypes.data, nul_flag.ctypes.data, int(P), int(bool(wide)), int(l_link), int(r_link),
                                        C.byref(s)), "dbg_host_polyA_insert")
     return int(s.value)
+
+
+def host_expand_nodes(bits: np.ndarray, n_slots: int, nodes: np.ndarray, array: np.ndarray, wide: bool) -> int:
+    """array[s] = next node of `nodes` where bit s of `bits` (MSB first) is set, else 0 (the host half of the pipelined export)"""
+    return int(load().dbg_host_expand_nodes(bits.ctypes.data, int(n_slots), nodes.ctypes.data, array.ctypes.data, int(bool(wide))))
 
 
 def hash_code_wide(lo: int, hi: int) -> int:

@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdbgb200.so")
-SOURCES = ["dbg_build.cu", "dbg_multi.cu", "synth.cu", "kfreq.cu", "seedidx.cu", "growth_host.cu", "checkpoint_host.cu"]
-HEADERS = ["dbg_core.cuh", "dbg_kernels.cuh", "synth_core.h", os.path.join(REPO, "include", "dbg_b200.h")]
+SOURCES = ["dbg_build.cu", "dbg_multi.cu", "synth.cu", "kfreq.cu", "seedidx.cu", "growth_host.cu", "checkpoint_host.cu",
+           "export_pipe.cu", "export_expand.cpp"]
+HEADERS = ["dbg_core.cuh", "dbg_kernels.cuh", "synth_core.h", "export_pipe.h", os.path.join(REPO, "include", "dbg_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,7 @@
 
 #include "../../include/dbg_b200.h"
 #include "dbg_kernels.cuh"
+#include "export_pipe.h"
 
 using namespace dbg;
 
@@ -171,6 +172,7 @@ struct dbg_ctx {
     LayoutInfo *d_layout_info;
     LayoutRegion *d_regions;
     int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
+    int pipeline;                  // env DBG_B200_PIPELINE (default 1): a large dbg_submit_reads call scatters sub-block i while sub-block i+1 is copied
     int optimistic;                // env DBG_B200_OPTIMISTIC (default 1): single-pass partition with fixed bucket regions first
     int opt_capb;                  // env DBG_B200_OPT_CAPB: force the region size (tests: provoke the overflow fallback)
     u32 *d_fill = nullptr;         // [n_buckets] tuples per bucket + [n_buckets] overflow flag
@@ -197,6 +199,8 @@ struct dbg_ctx {
     std::vector<EvPair> build_ev;
     std::vector<cudaEvent_t> ev_all, ev_free_list;   // every timing event this context ever created / the idle ones
     float ms[8];
+    ExportPipe *pipe = nullptr;    // pipelined export (export_pipe.cu): pinned ring, compact buffer, host worker threads
+    uint64_t export_info[4] = {0, 0, 0, 0};   // last dbg_export_kmerset: chunks sent compact, chunks sent plain, bytes over the link, nodes
 };
 
 static int node_bytes(const dbg_ctx *c) { return c->wide ? 32 : 16; }            // export image
@@ -251,6 +255,7 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    export_pipe_destroy(c->pipe);
     free_finalize_buffers(c);
     for (cudaEvent_t e : c->ev_all) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
@@ -333,6 +338,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     if (const char *e = getenv("DBG_B200_BATCH_READS")) { uint64_t v = strtoull(e, nullptr, 10); if (v >= 1) c->cap_reads = v; }
     if (c->sub_bases > c->cap_bases) c->sub_bases = c->cap_bases;
     if (c->sub_reads > c->cap_reads) c->sub_reads = c->cap_reads;
+    c->pipeline = getenv("DBG_B200_PIPELINE") ? atoi(getenv("DBG_B200_PIPELINE")) : 1;
     c->optimistic = getenv("DBG_B200_OPTIMISTIC") ? atoi(getenv("DBG_B200_OPTIMISTIC")) : 1;
     c->opt_capb = getenv("DBG_B200_OPT_CAPB") ? atoi(getenv("DBG_B200_OPT_CAPB")) : 0;
     c->stage_cap = getenv("DBG_B200_STAGE_CAP") ? atoi(getenv("DBG_B200_STAGE_CAP")) : -1;
@@ -777,6 +783,134 @@ static int flush_batch(dbg_ctx *c)
     return DBG_OK;
 }
 
+// One dbg_submit_reads call that is a whole partitioned block by itself (front ends that hand over a file's worth of reads,
+// bench e2e): pipeline it.  The optimistic scatter appends to fixed bucket regions, so it can run sub-block by sub-block --
+// the extraction + partition of sub-block i overlaps the host->device copy of sub-block i+1 -- and ONE bucketed insert
+// follows the last scatter.  Same table as the one-launch build (ordinals are global read indices); an overflowing region
+// falls back to the exact partition of the whole (device-resident) batch.
+template <bool WIDE>
+static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
+{
+    const uint64_t call_bases = offs[n_reads] - offs[0];
+    const int b = c->cur;
+    const uint32_t nb = c->n_buckets;
+    const uint32_t cap0 = stage_cap(c, WIDE);
+    const uint64_t capb64 = (c->opt_capb > 0 ? (uint64_t)c->opt_capb : c->cap_tuples / nb) / INS_TILE * INS_TILE;
+    const uint32_t capb = (uint32_t)capb64;
+    cudaStream_t s = c->stream;
+    int rc = DBG_OK;
+    if (!c->d_fill) {
+        CU_TRY(cudaMalloc(&c->d_fill, ((size_t)4096 + 1) * sizeof(u32)));
+        CU_TRY(cudaMalloc(&c->d_snap, (CNT_N + 8) * sizeof(u64)));
+        CU_TRY(cudaMallocHost(&c->h_flag, sizeof(u32)));
+    }
+    c->guard_total += call_bases;
+    c->batch_read_index0 = c->next_read_index;
+    CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemsetAsync(c->d_fill, 0, ((size_t)nb + 1) * sizeof(u32), s));
+    EvPair ev_build, ev_copy;
+    rc = ev_begin(c, s, &ev_build);
+    if (rc) return rc;
+    rc = ev_begin(c, c->copy_stream, &ev_copy);
+    if (rc) return rc;
+    std::vector<cudaEvent_t> sub_ev;
+    const uint64_t SUB_BASES = c->sub_bases, SUB_READS = c->sub_reads;
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        uint64_t lim = r0 + SUB_READS < n_reads ? r0 + SUB_READS : n_reads;
+        uint64_t lo = r0 + 1, hi = lim;
+        while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offs[mid] - offs[r0] <= SUB_BASES) lo = mid; else hi = mid - 1; }
+        const uint64_t r1 = lo;
+        if (offs[r1] < offs[r0]) return set_err(DBG_ERR_INVALID, "offsets must be non-decreasing");
+        const uint64_t nbases = offs[r1] - offs[r0], nr = r1 - r0;
+        if (c->batch_bases + nbases > c->cap_bases || c->batch_reads + nr > c->cap_reads)
+            return set_err(DBG_ERR_INVALID, "a single read longer than the sub-block size inside a pipelined submit");
+        if (nbases) CU_TRY(cudaMemcpyAsync(c->d_bases[b] + c->batch_bases, bases + offs[r0], nbases, cudaMemcpyHostToDevice, c->copy_stream));
+        // (one staging buffer for the offsets: the copy stream runs copy -> append in order, so it is free again when the
+        // next sub-block's offsets arrive)
+        CU_TRY(cudaMemcpyAsync(c->d_offs_stage, offs + r0, (nr + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->copy_stream));
+        k_append_offs<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, c->copy_stream>>>(c->d_offs_stage, nr, c->d_offs[b] + c->batch_reads, c->batch_bases);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        cudaEvent_t e;
+        rc = ev_get(c, &e);
+        if (rc) return rc;
+        sub_ev.push_back(e);
+        CU_TRY(cudaEventRecord(e, c->copy_stream));
+        CU_TRY(cudaStreamWaitEvent(s, e, 0));
+        if (nbases) {
+            const uint64_t first_base = c->batch_bases, abase = first_base & ~15ull;
+            const uint64_t n_chunks = (first_base + nbases - abase + CB - 1) / CB;
+            rc = ensure_chunks(c, n_chunks);     // (grows with a device-wide synchronize, so launches in flight are safe)
+            if (rc) return rc;
+            k_chunk_first<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, s>>>(c->d_offs[b] + c->batch_reads, nr, abase, n_chunks, c->d_chunk_first);
+            CU_TRY(cudaGetLastError());
+            c->launches++;
+            BuildArgs a;
+            a.bases = c->d_bases[b]; a.offs = c->d_offs[b] + c->batch_reads; a.n_reads = nr; a.abase = abase; a.end_base = first_base + nbases;
+            a.chunk_first = c->d_chunk_first; a.read_index0 = c->batch_read_index0 + c->batch_reads; a.K = c->prm.K; a.R = c->prm.max_read_len;
+            a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1; a.seed = c->prm.payload_mode == 1;
+            StagedScatterSink<WIDE, true> st; st.t = view_of(c); st.shift = c->part_shift; st.n_buckets = nb; st.cap = cap0;
+            st.matrix = nullptr; st.tuples = c->d_tuples; st.fill = c->d_fill; st.capb = capb; st.flag = c->d_fill + nb; st.filled = 0;
+            rc = launch_build<WIDE>(c, a, st, n_chunks, s, 0, StageBuf<WIDE>::bytes(cap0, nb));
+            if (rc) return rc;
+        }
+        c->batch_bases += nbases; c->batch_reads += nr;
+        r0 = r1;
+    }
+    CU_TRY(cudaEventRecord(ev_copy.b, c->copy_stream));
+    CU_TRY(cudaMemcpyAsync(c->h_flag, c->d_fill + nb, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));            // every copy has landed too: the host buffers are reusable from here on
+    { float t = 0; CU_TRY(cudaEventElapsedTime(&t, ev_copy.a, ev_copy.b)); c->ms[4] += t; ev_put(c, ev_copy); }
+    for (cudaEvent_t e : sub_ev) c->ev_free_list.push_back(e);
+    c->next_read_index += n_reads; c->reads_total += n_reads;
+    if (*c->h_flag == 0) {
+        k_opt_finish<WIDE><<<nb, 256, 0, s>>>(c->d_tuples, c->d_fill, capb, nb, c->d_boffs, (u32)INS_TILE);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        c->path_counts[2]++;
+        c->part_blocks++;
+        EvPair ev;
+        rc = ev_begin(c, s, &ev);
+        if (rc) return rc;
+        ev.slot = 6;
+        rc = insert_any(c, c->d_tuples, (uint64_t)capb * nb, nullptr, s, true, c->d_fill);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(ev.b, s));
+        c->build_ev.push_back(ev);
+        CU_TRY(cudaEventRecord(ev_build.b, s));
+        c->build_ev.push_back(ev_build);
+    } else {
+        // a bucket region overflowed (skewed input): nothing was inserted; undo the side counters and build the whole
+        // batch -- it is resident -- through the exact partition
+        CU_TRY(cudaMemcpyAsync(c->d_counters, c->d_snap, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->d_polyA, c->d_snap + CNT_N, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaEventRecord(ev_build.b, s));
+        c->build_ev.push_back(ev_build);
+        c->path_counts[3]++;
+        c->guard_total -= call_bases;            // build_device counts the block again
+        const int opt = c->optimistic;
+        c->optimistic = 0;
+        rc = build_device(c, c->d_bases[b], c->d_offs[b], c->batch_reads, 0, c->batch_bases, c->batch_read_index0, s, 0, nullptr, 0, nullptr);
+        c->optimistic = opt;
+        if (rc) return rc;
+    }
+    // the tail of flush_batch: counters to pinned memory (prompt table-full report), hand the buffer over
+    if (!c->h_cnt) {
+        CU_TRY(cudaMallocHost(&c->h_cnt, CNT_N * sizeof(u64)));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_cnt, cudaEventDisableTiming));
+    }
+    CU_TRY(cudaMemcpyAsync(c->h_cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaEventRecord(c->ev_cnt, s));
+    c->cnt_pending = true;
+    CU_TRY(cudaEventRecord(c->ev_free[b], s));
+    c->cur ^= 1;
+    c->batch_reads = 0; c->batch_bases = 0;
+    CU_TRY(cudaEventSynchronize(c->ev_free[c->cur]));
+    return DBG_OK;
+}
+
 extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
 {
     if (!c || (!bases && n_reads) || (!offs && n_reads)) return set_err(DBG_ERR_INVALID, "dbg_submit_reads: NULL argument");
@@ -787,6 +921,21 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
     if (rc) return rc;
     rc = ensure_batch(c);
     if (rc) return rc;
+    if (n_reads && c->pipeline && c->optimistic && c->part_mode != 0 && offs[n_reads] >= offs[0]) {
+        // a call that is a partitioned block by itself and spans several sub-blocks: scatter while copying
+        const uint64_t call_bases = offs[n_reads] - offs[0];
+        if (call_bases > c->sub_bases && call_bases <= c->cap_bases && n_reads <= c->cap_reads && want_partition(c, call_bases) &&
+            stage_cap(c, c->wide) != 0) {
+            rc = flush_batch(c);                 // reads of earlier, smaller calls: their own block, in call order
+            if (rc) return rc;
+            const uint32_t nbk = c->n_buckets;
+            if (ensure_tuples(c, call_bases) == DBG_OK) {
+                const uint64_t capb64 = (c->opt_capb > 0 ? (uint64_t)c->opt_capb : c->cap_tuples / nbk) / INS_TILE * INS_TILE;
+                if (capb64 >= INS_TILE && capb64 * nbk <= c->cap_tuples && capb64 * nbk < (1ull << 32))
+                    return c->wide ? submit_pipelined<true>(c, bases, offs, n_reads) : submit_pipelined<false>(c, bases, offs, n_reads);
+            }
+        }
+    }
     const uint64_t SUB_BASES = c->sub_bases, SUB_READS = c->sub_reads;
     uint64_t r0 = 0;
     while (r0 < n_reads) {
@@ -1717,16 +1866,44 @@ extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
     if (!c || !array || !nul_flag) return set_err(DBG_ERR_INVALID, "NULL argument");
     if (!c->finalized || !c->d_out || c->n_shards > 1) return set_err(DBG_ERR_STATE, "dbg_export_kmerset needs dbg_finalize on an unsharded context (sharded: dbg_export_shard_slice)");
     CU_TRY(cudaSetDevice(c->device));
+    const uint64_t image_bytes = c->P * (uint64_t)node_bytes(c), nul_bytes = c->P / 8 + 1;
+    // DBG_B200_EXPORT=pipe: pipelined hand-over (export_pipe.cu) -- occupied nodes only over the link, host threads expand
+    // them into `array`; it steps aside (returns 1) for small tables, without host threads, or when its buffers cannot be
+    // allocated.  Opt-in: it halves the bytes on the link but triples the host-memory traffic, and on the measured hosts
+    // (16-vCPU VMs, ~80 GB/s of host memory bandwidth) the plain DMA copy is faster (profiles/README.md); same bytes either way.
+    const char *mode = getenv("DBG_B200_EXPORT");
+    if (mode && strcmp(mode, "pipe") == 0) {
+        char msg[256] = "";
+        float ms = 0;
+        int prc = export_pipe_run(&c->pipe, c->device, c->stream, c->d_out, c->d_nul32, nul_words(c->P), c->P, node_bytes(c), array, nul_flag,
+                                  &ms, c->export_info, msg, (int)sizeof(msg));
+        if (prc < 0) return set_err(DBG_ERR_CUDA, "%s", msg);
+        if (prc == 0) { c->ms[5] = ms; c->launches += 2 + c->export_info[0] + c->export_info[1]; return DBG_OK; }
+    }
     EvPair e;
     int rc = ev_begin(c, c->stream, &e);
     if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(array, c->d_out, c->P * (size_t)node_bytes(c), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaMemcpyAsync(nul_flag, c->d_nul32, c->P / 8 + 1, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(array, c->d_out, image_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(nul_flag, c->d_nul32, nul_bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaEventRecord(e.b, c->stream));
     CU_TRY(cudaEventSynchronize(e.b));
     CU_TRY(cudaEventElapsedTime(&c->ms[5], e.a, e.b));
     ev_put(c, e);
+    c->export_info[0] = 0; c->export_info[1] = 1; c->export_info[2] = image_bytes + nul_bytes; c->export_info[3] = c->st.count;
     return DBG_OK;
+}
+
+extern "C" int dbg_export_info(const dbg_ctx *c, uint64_t info[4])
+{
+    if (!c || !info) return set_err(DBG_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 4; i++) info[i] = c->export_info[i];
+    return DBG_OK;
+}
+
+extern "C" uint64_t dbg_host_expand_nodes(const uint8_t *bits, uint64_t n_slots, const void *nodes, void *array, int32_t wide)
+{
+    if (!bits || !nodes || !array) return 0;
+    return expand_nodes(bits, n_slots, nodes, array, wide ? 32 : 16);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -232,6 +232,12 @@ class DBGBuilder:
         capi.check(self.L.dbg_export_kmerset(self.h, array.ctypes.data, nul_flag.ctypes.data), "dbg_export_kmerset")
         return array, nul_flag
 
+    def export_info(self):
+        """how the last export_kmerset moved the table (include/dbg_b200.h: dbg_export_info)"""
+        a = np.zeros(4, dtype=np.uint64)
+        capi.check(self.L.dbg_export_info(self.h, a.ctypes.data), "dbg_export_info")
+        return dict(chunks_compact=int(a[0]), chunks_plain=int(a[1]), link_bytes=int(a[2]), nodes=int(a[3]))
+
     def export_links(self, freq_cutoff=2, lists=True):
         P = self.stats["array_size"]
         klink = np.empty(2 * P, dtype=np.uint8)

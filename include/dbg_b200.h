@@ -221,6 +221,19 @@ int  dbg_get_stats(dbg_ctx *ctx, dbg_stats *stats);
 /* The KmerSet the reference's traversal consumes (kmerSet.h:88-99): array[P] in reference slot
  * layout (16-B nodes, or 32-B nodes on the wide path) and nul_flag[P/8+1], MSB first. */
 int  dbg_export_kmerset(dbg_ctx *ctx, void *array, uint8_t *nul_flag);
+/* How the last dbg_export_kmerset moved the table: info = {chunks sent compact, chunks sent plain, bytes moved over the
+ * link, occupied nodes}.  Default: ONE plain copy of the image ({0, 1, P*node + P/8+1, count}).  With the environment
+ * variable DBG_B200_EXPORT=pipe, tables of more than a few million slots travel as occupied nodes only (compacted on the
+ * device in slot order, chunk by chunk) and host threads of the library expand them into `array` while later chunks are on
+ * the link; when the host threads fall behind, a chunk travels as plain image bytes instead (only if `array` is pinned:
+ * dbg_host_alloc / dbg_host_register).  Same bytes in `array` / `nul_flag` either way.  It pays on hosts whose memory
+ * bandwidth is several times the PCIe link's; on the measured 16-vCPU hosts the plain copy is faster, hence opt-in.
+ * Knobs: DBG_B200_EXPORT_THREADS, DBG_B200_EXPORT_CHUNK (slots), DBG_B200_EXPORT_SLOTS (pinned ring slots),
+ * DBG_B200_EXPORT_NO_DIRECT, DBG_B200_EXPORT_PLAIN_PCT. */
+int  dbg_export_info(const dbg_ctx *ctx, uint64_t info[4]);
+/* host helper of that path: array[s] = (bit s of `bits`, MSB first as in nul_flag) ? next node of `nodes` : 0 for
+ * n_slots slots; returns the nodes consumed.  `nodes` must be readable 16 bytes past its last node. */
+uint64_t dbg_host_expand_nodes(const uint8_t *bits, uint64_t n_slots, const void *nodes, void *array, int32_t wide);
 
 /* calculate_kmer_links (contig.cpp:107-205) on the device: klink[P*2] (KmerLink bit layout,
  * contig.h:31-42), del_flag[P/8+1], depth_hist[256], index-ordered tip and branch lists (capacity

@@ -499,6 +499,60 @@ def test_partition_variants_match_oracle(dbg, oracle_mod, build_path, monkeypatc
     o.close()
 
 
+@pytest.mark.parametrize("K", [31, 55])
+@pytest.mark.parametrize("variant", ["optimistic", "overflow_fallback"])
+def test_pipelined_submit_matches_oracle(dbg, oracle_mod, build_path, monkeypatch, variant, K):
+    """a dbg_submit_reads call that is a partitioned block by itself is pipelined: the scatter of sub-block i runs while
+    sub-block i+1 is copied, one insert follows (submit_pipelined, csrc/dbg_build.cu).  Small sub-blocks make every call a
+    dozen launches; a second call appends to a table that already holds nodes; the overflow variant forces the regions too
+    small, so the whole resident batch is redone by the exact partition.  Bit-identical to the oracle, layout included."""
+    if build_path != "partitioned":
+        pytest.skip("partitioned path only")
+    for k in ("DBG_B200_PART_SHIFT", "DBG_B200_BATCH_BASES", "DBG_B200_BATCH_READS"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("DBG_B200_PART_SHIFT", "14")
+    monkeypatch.setenv("DBG_B200_SUB_BASES", "700000")
+    monkeypatch.setenv("DBG_B200_SUB_READS", "5000")
+    if variant == "overflow_fallback":
+        monkeypatch.setenv("DBG_B200_OPT_CAPB", "1000")
+    from dbg_assembly_b200 import synth
+    p = synth.make_params(seed=21, genome_len=300_000, read_len=150, insert=500, err=0.01, n_rate=0.002)
+    n = 100_000
+    hb, ho = synth.reads_host(p, 0, n)
+    extra = [b"A" * 150] * 40 + [b"ACGT" * 10]          # poly-A side counters; a read shorter than K=55
+    eb = np.frombuffer(b"".join(extra), dtype=np.uint8)
+    hb = np.concatenate([hb, eb])
+    ho = np.concatenate([ho, ho[-1] + np.cumsum(np.array([len(x) for x in extra], dtype=ho.dtype))])
+    n_all = len(ho) - 1
+    init_slots = 10_000_000
+    o = oracle_build(oracle_mod, [(hb, ho)], K, 150, init_slots, wide=K > 31)
+    launches = {}
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("DBG_B200_PIPELINE", pipe)
+        with dbg.DBGBuilder(K=K, max_read_len=150, init_slots=init_slots, load_factor=0.7) as b:
+            cut = n_all * 2 // 3
+            b.submit(hb, ho[: cut + 1])
+            b.submit(hb, ho[cut:])
+            st = b.finalize()
+            arr, nul = b.export_kmerset()
+            pc = b.path_counts()
+            launches[pipe] = b.launches
+        assert pc["direct"] == 0
+        blocks = 2 if pipe == "1" else 1       # pipelined: every call is its own block; otherwise both calls share one batch
+        if variant == "optimistic":
+            assert pc["optimistic"] == blocks and pc["overflows"] == 0 and pc["exact"] == 0, (pc, pipe)
+        else:
+            assert pc["overflows"] == blocks and pc["exact"] == blocks and pc["optimistic"] == 0, (pc, pipe)
+        assert st["count"] == o.count and st["occurrences"] == o.occurrences and st["kmers_logged"] == o.kmers_logged
+        assert st["reads"] == n_all
+        e = o.dump()
+        d = image_to_dump(arr, nul, o.size)
+        for k in ("slot", "kmer", "l", "r") + (("kmer_hi",) if K > 31 else ()):
+            assert np.array_equal(d[k], e[k]), (k, pipe)
+    assert launches["1"] > launches["0"] + 10, launches      # the pipelined calls really ran sub-block by sub-block
+    o.close()
+
+
 def test_full_size_properties_C2(dbg, build_path, monkeypatch):
     """BASELINE config C2 at full size (3.07 M reads, 3.68e8 occurrences): size-independent properties
     -- conservation of occurrences in the link lanes, idempotent rebuild, and the direct and the
