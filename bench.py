@@ -504,6 +504,8 @@ def run_b200(args):
 
         def e2e_step():
             b2.reset()
+            if args.e2e_api == "finish_export":
+                return b2.finish_export_ptr(h_bases.ptr, h_offs.ptr, n, h_arr.ptr, h_nul.ptr)
             b2.submit_ptr(h_bases.ptr, h_offs.ptr, n)
             s = b2.finalize()
             dbg.capi.check(Lb.dbg_export_kmerset(b2.h, h_arr.ptr, h_nul.ptr), "dbg_export_kmerset")
@@ -523,9 +525,11 @@ def run_b200(args):
                        "d2h_bytes_per_step": int(xi["link_bytes"]), "ms_per_step": dt * 1e3, "steps": e_steps,
                        "h2d_ms": tm["h2d_ms"], "d2h_ms": tm["d2h_ms"], "build_ms": tm["build_ms"], "layout_ms": tm["layout_ms"],
                        "result_bytes_on_host": int(P * nbytes_node + P // 8 + 1), "export": xi,
-                       "what": "dbg_submit_reads (pinned host reads) -> dbg_finalize -> dbg_export_kmerset (the whole P-slot KmerSet image + nul_flag "
-                               "land in pinned host memory; occupied nodes travel compact and host threads of the library expand them, "
-                               "chunks the host cannot absorb travel as plain image bytes: export.chunks_compact / chunks_plain); wall clock"}
+                       "api": args.e2e_api,
+                       "what": ("dbg_reset + dbg_finish_export(pinned host reads -> the whole P-slot KmerSet image + nul_flag in pinned host memory): one "
+                                "call = dbg_submit_reads + dbg_finalize + dbg_export_kmerset, pipelined (H2D || extraction; insert / layout / D2H slice "
+                                "group by slice group: export.chunks_plain windows); wall clock" if args.e2e_api == "finish_export" else
+                                "dbg_reset + dbg_submit_reads (pinned host reads) -> dbg_finalize -> dbg_export_kmerset (KmerSet image into pinned host memory); wall clock")}
         b2.close()
         for hb in (h_bases, h_offs, h_arr, h_nul):
             hb.close()
@@ -594,6 +598,8 @@ def main():
                     help="multi-GPU: 'peer' = ONE extraction pass stores tuples into fixed regions of the owners' buffers over NVLink, pipelined "
                          "with the owners' inserts; 'peer_exact' = count pass + exact offsets + scatter; 'nccl' = pack + send/recv")
     ap.add_argument("--sub-blocks", type=int, default=4, help="multi-GPU 'peer': sub-blocks per step (scatter k+1 overlaps insert k)")
+    ap.add_argument("--e2e-api", default="finish_export", choices=["finish_export", "separate"],
+                    help="N=1 e2e leg: the fused, pipelined dbg_finish_export (default) or the three separate calls")
     ap.add_argument("--no-other", action="store_true", help="N=1: skip the short C1 / C3 lines (other_workloads)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cpu-t1", action="store_true", help="skip the -t 1 run of the reference in cpu_baseline")

@@ -199,6 +199,9 @@ struct dbg_ctx {
     std::vector<EvPair> build_ev;
     std::vector<cudaEvent_t> ev_all, ev_free_list;   // every timing event this context ever created / the idle ones
     float ms[8];
+    LayoutInfo *d_layout_info2 = nullptr;      // dbg_finish_export: the wrap-around region found after the grouped layout
+    LayoutRegion *d_regions2 = nullptr;
+    LayoutRegion *h_regions = nullptr;         // pinned copy of the region list (patch copies)
     ExportPipe *pipe = nullptr;    // pipelined export (export_pipe.cu): pinned ring, compact buffer, host worker threads
     uint64_t export_info[4] = {0, 0, 0, 0};   // last dbg_export_kmerset: chunks sent compact, chunks sent plain, bytes over the link, nodes
 };
@@ -243,6 +246,8 @@ static int ev_begin(dbg_ctx *c, cudaStream_t s, EvPair *p)
 static void free_finalize_buffers(dbg_ctx *c)
 {
     cudaFree(c->d_owner); cudaFree(c->d_out); cudaFree(c->d_nul32); cudaFree(c->d_layout_info); cudaFree(c->d_regions);
+    cudaFree(c->d_layout_info2); cudaFree(c->d_regions2); if (c->h_regions) cudaFreeHost(c->h_regions);
+    c->d_layout_info2 = nullptr; c->d_regions2 = nullptr; c->h_regions = nullptr;
     c->owner_cap = 0; c->d_layout_info = nullptr; c->d_regions = nullptr;
     cudaFree(c->d_klink); cudaFree(c->d_del32); cudaFree(c->d_tile_counts); cudaFree(c->d_tile_offs); cudaFree(c->d_small);
     c->d_owner = nullptr; c->d_out = nullptr; c->d_nul32 = nullptr;
@@ -433,26 +438,29 @@ static int launch_build(dbg_ctx *c, const BuildArgs &a, Sink sink, uint64_t n_ch
 }
 
 template <bool WIDE, bool TRACK>
-static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed, const u32 *d_fill)
+static int launch_insert(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed, const u32 *d_fill,
+                         uint64_t t_begin = 0, uint32_t b_begin = 0)
 {
-    if (n_upper == 0) return DBG_OK;
-    uint64_t tiles = (n_upper + INS_TILE - 1) / INS_TILE;
+    if (n_upper <= t_begin) return DBG_OK;
+    uint64_t tiles = (n_upper - t_begin + INS_TILE - 1) / INS_TILE;
     uint64_t persistent = (uint64_t)c->n_sms * INS_CTAS;
     unsigned grid = (unsigned)(tiles < persistent ? tiles : persistent);
     CU_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(u64), s));      // tile counter
     k_insert_tuples<WIDE, TRACK><<<grid, INS_BLOCK, 0, s>>>((const u64 *)d_tuples, n_upper, d_n, view_of(c),
                                                             bucketed ? c->d_boffs : nullptr, c->n_buckets, c->part_shift,
-                                                            c->d_counters + 7, d_fill);
+                                                            c->d_counters + 7, d_fill, t_begin, b_begin);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return DBG_OK;
 }
 
 static int insert_any(dbg_ctx *c, const void *d_tuples, uint64_t n_upper, const u64 *d_n, cudaStream_t s, bool bucketed = false,
-                      const u32 *d_fill = nullptr)
+                      const u32 *d_fill = nullptr, uint64_t t_begin = 0, uint32_t b_begin = 0)
 {
-    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill) : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill);
-    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill) : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill);
+    if (c->wide) return c->track ? launch_insert<true, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill, t_begin, b_begin)
+                                 : launch_insert<true, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill, t_begin, b_begin);
+    return c->track ? launch_insert<false, true>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill, t_begin, b_begin)
+                    : launch_insert<false, false>(c, d_tuples, n_upper, d_n, s, bucketed, d_fill, t_begin, b_begin);
 }
 
 // batch capacity (tuples) of the shared-memory staging of the scatter passes; 0 = store tuples one by one
@@ -783,13 +791,18 @@ static int flush_batch(dbg_ctx *c)
     return DBG_OK;
 }
 
+// dbg_finish_export: where the caller wants the table image (filled by the grouped insert / layout / copy pipeline)
+struct FinishExport { void *array; uint8_t *nul_flag; bool done; };
+template <bool WIDE, bool TRACK>
+static int grouped_finish(dbg_ctx *c, uint32_t capb, FinishExport *fx);
+
 // One dbg_submit_reads call that is a whole partitioned block by itself (front ends that hand over a file's worth of reads,
 // bench e2e): pipeline it.  The optimistic scatter appends to fixed bucket regions, so it can run sub-block by sub-block --
 // the extraction + partition of sub-block i overlaps the host->device copy of sub-block i+1 -- and ONE bucketed insert
 // follows the last scatter.  Same table as the one-launch build (ordinals are global read indices); an overflowing region
 // falls back to the exact partition of the whole (device-resident) batch.
 template <bool WIDE>
-static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
+static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads, FinishExport *fx)
 {
     const uint64_t call_bases = offs[n_reads] - offs[0];
     const int b = c->cur;
@@ -871,16 +884,25 @@ static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs,
         c->launches++;
         c->path_counts[2]++;
         c->part_blocks++;
-        EvPair ev;
-        rc = ev_begin(c, s, &ev);
-        if (rc) return rc;
-        ev.slot = 6;
-        rc = insert_any(c, c->d_tuples, (uint64_t)capb * nb, nullptr, s, true, c->d_fill);
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(ev.b, s));
-        c->build_ev.push_back(ev);
-        CU_TRY(cudaEventRecord(ev_build.b, s));
-        c->build_ev.push_back(ev_build);
+        int grc = 1;
+        if (fx) {
+            // last block of the build and the caller waits for the image: insert, lay out and copy slice group by slice group
+            CU_TRY(cudaEventRecord(ev_build.b, s));
+            c->build_ev.push_back(ev_build);
+            grc = c->track ? grouped_finish<WIDE, true>(c, capb, fx) : grouped_finish<WIDE, false>(c, capb, fx);
+            if (grc < 0) return grc;
+        }
+        if (grc == 1) {            // (1 = the grouped pipeline does not apply here: nothing was inserted yet)
+            EvPair ev;
+            rc = ev_begin(c, s, &ev);
+            if (rc) return rc;
+            ev.slot = 6;
+            rc = insert_any(c, c->d_tuples, (uint64_t)capb * nb, nullptr, s, true, c->d_fill);
+            if (rc) return rc;
+            CU_TRY(cudaEventRecord(ev.b, s));
+            c->build_ev.push_back(ev);
+            if (!fx) { CU_TRY(cudaEventRecord(ev_build.b, s)); c->build_ev.push_back(ev_build); }
+        }
     } else {
         // a bucket region overflowed (skewed input): nothing was inserted; undo the side counters and build the whole
         // batch -- it is resident -- through the exact partition
@@ -911,7 +933,7 @@ static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs,
     return DBG_OK;
 }
 
-extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
+static int submit_impl(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads, FinishExport *fx)
 {
     if (!c || (!bases && n_reads) || (!offs && n_reads)) return set_err(DBG_ERR_INVALID, "dbg_submit_reads: NULL argument");
     if (c->finalized) return set_err(DBG_ERR_STATE, "submit after finalize");
@@ -932,7 +954,7 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
             if (ensure_tuples(c, call_bases) == DBG_OK) {
                 const uint64_t capb64 = (c->opt_capb > 0 ? (uint64_t)c->opt_capb : c->cap_tuples / nbk) / INS_TILE * INS_TILE;
                 if (capb64 >= INS_TILE && capb64 * nbk <= c->cap_tuples && capb64 * nbk < (1ull << 32))
-                    return c->wide ? submit_pipelined<true>(c, bases, offs, n_reads) : submit_pipelined<false>(c, bases, offs, n_reads);
+                    return c->wide ? submit_pipelined<true>(c, bases, offs, n_reads, fx) : submit_pipelined<false>(c, bases, offs, n_reads, fx);
             }
         }
     }
@@ -980,6 +1002,11 @@ extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *o
         r0 = r1;
     }
     return DBG_OK;
+}
+
+extern "C" int dbg_submit_reads(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads)
+{
+    return submit_impl(c, bases, offs, n_reads, nullptr);
 }
 
 extern "C" int dbg_submit_reads_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
@@ -1483,6 +1510,7 @@ static LayoutGeom layout_geom(const dbg_ctx *c)
         g.v_begin = c->porch - c->tail_a_in;
         g.v_end = c->porch + ((c->shard_hi - c->shard_lo) - c->tail_a_own);
     }
+    g.v_first = g.v_begin; g.v_halo = g.v_end; g.v_final = g.v_end;
     return g;
 }
 
@@ -1591,6 +1619,184 @@ static int run_layout_sharded(dbg_ctx *c)
         }
     }
     return DBG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dbg_finish_export: the last block's insert, the reference layout and the copy of the image, slice group by slice group.
+// The tuples of the block are bucket-ordered (bucket = table slice), so after the insert of the buckets [0, b) every slot
+// below b << part_shift is FINAL (later keys have later homes and linear probing only moves forward).  Group g therefore
+// runs  insert(buckets of g) -> k_layout_clusters(window of g) -> D2H(window of g)  with the copy on its own stream: the
+// image is on the PCIe link -- the bound of the whole hand-over -- while later groups are still being inserted.
+// Windows end GUARD slots before the group's last slot so that tiles read their halo, and long clusters are measured,
+// inside final territory.  The wrap-around region, clusters longer than the shared-memory window and the k-mer-0 node are
+// settled after the last group and their (few, small) slot ranges are copied again.
+// Returns 0 = image delivered and context finalized; 1 = not applicable, nothing touched; 2 = table built, but the layout
+// must be redone in one pass (dense table: too many long clusters) -- the caller goes through dbg_finalize / dbg_export.
+// ---------------------------------------------------------------------------------------------------
+template <bool WIDE, bool TRACK>
+static int grouped_finish(dbg_ctx *c, uint32_t capb, FinishExport *fx)
+{
+    const uint32_t nb = c->n_buckets;
+    const uint64_t bucket_slots = 1ull << c->part_shift;
+    const uint64_t GUARD = MARGIN_SLOTS;
+    const uint64_t P = c->P;
+    const size_t nbytes = (size_t)node_bytes(c);
+    if (c->n_shards > 1 || c->layout_mode != 0 || c->prm.payload_mode != 0) return 1;
+    int G = getenv("DBG_B200_FINISH_GROUPS") ? atoi(getenv("DBG_B200_FINISH_GROUPS")) : 8;
+    if (G < 2) return 1;
+    uint32_t per = (nb + G - 1) / G;
+    if (per == 0 || (uint64_t)per * bucket_slots < 4 * GUARD || P < 8 * GUARD) return 1;
+    cudaStream_t s = c->stream, cs = c->copy_stream;
+    int rc = ensure_layout_scratch(c);
+    if (rc) return rc < 0 ? rc : -1;
+    if (!c->d_out) {
+        CU_TRY(cudaMalloc(&c->d_out, P * nbytes));
+        CU_TRY(cudaMalloc(&c->d_nul32, nul_words(P) * sizeof(u32)));
+    }
+    if (!c->d_layout_info2) {
+        CU_TRY(cudaMalloc(&c->d_layout_info2, sizeof(LayoutInfo)));
+        CU_TRY(cudaMalloc(&c->d_regions2, 4 * sizeof(LayoutRegion)));
+        CU_TRY(cudaMallocHost(&c->h_regions, 4096 * sizeof(LayoutRegion)));
+    }
+    const NodeT<WIDE> *nodes = (const NodeT<WIDE> *)c->d_nodes;
+    char *array = static_cast<char *>(fx->array);
+    uint8_t *nul_flag = fx->nul_flag;
+    uint64_t link_bytes = 0, n_windows = 0;
+    auto copy_range = [&](uint64_t s0, uint64_t s1, bool to_end) -> cudaError_t {
+        if (s1 <= s0) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(array + s0 * nbytes, static_cast<const char *>(c->d_out) + s0 * nbytes, (s1 - s0) * nbytes, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) return e;
+        const uint64_t by0 = s0 / 8, by1 = to_end ? P / 8 + 1 : (s1 + 7) / 8;
+        link_bytes += (s1 - s0) * nbytes + (by1 - by0);
+        return cudaMemcpyAsync(nul_flag + by0, reinterpret_cast<const uint8_t *>(c->d_nul32) + by0, by1 - by0, cudaMemcpyDeviceToHost, cs);
+    };
+    CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(P) * sizeof(u32), s));
+    LayoutInfo li0;
+    memset(&li0, 0, sizeof(li0));
+    li0.e = ~0ULL;                       // no wrap region while the groups run: it is settled at the end
+    CU_TRY(cudaMemcpyAsync(c->d_layout_info, &li0, sizeof(li0), cudaMemcpyHostToDevice, s));
+    EvPair ev_d2h;
+    bool d2h_started = false;
+    std::vector<cudaEvent_t> gev;
+    uint64_t win_begin = 0, lastw = 0;       // lastw: first slot of the last window
+    for (uint32_t b0 = 0; b0 < nb;) {
+        uint32_t b1 = b0 + per < nb ? b0 + per : nb;
+        uint64_t end_g = (uint64_t)b1 * bucket_slots;
+        if (end_g >= P + GUARD || end_g - GUARD >= P || end_g - GUARD <= win_begin + GUARD) { b1 = nb; end_g = c->n_local; }   // the rest is the last group
+        const bool last = b1 == nb;
+        EvPair evi;
+        rc = ev_begin(c, s, &evi);
+        if (rc) return rc;
+        evi.slot = 6;
+        rc = insert_any(c, c->d_tuples, (uint64_t)capb * b1, nullptr, s, true, c->d_fill, (uint64_t)capb * b0, b0);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(evi.b, s));
+        c->build_ev.push_back(evi);
+        LayoutGeom geo;
+        geo.P = P; geo.M = c->M; geo.gbase = 0; geo.v_first = 0; geo.v_halo = P;
+        geo.v_begin = win_begin; geo.v_end = last ? P : end_g - GUARD; geo.v_final = last ? P : end_g;
+        EvPair evl;
+        rc = ev_begin(c, s, &evl);
+        if (rc) return rc;
+        evl.slot = 2;
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, s>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info, c->d_regions, SCRATCH_CAP);
+        CU_TRY(cudaGetLastError());
+        c->launches++;
+        CU_TRY(cudaEventRecord(evl.b, s));
+        c->build_ev.push_back(evl);
+        if (last) lastw = geo.v_begin;
+        else {
+            cudaEvent_t e;
+            rc = ev_get(c, &e);
+            if (rc) return rc;
+            gev.push_back(e);
+            CU_TRY(cudaEventRecord(e, s));
+            CU_TRY(cudaStreamWaitEvent(cs, e, 0));
+            if (!d2h_started) { rc = ev_begin(c, cs, &ev_d2h); if (rc) return rc; d2h_started = true; }
+            CU_TRY(copy_range(geo.v_begin, geo.v_end, false));
+            n_windows++;
+        }
+        win_begin = geo.v_end;
+        b0 = b1;
+    }
+    // ---- after the last insert: wrap-around region, long clusters, k-mer-0 node ----
+    EvPair evt;
+    rc = ev_begin(c, s, &evt);
+    if (rc) return rc;
+    evt.slot = 2;
+    k_layout_wrapscan<WIDE><<<1, 32, 0, s>>>(nodes, c->n_local, P, c->d_layout_info2, c->d_regions2, SCRATCH_CAP);
+    CU_TRY(cudaGetLastError());
+    LayoutGeom whole;
+    whole.P = P; whole.M = c->M; whole.gbase = 0; whole.v_begin = 0; whole.v_end = P; whole.v_first = 0; whole.v_halo = P; whole.v_final = P;
+    k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, s>>>(nodes, whole, c->d_out, c->d_nul32, c->d_layout_info, c->d_regions, c->d_owner);
+    CU_TRY(cudaGetLastError());
+    k_layout_regions<WIDE, TRACK><<<1, 256, 0, s>>>(nodes, whole, c->d_out, c->d_nul32, c->d_layout_info2, c->d_regions2, c->d_owner);
+    CU_TRY(cudaGetLastError());
+    k_polyA_insert<WIDE><<<1, 32, 0, s>>>(P, c->M, c->d_polyA, c->d_out, c->d_nul32, c->d_counters + 6);
+    CU_TRY(cudaGetLastError());
+    c->launches += 4;
+    CU_TRY(cudaEventRecord(evt.b, s));
+    c->build_ev.push_back(evt);
+    LayoutInfo li1, li2;
+    u64 cnt[CNT_N];
+    CU_TRY(cudaMemcpyAsync(&li1, c->d_layout_info, sizeof(li1), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&li2, c->d_layout_info2, sizeof(li2), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(cnt, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    for (cudaEvent_t e : gev) c->ev_free_list.push_back(e);
+    auto give_up = [&]() -> int {
+        // the table is complete but this layout is not usable: let the copies in flight drain, then the one-pass path
+        cudaStreamSynchronize(cs);
+        if (d2h_started) ev_put(c, ev_d2h);
+        return 2;
+    };
+    if (cnt[CNT_ERROR] == 1 || cnt[CNT_NEW] + 1 > P) return give_up();          // (dbg_finalize reports DBG_ERR_TABLE_FULL)
+    const uint32_t MAXR = 4096;
+    if (li1.overflow || li2.overflow || li1.n_regions > MAXR) return give_up();
+    if (li1.n_regions) CU_TRY(cudaMemcpyAsync(c->h_regions, c->d_regions, li1.n_regions * sizeof(LayoutRegion), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // the last window, then the ranges that changed after their window had left
+    if (!d2h_started) { rc = ev_begin(c, cs, &ev_d2h); if (rc) return rc; d2h_started = true; }
+    CU_TRY(copy_range(lastw, P, true));
+    n_windows++;
+    for (uint32_t r = 0; r < li1.n_regions; r++) {
+        const LayoutRegion &rg = c->h_regions[r];
+        if (rg.a < lastw) CU_TRY(copy_range(rg.a, rg.a + rg.n < lastw ? rg.a + rg.n : lastw, false));
+    }
+    if (li2.n_regions && li2.g > 0) CU_TRY(copy_range(0, li2.g < lastw ? li2.g : lastw, false));      // ([e, P) lies in the last window or is patched here:)
+    if (li2.n_regions && li2.e < lastw) CU_TRY(copy_range(li2.e, lastw, false));
+    CU_TRY(cudaEventRecord(ev_d2h.b, cs));
+    CU_TRY(cudaEventSynchronize(ev_d2h.b));
+    CU_TRY(cudaEventElapsedTime(&c->ms[5], ev_d2h.a, ev_d2h.b));
+    ev_put(c, ev_d2h);
+    CU_TRY(cudaMemcpy(&c->polyA_links, c->d_counters + 6, sizeof(u64), cudaMemcpyDeviceToHost));
+    // the k-mer-0 node went into the device image after its window had left: the same insertion on the host copy
+    // (the windows carried the image WITHOUT it, except the last one -- dbg_host_polyA_insert is idempotent only on a table
+    // that lacks the node, so take it out of the last window's bits first if it landed there)
+    {
+        const uint64_t home0 = (WIDE ? hash_code_wide(0, 0) : hash_code(0)) % P;
+        // find where the device put it: first slot from home0 whose image k-mer is 0 while its bit is set
+        uint64_t sl = home0;
+        for (;;) {
+            const bool bit = (nul_flag[sl >> 3] >> (7 - (sl & 7))) & 1;
+            if (!bit) break;                                              // free slot: the node is not in the host copy yet
+            const uint64_t *nd = reinterpret_cast<const uint64_t *>(array + sl * nbytes);
+            if (nd[0] == 0 && (!WIDE || nd[1] == 0)) { sl = ~0ULL; break; }  // already there (it travelled with its window)
+            sl = sl + 1 == P ? 0 : sl + 1;
+        }
+        if (sl != ~0ULL) {
+            uint64_t slot_out = 0;
+            int hrc = dbg_host_polyA_insert(array, nul_flag, P, WIDE ? 1 : 0, (uint32_t)(c->polyA_links & 0xffffffffu), (uint32_t)(c->polyA_links >> 32), &slot_out);
+            if (hrc) return hrc;
+        }
+    }
+    for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; ev_put(c, e); }
+    c->build_ev.clear();
+    c->layout_regions = li1.n_regions + li2.n_regions;
+    c->finalized = true;
+    c->export_info[0] = 0; c->export_info[1] = n_windows; c->export_info[2] = link_bytes; c->export_info[3] = cnt[CNT_NEW] + 1;
+    fx->done = true;
+    return 0;
 }
 
 extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
@@ -1891,6 +2097,20 @@ extern "C" int dbg_export_kmerset(dbg_ctx *c, void *array, uint8_t *nul_flag)
     ev_put(c, e);
     c->export_info[0] = 0; c->export_info[1] = 1; c->export_info[2] = image_bytes + nul_bytes; c->export_info[3] = c->st.count;
     return DBG_OK;
+}
+
+extern "C" int dbg_finish_export(dbg_ctx *c, const char *bases, const uint64_t *offs, uint64_t n_reads, dbg_stats *stats, void *array, uint8_t *nul_flag)
+{
+    if (!c || !array || !nul_flag) return set_err(DBG_ERR_INVALID, "NULL argument");
+    if (c->n_shards > 1) return set_err(DBG_ERR_STATE, "dbg_finish_export: unsharded contexts only");
+    FinishExport fx{array, nul_flag, false};
+    if (n_reads) {
+        int rc = submit_impl(c, bases, offs, n_reads, &fx);
+        if (rc) return rc;
+    }
+    int rc = dbg_finalize(c, stats);
+    if (rc) return rc;
+    return fx.done ? DBG_OK : dbg_export_kmerset(c, array, nul_flag);
 }
 
 extern "C" int dbg_export_info(const dbg_ctx *c, uint64_t info[4])

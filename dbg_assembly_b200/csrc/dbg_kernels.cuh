@@ -922,11 +922,14 @@ constexpr int INS_CTAS = DBG_INS_CTAS;      // per SM (x8 warps)
 template <bool WIDE, bool TRACK>
 __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64 *__restrict__ tuples, u64 n, const u64 *__restrict__ n_ptr,
                                                                        TableView t, const u64 *__restrict__ boffs, u32 n_buckets, int shift,
-                                                                       u64 *tile_counter, const u32 *__restrict__ fill)
+                                                                       u64 *tile_counter, const u32 *__restrict__ fill,
+                                                                       u64 t_begin = 0, u32 b_begin = 0)
 {
+    // (t_begin, b_begin: a launch over the bucket range [b_begin, ...) of the stream, tuples [t_begin, n) -- the grouped
+    // insert of dbg_finish_export; boffs / fill / n stay in whole-stream coordinates)
     if (n_ptr) n = *n_ptr;      // exact count produced on the device (partitioned build): no host round trip
     u32 n_new = 0, n_conf = 0;
-    u32 b = 0;                  // current bucket of this CTA's tile (monotone)
+    u32 b = b_begin;            // current bucket of this CTA's tile (monotone)
     u64 b0 = 0, b1 = 0;         // the bucket's region in the tuple stream
     u64 used = 0;               // tuples actually stored in it (== b1 - b0 unless the regions are fixed-size: `fill`)
     float ratio = 0.f;
@@ -939,8 +942,8 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
         return (float)(slice_n * sizeof(NodeT<WIDE>) / 128) / (float)used;      // 128-B L2 lines per tuple
     };
     if (boffs) {
-        b0 = __ldg(boffs); b1 = __ldg(boffs + 1);
-        used = fill ? (u64)__ldg(fill) : b1 - b0;
+        b0 = __ldg(boffs + b); b1 = __ldg(boffs + b + 1);
+        used = fill ? (u64)__ldg(fill + b) : b1 - b0;
         ratio = next_slice_ratio();
     }
     __shared__ u64 s_tile[2];
@@ -954,7 +957,7 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
     for (u32 par = 0;; par ^= 1) {
         if (threadIdx.x == 0) s_tile[par] = next_tile;
         __syncthreads();
-        const u64 tile = s_tile[par] * INS_TILE;
+        const u64 tile = t_begin + s_tile[par] * INS_TILE;
         if (tile >= n) break;
         if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
         if (boffs && tile >= b1 && b + 1 < n_buckets) {
@@ -1071,7 +1074,13 @@ struct LayoutGeom {
     u64 P, M;
     u64 gbase;        // global slot of v = 0
     u64 v_begin;      // first slot laid out
-    u64 v_end;        // one past the last slot laid out (slots >= v_end are treated as absent)
+    u64 v_end;        // one past the last slot laid out
+    // A pass over a SUB-window of a table that exists beyond it (dbg_finish_export lays the table out group by group,
+    // behind the inserts): slots in [v_first, v_halo) exist -- tiles read their halo there, and a cluster that starts
+    // inside the window is replayed (and written) to its end even past v_end; slots >= v_final are not final yet, a long
+    // cluster that reaches them raises `overflow` (the caller redoes the layout in one pass).  Whole windows:
+    // v_first = v_begin, v_halo = v_final = v_end.
+    u64 v_first, v_halo, v_final;
 };
 
 __device__ __forceinline__ u64 home_virtual(const LayoutGeom &g, u64 klo, u64 khi, bool wide)
@@ -1210,7 +1219,7 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
         for (int k = t; k < LT + LH; k += LT) {          // k = t, and t + LT for the first LH threads (warp uniform)
             const u64 s = i0 + k;
             NodeRegs nd; nd.klo = 0; nd.khi = 0; nd.nord = 0; nd.c0 = 0; nd.c1 = 0;
-            if (s < v_end) load_node(nodes + s, nd);
+            if (s < geo.v_halo) load_node(nodes + s, nd);
             const bool o = (nd.klo | nd.khi) != 0;
             if (WIDE) { s_raw[3 * k] = make_ulonglong2(nd.klo, nd.khi); s_raw[3 * k + 1] = make_ulonglong2(nd.nord, 0ULL); s_raw[3 * k + 2] = make_ulonglong2(nd.c0, nd.c1); }
             else { s_raw[2 * k] = make_ulonglong2(nd.klo, nd.nord); s_raw[2 * k + 1] = make_ulonglong2(nd.c0, nd.c1); }
@@ -1222,7 +1231,7 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
             }
             if (k < LT && s < v_end && !o) write_image<WIDE>(out, s, 0, 0, 0);
         }
-        if (t == 0) s_prev = (i0 > geo.v_begin) && slot_occupied<WIDE>(nodes, i0 - 1);
+        if (t == 0) s_prev = (i0 > geo.v_first) && slot_occupied<WIDE>(nodes, i0 - 1);
         __syncthreads();
         u32 n_occ = 0;
 #pragma unroll
@@ -1245,7 +1254,8 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
                 // longer than the shared-memory window: measure it in global memory, hand it to k_layout_regions
                 if (k == start) {
                     u64 len = (u64)(end > LT + LH ? LT + LH - start : end - start);
-                    while (cs + len < v_end && slot_occupied<WIDE>(nodes, cs + len)) len++;
+                    while (cs + len < geo.v_halo && slot_occupied<WIDE>(nodes, cs + len)) len++;
+                    if (cs + len >= geo.v_final && geo.v_final < geo.v_halo) info->overflow = 1;      // ran into slots still being built
                     u32 rr = atomicAdd(&info->n_regions, 1u);
                     u64 off = atomicAdd(&info->scratch_used, len);
                     if (rr >= MAX_REGIONS || off + len > scratch_cap) info->overflow = 1;

@@ -232,6 +232,28 @@ class DBGBuilder:
         capi.check(self.L.dbg_export_kmerset(self.h, array.ctypes.data, nul_flag.ctypes.data), "dbg_export_kmerset")
         return array, nul_flag
 
+    def finish_export(self, bases, offs, array=None, nul_flag=None):
+        """last block + finalize + export in one pipelined call (dbg_finish_export) -> (stats, array, nul_flag)"""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = max(len(offs) - 1, 0)
+        P = self.get_stats()["array_size"]
+        if array is None:
+            array = np.empty(P, dtype=NODE32 if self.wide else NODE16)
+        if nul_flag is None:
+            nul_flag = np.empty(P // 8 + 1, dtype=np.uint8)
+        st = capi.dbg_stats()
+        capi.check(self.L.dbg_finish_export(self.h, bases.ctypes.data if bases.size else None, offs.ctypes.data if n else None, n,
+                                            C.byref(st), array.ctypes.data, nul_flag.ctypes.data), "dbg_finish_export")
+        self.stats = st.as_dict()
+        return self.stats, array, nul_flag
+
+    def finish_export_ptr(self, bases_ptr, offs_ptr, n_reads, array_ptr, nul_ptr):
+        st = capi.dbg_stats()
+        capi.check(self.L.dbg_finish_export(self.h, bases_ptr, offs_ptr, int(n_reads), C.byref(st), array_ptr, nul_ptr), "dbg_finish_export")
+        self.stats = st.as_dict()
+        return self.stats
+
     def export_info(self):
         """how the last export_kmerset moved the table (include/dbg_b200.h: dbg_export_info)"""
         a = np.zeros(4, dtype=np.uint64)

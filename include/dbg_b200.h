@@ -221,6 +221,16 @@ int  dbg_get_stats(dbg_ctx *ctx, dbg_stats *stats);
 /* The KmerSet the reference's traversal consumes (kmerSet.h:88-99): array[P] in reference slot
  * layout (16-B nodes, or 32-B nodes on the wide path) and nul_flag[P/8+1], MSB first. */
 int  dbg_export_kmerset(dbg_ctx *ctx, void *array, uint8_t *nul_flag);
+/* build_debruijn_graph's tail in ONE call, for a front end that holds the LAST block of reads in host memory:
+ *   dbg_submit_reads(bases, offs, n_reads) + dbg_finalize(stats) + dbg_export_kmerset(array, nul_flag)
+ * -- same results, but pipelined where the block is large enough for the partitioned build: the copy of the reads, the
+ * extraction, and then insert / reference layout / copy of the image run slice group by slice group, so the image is on
+ * the PCIe link (the bound of the hand-over) while later groups are still being inserted.  n_reads may be 0 (finalize +
+ * export).  `array` should be pinned (dbg_host_alloc / dbg_host_register) for the copies to overlap.
+ * Environment: DBG_B200_FINISH_GROUPS (default 8; < 2 = the plain sequence). */
+int  dbg_finish_export(dbg_ctx *ctx, const char *bases, const uint64_t *offs, uint64_t n_reads, dbg_stats *stats,
+                       void *array, uint8_t *nul_flag);
+
 /* How the last dbg_export_kmerset moved the table: info = {chunks sent compact, chunks sent plain, bytes moved over the
  * link, occupied nodes}.  Default: ONE plain copy of the image ({0, 1, P*node + P/8+1, count}).  With the environment
  * variable DBG_B200_EXPORT=pipe, tables of more than a few million slots travel as occupied nodes only (compacted on the

@@ -553,6 +553,78 @@ def test_pipelined_submit_matches_oracle(dbg, oracle_mod, build_path, monkeypatc
     o.close()
 
 
+FINISH_CASES = [
+    # name, K, reads, init_slots, groups, earlier block, expect
+    ("medium_k31", 31, 100_000, 10_000_000, 8, False, "grouped"),
+    ("medium_k55", 55, 100_000, 10_000_000, 5, False, "grouped"),
+    ("second_block", 31, 100_000, 10_000_000, 8, True, "grouped"),
+    ("wrap_and_long_clusters", 31, 12_000, 1_000_200, 3, False, "grouped"),       # 2 keys wrap past slot P-1, 42 clusters > 64 slots
+    ("dense_patches", 31, 12_000, 700_700, 2, False, "grouped"),                   # load 0.96: ~1800 long clusters re-copied
+    ("too_dense_redone", 31, 36_000, 1_600_000, 4, False, "plain"),                # > 4096 long clusters: one-pass layout + plain copy
+    ("small_call", 31, 1_500, 1_000_200, 3, False, "plain"),                       # not a partitioned block: the plain sequence
+]
+
+
+@pytest.mark.parametrize("name,K,n,init_slots,groups,earlier,expect", FINISH_CASES, ids=[c[0] for c in FINISH_CASES])
+def test_finish_export_matches_oracle(dbg, oracle_mod, build_path, monkeypatch, name, K, n, init_slots, groups, earlier, expect):
+    """dbg_finish_export = submit + finalize + export in one call; where the last block is a partitioned block it runs
+    insert -> layout -> copy slice group by slice group (grouped_finish, csrc/dbg_build.cu).  The table image handed to
+    the caller must be the reference's, bit for bit: windows, the wrap-around region, long clusters (patched after their
+    window left), the k-mer-0 node (inserted on the host copy), and the fall-backs."""
+    if build_path != "partitioned":
+        pytest.skip("partitioned path only")
+    for k in ("DBG_B200_PART_SHIFT", "DBG_B200_BATCH_BASES", "DBG_B200_BATCH_READS"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("DBG_B200_PART_SHIFT", "14")
+    monkeypatch.setenv("DBG_B200_SUB_BASES", "300000")
+    monkeypatch.setenv("DBG_B200_SUB_READS", "5000")
+    monkeypatch.setenv("DBG_B200_FINISH_GROUPS", str(groups))
+    from dbg_assembly_b200 import synth
+    seed = 33 if init_slots < 5_000_000 else 21
+    glen = 250_000 if init_slots < 5_000_000 else 300_000
+    p = synth.make_params(seed=seed, genome_len=glen, read_len=150, insert=500, err=0.01, n_rate=0.002)
+    hb, ho = synth.reads_host(p, 0, n)
+    if init_slots >= 5_000_000:
+        extra = [b"A" * 150] * 40 + [b"T" * 150] * 3      # the k-mer-0 node with saturating lanes
+        eb = np.frombuffer(b"".join(extra), dtype=np.uint8)
+        hb = np.concatenate([hb, eb])
+        ho = np.concatenate([ho, ho[-1] + np.cumsum(np.array([len(x) for x in extra], dtype=ho.dtype))])
+    n_all = len(ho) - 1
+    o = oracle_build(oracle_mod, [(hb, ho)], K, 150, init_slots, load=0.9, wide=K > 31)
+    with dbg.DBGBuilder(K=K, max_read_len=150, init_slots=init_slots, load_factor=0.9) as b:
+        cut = n_all // 4 if earlier else 0
+        if earlier:
+            b.submit(hb, ho[: cut + 1])
+        P = b.get_stats()["array_size"]
+        pa = dbg.capi.PinnedBuffer(P * (32 if K > 31 else 16)); pn = dbg.capi.PinnedBuffer(P // 8 + 1)
+        try:
+            from dbg_assembly_b200.graph import NODE16, NODE32
+            arr = pa.array.view(NODE32 if K > 31 else NODE16); nul = pn.array
+            arr.view(np.uint8)[:] = 0xEE; nul[:] = 0xEE
+            st, _, _ = b.finish_export(hb, ho[cut:], arr, nul)
+            info = b.export_info()
+            if expect == "grouped":
+                assert info["chunks_plain"] >= 2 and info["chunks_compact"] == 0, info          # windows
+            else:
+                assert info["chunks_plain"] == 1, info
+            assert st["count"] == o.count and st["occurrences"] == o.occurrences and st["kmers_logged"] == o.kmers_logged
+            assert st["reads"] == n_all
+            e = o.dump()
+            d = image_to_dump(arr, nul, o.size)
+            for k in ("slot", "kmer", "l", "r") + (("kmer_hi",) if K > 31 else ()):
+                assert np.array_equal(d[k], e[k]), k
+            # and the device image the link pass works on is the same table
+            arr2, nul2 = b.export_kmerset()
+            assert np.array_equal(nul2, nul) and arr2.tobytes() == arr.tobytes()
+            # n_reads == 0 on a finalized context: export only
+            arr.view(np.uint8)[:] = 0x11; nul[:] = 0x11
+            b.finish_export(hb[:0], ho[:1], arr, nul)
+            assert np.array_equal(nul2, nul) and arr2.tobytes() == arr.tobytes()
+        finally:
+            pa.close(); pn.close()
+    o.close()
+
+
 def test_full_size_properties_C2(dbg, build_path, monkeypatch):
     """BASELINE config C2 at full size (3.07 M reads, 3.68e8 occurrences): size-independent properties
     -- conservation of occurrences in the link lanes, idempotent rebuild, and the direct and the
