@@ -318,6 +318,64 @@ def e2e_sharded(args, cfg, sb, d_bases, d_offs, n, L, K, first_read, occ_rank, s
 # ---------------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------
+def kfreq_measure(cfg, world, rank, local, dev, steps, warmup, dist, torch, synth):
+    """C4: the K-mer frequency table of correct_error (kfreq_* C ABI).  A step = zero this rank's part of the 4^K-entry table,
+    all-gather the ranks' reads (N > 1; 1.25 B per occurrence over NVLink), extract every canonical k-mer and count the ones
+    in the rank's index range (table sharded by .cz block), read the counters back.  Device-timed, max over ranks."""
+    from dbg_assembly_b200.kfreq import KmerFreq
+    n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
+    p = synth.make_params(cfg["seed"], cfg["genome_len_total"], L, cfg["insert"], cfg["err"], cfg["n_rate"])
+    mine = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    synth.reads_device(p, rank * n, n, mine.data_ptr(), device=local)
+    everything = torch.empty(world * n * L, dtype=torch.uint8, device=dev) if world > 1 else mine
+    d_offs = torch.arange(world * n + 1, dtype=torch.int64, device=dev) * L
+    torch.cuda.synchronize()
+    kf = KmerFreq(K=K, device=local, block_rank=rank, block_count=world)
+
+    def step():
+        kf.reset()
+        if world > 1:
+            dist.all_gather_into_tensor(everything, mine)
+            torch.cuda.synchronize()
+        kf.submit_device(everything.data_ptr(), d_offs.data_ptr(), world * n, 0, world * n * L)
+        return kf.finalize()
+    for _ in range(warmup):
+        st = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        st = step()
+    e1.record(); torch.cuda.synchronize()
+    # (the library works on its own stream and synchronises inside kfreq_finalize: the events bracket whole steps)
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    hist = kf.histogram()
+    species = int(hist[1:].sum())
+    lo, hi = kf.index_range()
+    if world > 1:
+        t = torch.tensor([species], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        species = int(t.item())
+    occ = int(st["occurrences"])          # every rank extracts every read: the global count
+    kf.close()
+    del mine, everything, d_offs
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "value": occ / (ms * 1e-3), "unit": UNIT, "occurrences_per_step": occ, "species": species,
+            "table_entries_per_gpu": int(hi - lo), "table_bytes_per_gpu": int(hi - lo) * 4, "steps": steps, "warmup": warmup, "dtype": "u32",
+            "config": f"C4: K={K} direct-index frequency table (4^{K} u32 counters, sharded by .cz block over {world} GPUs), "
+                      f"{cfg['genome_len_total'] / 1e6:.1f} Mb genome, {world * n} x {L} bp reads ({world * n * L / cfg['genome_len_total']:.0f}x), "
+                      f"{cfg['err'] * 100:g}% substitutions",
+            "what": "zero the table + (N > 1: all-gather of the reads) + k_build<FreqSink> (fused 2-bit pack, canonical k-mer, RED.ADD into the "
+                    "rank's index range) + counters; every rank extracts all reads and keeps its range (DESIGN.md section 6)"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -345,6 +403,30 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload(args.workload, world, args.scale)
+    if args.workload == "C4":
+        # the other front end of the north star: correct_error's K-mer frequency table, sharded by index range
+        sampler = ClockSampler(local)
+        sampler.start()
+        r = kfreq_measure(cfg, world, rank, local, dev, args.steps, args.warmup, dist, torch, synth)
+        clocks = sampler.stop()
+        peak, peak_src = measured_peaks()
+        ach = r["occurrences_per_step"] * 8 / (r["ms_per_step"] * 1e-3) / 1e9
+        line = {"metric": "canonical k-mers/sec into the K-mer frequency table (count)", "value": r["value"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": {"workload": r["config"], "K": cfg["K"],
+                "l2_policy": "the 68.7 GB table (whole, or its per-GPU shard) and the reads far exceed the 126 MB L2; table re-zeroed every step"},
+                "clocks": clocks, "gpu_launches": 3 * args.steps, "occurrences_per_step": r["occurrences_per_step"], "species": r["species"],
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "kernel": "k_build<FreqSink> (random 4-B RED.ADD per occurrence into the direct-index table)",
+                             "algorithmic_bytes_per_occurrence": 8, "peak_source": peak_src},
+                "e2e": None, "what": r["what"]}
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        sys.stdout.flush()
+        if rank == 0:
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        os.close(real_stdout)
+        return 0
     if args.init_g:
         cfg["init_g"] = args.init_g; cfg["init_g_total"] = args.init_g * world
     n, L, K = cfg["n_reads"], cfg["read_len"], cfg["K"]
@@ -552,6 +634,10 @@ def run_b200(args):
                 line["other_workloads"][wname] = short_workload(args, wname, local, dev, torch, dbg, synth)
             except Exception as e:
                 line["other_workloads"][wname] = {"error": f"{type(e).__name__}: {e}"}
+        try:      # C4's per-GPU share of reads against the WHOLE 4^17 table on this one GPU (68.7 GB)
+            line["other_workloads"]["C4"] = kfreq_measure(workload("C4", 1, 1.0), 1, 0, local, dev, 2, 1, dist, torch, synth)
+        except Exception as e:
+            line["other_workloads"]["C4"] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference on the WHOLE workload, all host threads, one build;
     # ---- and with -t 1 ----

@@ -88,7 +88,7 @@ SYMBOLS = [
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
     "dbg_device_build_table", "seedidx_create", "seedidx_destroy", "seedidx_add_contigs", "seedidx_finalize", "seedidx_export",
     "seedidx_align_reads", "seedidx_launch_count", "seedidx_last_error",
-    "dbg_export_info", "dbg_host_expand_nodes", "dbg_finish_export",
+    "dbg_export_info", "dbg_host_expand_nodes", "dbg_finish_export", "kfreq_reset",
 ]
 
 _lib = None
@@ -177,6 +177,7 @@ def load(build_if_missing: bool = True):
         "kfreq_submit_reads": (C.c_int, [vp, vp, vp, u64]),
         "kfreq_submit_reads_device": (C.c_int, [vp, vp, vp, u64, u64, u64]),
         "kfreq_finalize": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "kfreq_reset": (C.c_int, [vp]),
         "kfreq_index_range": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "kfreq_histogram": (C.c_int, [vp, vp]),
         "kfreq_export": (C.c_int, [vp, i32, i32, vp]),

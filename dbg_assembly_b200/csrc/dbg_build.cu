@@ -171,6 +171,7 @@ struct dbg_ctx {
     uint64_t owner_cap;
     LayoutInfo *d_layout_info;
     LayoutRegion *d_regions;
+    int layout_v;                  // cluster-local pass: 2 (default) or 1 (env DBG_B200_LAYOUT_V)
     int layout_mode;               // 0 cluster-local (default), 1 global atomicMin method (env DBG_B200_LAYOUT=global)
     int pipeline;                  // env DBG_B200_PIPELINE (default 1): a large dbg_submit_reads call scatters sub-block i while sub-block i+1 is copied
     int optimistic;                // env DBG_B200_OPTIMISTIC (default 1): single-pass partition with fixed bucket regions first
@@ -348,6 +349,7 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     c->opt_capb = getenv("DBG_B200_OPT_CAPB") ? atoi(getenv("DBG_B200_OPT_CAPB")) : 0;
     c->stage_cap = getenv("DBG_B200_STAGE_CAP") ? atoi(getenv("DBG_B200_STAGE_CAP")) : -1;
     c->peer_unstaged = getenv("DBG_B200_PEER_UNSTAGED") ? atoi(getenv("DBG_B200_PEER_UNSTAGED")) : 0;
+    c->layout_v = getenv("DBG_B200_LAYOUT_V") && atoi(getenv("DBG_B200_LAYOUT_V")) == 1 ? 1 : 2;
     c->layout_mode = 0;
     if (const char *e = getenv("DBG_B200_LAYOUT")) c->layout_mode = strcmp(e, "global") == 0 ? 1 : 0;
     c->part_mode = 2;
@@ -1514,6 +1516,17 @@ static LayoutGeom layout_geom(const dbg_ctx *c)
     return g;
 }
 
+// the cluster-local layout pass over one window: version 2 (warp-owned word pairs, default) or 1 (block-wide renumbering;
+// env DBG_B200_LAYOUT_V=1, kept for A/B measurements)
+template <bool WIDE, bool TRACK>
+static void launch_layout_clusters(dbg_ctx *c, const NodeT<WIDE> *nodes, const LayoutGeom &geo, u32 *nul32, LayoutInfo *info, LayoutRegion *regions, cudaStream_t s)
+{
+    if (c->layout_v == 1)
+        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, s>>>(nodes, geo, c->d_out, nul32, info, regions, SCRATCH_CAP);
+    else
+        k_layout_clusters2<WIDE, TRACK><<<c->n_sms * (2048 / L2N), L2N, 0, s>>>(nodes, geo, c->d_out, nul32, info, regions, SCRATCH_CAP);
+}
+
 static int ensure_layout_scratch(dbg_ctx *c)
 {
     if (c->owner_cap < SCRATCH_CAP) {
@@ -1541,8 +1554,7 @@ static int run_layout(dbg_ctx *c)
         CU_TRY(cudaMemsetAsync(c->d_nul32, 0, nul_words(c->P) * sizeof(u32), c->stream));
         k_layout_wrapscan<WIDE><<<1, 32, 0, c->stream>>>(nodes, c->n_local, c->P, c->d_layout_info, c->d_regions, SCRATCH_CAP);
         CU_TRY(cudaGetLastError());
-        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info,
-                                                                             c->d_regions, SCRATCH_CAP);
+        launch_layout_clusters<WIDE, TRACK>(c, nodes, geo, c->d_nul32, c->d_layout_info, c->d_regions, c->stream);
         CU_TRY(cudaGetLastError());
         k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info,
                                                                             c->d_regions, c->d_owner);
@@ -1583,7 +1595,7 @@ static int run_layout_sharded(dbg_ctx *c)
     li0.e = ~0ULL;                                                           // no wrap region inside a shard window
     CU_TRY(cudaMemcpyAsync(c->d_layout_info, &li0, sizeof(li0), cudaMemcpyHostToDevice, c->stream));
     if (geo.v_end > geo.v_begin) {
-        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, c->stream>>>(base, geo, c->d_out, nullptr, c->d_layout_info, c->d_regions, SCRATCH_CAP);
+        launch_layout_clusters<WIDE, TRACK>(c, base, geo, nullptr, c->d_layout_info, c->d_regions, c->stream);
         CU_TRY(cudaGetLastError());
         k_layout_regions<WIDE, TRACK><<<c->n_sms * 4, 256, 0, c->stream>>>(base, geo, c->d_out, nullptr, c->d_layout_info, c->d_regions, c->d_owner);
         CU_TRY(cudaGetLastError());
@@ -1699,7 +1711,7 @@ static int grouped_finish(dbg_ctx *c, uint32_t capb, FinishExport *fx)
         rc = ev_begin(c, s, &evl);
         if (rc) return rc;
         evl.slot = 2;
-        k_layout_clusters<WIDE, TRACK><<<c->n_sms * (2048 / LT), LT, 0, s>>>(nodes, geo, c->d_out, c->d_nul32, c->d_layout_info, c->d_regions, SCRATCH_CAP);
+        launch_layout_clusters<WIDE, TRACK>(c, nodes, geo, c->d_nul32, c->d_layout_info, c->d_regions, s);
         CU_TRY(cudaGetLastError());
         c->launches++;
         CU_TRY(cudaEventRecord(evl.b, s));

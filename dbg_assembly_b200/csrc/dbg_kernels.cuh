@@ -1292,6 +1292,148 @@ __global__ void __launch_bounds__(LT, 2048 / LT) k_layout_clusters(const NodeT<W
     }
 }
 
+// ---- version 2 of the cluster-local layout pass ------------------------------------------------------------------
+// Same algorithm, different work assignment.  A tile is L2T slots + LH halo = L2S slots = L2W occupancy words, worked on by
+// L2S/2 threads: every thread LOADS two slots, and in the replay / write-out phases every WARP owns two occupancy words
+// (64 slots, about 32 of them occupied at load 0.5), lane l taking the l-th occupied slot of the pair -- full warps without
+// the block-wide renumbering (which cost a 10-word prefix walk per key, twice), and the hash is computed only for keys that
+// are replayed here (not for singleton clusters, not for halo keys that belong to the next tile).
+#ifndef DBG_L2T
+#define DBG_L2T 448
+#endif
+constexpr int L2T = DBG_L2T;            // slots per tile (multiple of 64)
+constexpr int L2S = L2T + LH;           // slots staged
+constexpr int L2W = L2S / 32;           // occupancy words
+constexpr int L2N = L2S / 2;            // threads per CTA
+static_assert(L2T % 64 == 0 && L2N % 32 == 0, "tile geometry");
+
+__device__ __forceinline__ void cluster_bounds2(const u32 *W, int k, bool prev_occ, int &start, int &end)
+{
+    int w = k >> 5;
+    u32 m = ~W[w] & ((1u << (k & 31)) - 1u);
+    start = -2;
+    for (;;) {
+        if (m) { start = (w << 5) + 32 - __clz(m); break; }
+        if (--w < 0) break;
+        m = ~W[w];
+    }
+    if (start == -2) start = prev_occ ? -1 : 0;
+    w = k >> 5;
+    m = ~W[w] & ~((2u << (k & 31)) - 1u);
+    end = L2S + 1;
+    for (;;) {
+        if (m) { end = (w << 5) + __ffs(m) - 1; break; }
+        if (++w >= L2W) break;
+        m = ~W[w];
+    }
+}
+
+// position of the r-th (0-based) set bit of w
+__device__ __forceinline__ u32 nth_set_bit(u32 w, u32 r)
+{
+    u32 pos = 0, t;
+    t = __popc(w & 0xFFFFu); if (r >= t) { pos += 16; r -= t; w >>= 16; }
+    t = __popc(w & 0xFFu);   if (r >= t) { pos += 8;  r -= t; w >>= 8; }
+    t = __popc(w & 0xFu);    if (r >= t) { pos += 4;  r -= t; w >>= 4; }
+    t = __popc(w & 0x3u);    if (r >= t) { pos += 2;  r -= t; w >>= 2; }
+    t = w & 1u;              if (r >= t) { pos += 1; }
+    return pos & 31u;
+}
+
+template <bool WIDE, bool TRACK>
+__global__ void __launch_bounds__(L2N, 2048 / L2N) k_layout_clusters2(const NodeT<WIDE> *__restrict__ nodes, LayoutGeom geo, void *out, u32 *nul32,
+                                                                      LayoutInfo *info, LayoutRegion *regions, u64 scratch_cap)
+{
+    constexpr int NQ = WIDE ? 3 : 2;
+    __shared__ ulonglong2 s_raw[NQ * L2S];
+    __shared__ u64 s_owner[L2S];
+    __shared__ u32 s_W[L2W];
+    __shared__ int s_prev;
+    const u64 e_skip = info->e, g_skip = info->g;
+    const u64 v_end = geo.v_end;
+    const int t = threadIdx.x;
+    const u32 lane = t & 31, warp = t >> 5;
+    for (u64 i0 = geo.v_begin + (u64)blockIdx.x * L2T; i0 < v_end; i0 += (u64)gridDim.x * L2T) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int k = t + j * L2N;
+            const u64 s = i0 + k;
+            NodeRegs nd; nd.klo = 0; nd.khi = 0; nd.nord = 0; nd.c0 = 0; nd.c1 = 0;
+            if (s < geo.v_halo) load_node(nodes + s, nd);
+            const bool o = (nd.klo | nd.khi) != 0;
+            if (WIDE) { s_raw[3 * k] = make_ulonglong2(nd.klo, nd.khi); s_raw[3 * k + 1] = make_ulonglong2(nd.nord, 0ULL); s_raw[3 * k + 2] = make_ulonglong2(nd.c0, nd.c1); }
+            else { s_raw[2 * k] = make_ulonglong2(nd.klo, nd.nord); s_raw[2 * k + 1] = make_ulonglong2(nd.c0, nd.c1); }
+            s_owner[k] = EMPTY_PRI;
+            const u32 bal = __ballot_sync(0xffffffffu, o);
+            if (lane == 0) {
+                s_W[k >> 5] = bal;
+                if (nul32 && k < L2T && s < v_end) nul32[s >> 5] = __byte_perm(__brev(bal), 0, 0x0123);
+            }
+            if (k < L2T && s < v_end && !o) write_image<WIDE>(out, s, 0, 0, 0);
+        }
+        if (t == 0) s_prev = (i0 > geo.v_first) && slot_occupied<WIDE>(nodes, i0 - 1);
+        __syncthreads();
+        // ---- replay: this warp's two words ----
+        const u32 w0 = s_W[2 * warp], w1 = s_W[2 * warp + 1];
+        const u32 c0 = __popc(w0), n_mine = c0 + __popc(w1);
+        u32 mine[2];                    // per pass: (home - i0) << 16 | slot index in the tile; 0xffffffff: nothing left for phase 3
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            const u32 idx = lane + 32 * pass;
+            mine[pass] = 0xffffffffu;
+            if (idx >= n_mine) continue;
+            const int k = idx < c0 ? (int)(64 * warp + nth_set_bit(w0, idx)) : (int)(64 * warp + 32 + nth_set_bit(w1, idx - c0));
+            int start, end;
+            cluster_bounds2(s_W, k, s_prev != 0, start, end);
+            if (start < 0 || start >= L2T) continue;                  // belongs to the previous / next tile
+            const u64 cs = i0 + start;
+            if (cs < g_skip || cs == e_skip) continue;                // wrap-around region: k_layout_regions
+            if (end > L2S || end - start > LH) {
+                if (k == start) {
+                    u64 len = (u64)(end > L2S ? L2S - start : end - start);
+                    while (cs + len < geo.v_halo && slot_occupied<WIDE>(nodes, cs + len)) len++;
+                    if (cs + len >= geo.v_final && geo.v_final < geo.v_halo) info->overflow = 1;
+                    u32 rr = atomicAdd(&info->n_regions, 1u);
+                    u64 off = atomicAdd(&info->scratch_used, len);
+                    if (rr >= MAX_REGIONS || off + len > scratch_cap) info->overflow = 1;
+                    else { regions[rr].a = cs; regions[rr].n = len; regions[rr].off = off; regions[rr].wrap = 0; }
+                }
+                continue;
+            }
+            u64 klo, khi = 0, nord;
+            if (WIDE) { const ulonglong2 a = s_raw[3 * k]; klo = a.x; khi = a.y; nord = s_raw[3 * k + 1].x; }
+            else { const ulonglong2 a = s_raw[2 * k]; klo = a.x; nord = a.y; }
+            if (end - start == 1) {
+                // alone between two empty slots: it sits at its home slot, nothing to replay (no hash needed either)
+                const ulonglong2 cc = s_raw[NQ * k + NQ - 1];
+                write_image<WIDE>(out, i0 + k, klo, khi, (u64)pack_link(cc.x) | ((u64)pack_link(cc.y) << 32));
+                continue;
+            }
+            u64 cur = TRACK ? ~nord : i0 + k;
+            u32 pos = (u32)(home_virtual(geo, klo, khi, WIDE) - i0);
+            mine[pass] = (pos << 16) | (u32)k;
+            for (;;) {
+                u64 old = atomicMin(&s_owner[pos], cur);
+                if (old == EMPTY_PRI) break;
+                if (old > cur) cur = old;      // we took the slot; carry the displaced key onwards
+                pos++;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            if (mine[pass] == 0xffffffffu) continue;
+            u32 pos = mine[pass] >> 16;
+            const int k = (int)(mine[pass] & 0xffffu);
+            const u64 pri = TRACK ? ~(WIDE ? s_raw[3 * k + 1].x : s_raw[2 * k].y) : i0 + k;
+            while (s_owner[pos] != pri) pos++;
+            const ulonglong2 a = s_raw[NQ * k], cc = s_raw[NQ * k + NQ - 1];
+            write_image<WIDE>(out, i0 + pos, a.x, WIDE ? a.y : 0ULL, (u64)pack_link(cc.x) | ((u64)pack_link(cc.y) << 32));
+        }
+        __syncthreads();
+    }
+}
+
 // long clusters and the wrap-around region: priority probing (atomicMin on the ordinal) inside a private scratch
 template <bool WIDE, bool TRACK>
 __global__ void __launch_bounds__(256) k_layout_regions(const NodeT<WIDE> *__restrict__ nodes, LayoutGeom geo, void *out, u32 *nul32,

@@ -167,6 +167,18 @@ extern "C" int kfreq_create(kfreq_ctx **out, int32_t K, int32_t device, int32_t 
     return DBG_OK;
 }
 
+// clear the table and the counters (a fresh count on the same context: benchmarks, repeated libraries)
+extern "C" int kfreq_reset(kfreq_ctx *c)
+{
+    if (!c) return kset_err(DBG_ERR_INVALID, "NULL ctx");
+    KCU(cudaSetDevice(c->device));
+    KCU(cudaMemsetAsync(c->d_table, 0, (c->hi - c->lo + 4) * sizeof(u32), c->stream));
+    KCU(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(u64), c->stream));
+    KCU(cudaStreamSynchronize(c->stream));
+    c->reads = 0;
+    return DBG_OK;
+}
+
 static int kfreq_count_device(kfreq_ctx *c, const char *d_bases, const u64 *d_offs, uint64_t n_reads, uint64_t first_base, uint64_t total_bases)
 {
     if (n_reads == 0 || total_bases == 0) return DBG_OK;

@@ -54,6 +54,9 @@ class KmerFreq:
         self._check(self.L.kfreq_submit_reads_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases)),
                     "kfreq_submit_reads_device")
 
+    def reset(self):
+        self._check(self.L.kfreq_reset(self.h), "kfreq_reset")
+
     def finalize(self):
         occ, reads = C.c_uint64(0), C.c_uint64(0)
         self._check(self.L.kfreq_finalize(self.h, C.byref(occ), C.byref(reads)), "kfreq_finalize")

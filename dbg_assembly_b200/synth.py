@@ -16,6 +16,9 @@ CONFIGS = {
     "C2": dict(seed=2, genome_len=4_600_000, read_len=150, insert=500, err=0.01, n_rate=0.001, n_reads=3_066_666, K=31, max_read_len=150, init_g=0.2),
     # C3: yeast-scale 12 Mb, 100 bp reads, K=63 (128-bit path)
     "C3": dict(seed=3, genome_len=12_000_000, read_len=100, insert=500, err=0.01, n_rate=0.0, n_reads=12_000_000, K=63, max_read_len=100, init_g=0.6),
+    # C4: the correct_error K=17 frequency table on 50x of a 100 Mb genome over 8 GPUs -- PER GPU: 12.5 Mb of genome and
+    # 4.17 M reads (x8 = 100 Mb, 33.3 M reads, 4.47e9 occurrences); the 4^17-entry table is sharded by .cz block
+    "C4": dict(seed=4, genome_len=12_500_000, read_len=150, insert=500, err=0.01, n_rate=0.0, n_reads=4_166_666, K=17, max_read_len=150, init_g=0.0),
     # C5s: the human-scale configuration (3.1 Gb, 30x PE150, K=31, 8 GPUs) at 1/8 of its size PER GPU -- 48.4 Mb of genome and
     # 9.69 M reads per GPU (x8 GPUs = 387.5 Mb, 77.5 M reads, 9.3e9 occurrences); DESIGN.md has the memory plan of the full C5
     "C5s": dict(seed=5, genome_len=48_437_500, read_len=150, insert=500, err=0.01, n_rate=0.0, n_reads=9_687_500, K=31, max_read_len=150, init_g=0.7),

@@ -355,6 +355,7 @@ int  kfreq_submit_reads(kfreq_ctx *ctx, const char *bases, const uint64_t *offs,
 int  kfreq_submit_reads_device(kfreq_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads,
                                uint64_t first_base, uint64_t total_bases);
 int  kfreq_finalize(kfreq_ctx *ctx, uint64_t *n_occurrences, uint64_t *n_reads);
+int  kfreq_reset(kfreq_ctx *ctx);     /* zero the table and the counters: a fresh count on the same context */
 int  kfreq_index_range(kfreq_ctx *ctx, uint64_t *lo, uint64_t *hi);
 /* hist[f] = species seen f times (f = 65535: that often or more), over the owned index range */
 int  kfreq_histogram(kfreq_ctx *ctx, uint64_t hist[65536]);
