@@ -507,10 +507,19 @@ def run_b200(args):
         extra["sub_blocks_used"] = sb.sub_blocks_used
         sc_ms = float(np.mean(scatter_ms))
         if sc_ms > 0:
-            # NVLink figure of the fused scatter kernel(s): bytes this rank stored into its peers' buffers / kernel time
-            extra["nvlink"] = {"scatter_kernel_ms_per_step": sc_ms, "bytes_out_per_step": extra["exchange_bytes_per_step_rank0"],
-                               "gbs_out": extra["exchange_bytes_per_step_rank0"] / (sc_ms * 1e-3) / 1e9,
-                               "what": "k_build<StagedScatterSink<OPT>> by owner: extraction fused with stores into the owners' receive regions over NVLink peer mappings (rank 0, CUDA events)"}
+            # NVLink figure: bytes this rank moved to/from its peers over the kernel that moves them (rank 0, CUDA events) --
+            # pull: the owners' reads inside k_insert_tuples_pull (by symmetry what rank 0 reads = what it serves);
+            # peer: the stores of the fused scatter kernel into the owners' receive regions
+            xb = extra["exchange_bytes_per_step_rank0"]
+            if sb.exchange == "pull" and not sb.opt_fallbacks:
+                im = float(np.mean(insert_ms))
+                extra["nvlink"] = {"scatter_kernel_ms_per_step": sc_ms, "insert_kernel_ms_per_step": im, "bytes_in_per_step": xb,
+                                   "gbs_in": xb / (im * 1e-3) / 1e9 if im > 0 else None,
+                                   "what": "pull exchange: k_build<StagedScatterSink<OPT>> partitions by (owner, table slice) into the LOCAL send buffer (no NVLink); "
+                                           "k_insert_tuples_pull reads the peers' regions over NVLink peer mappings while it inserts"}
+            else:
+                extra["nvlink"] = {"scatter_kernel_ms_per_step": sc_ms, "bytes_out_per_step": xb, "gbs_out": xb / (sc_ms * 1e-3) / 1e9,
+                                   "what": "k_build<StagedScatterSink<OPT>> by owner: extraction fused with stores into the owners' receive regions over NVLink peer mappings"}
     else:
         occ_total = st["occurrences"]
         nodes_total = st["count"]
@@ -680,9 +689,11 @@ def main():
                     help="reference arm / cpu_baseline: 0 = the whole workload (default), N = only its first N reads (said so in the output)")
     ap.add_argument("--ref-budget-s", type=float, default=900.0,
                     help="reference arm: wall-clock budget; at least 1 warm-up and 2 timed full builds run, more while it lasts")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_exact", "peer_sliced", "nccl"],
-                    help="multi-GPU: 'peer' = ONE extraction pass stores tuples into fixed regions of the owners' buffers over NVLink, pipelined "
-                         "with the owners' inserts; 'peer_exact' = count pass + exact offsets + scatter; 'nccl' = pack + send/recv")
+    ap.add_argument("--exchange", default="pull", choices=["pull", "peer", "peer_exact", "peer_sliced", "nccl"],
+                    help="multi-GPU: 'pull' (default) = ONE extraction pass partitions by (owner, table slice) into the source's own send buffer, "
+                         "the owners read their regions over NVLink inside the bucketed insert (falls back to 'peer' beyond 4096 buckets); "
+                         "'peer' = ONE extraction pass stores tuples into fixed regions of the owners' buffers over NVLink, then an owner-side "
+                         "partition + insert; 'peer_exact' = count pass + exact offsets + scatter; 'nccl' = pack + send/recv")
     ap.add_argument("--sub-blocks", type=int, default=4, help="multi-GPU 'peer': sub-blocks per step (scatter k+1 overlaps insert k)")
     ap.add_argument("--e2e-api", default="finish_export", choices=["finish_export", "separate"],
                     help="N=1 e2e leg: the fused, pipelined dbg_finish_export (default) or the three separate calls")

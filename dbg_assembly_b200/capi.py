@@ -88,7 +88,7 @@ SYMBOLS = [
     "kfreq_index_range", "kfreq_histogram", "kfreq_export", "kfreq_write_cz", "kfreq_last_error",
     "dbg_device_build_table", "seedidx_create", "seedidx_destroy", "seedidx_add_contigs", "seedidx_finalize", "seedidx_export",
     "seedidx_align_reads", "seedidx_launch_count", "seedidx_last_error",
-    "dbg_export_info", "dbg_host_expand_nodes", "dbg_finish_export", "kfreq_reset",
+    "dbg_export_info", "dbg_host_expand_nodes", "dbg_finish_export", "kfreq_reset", "dbg_exchange_scatter_pull_device", "dbg_insert_pull_device",
 ]
 
 _lib = None
@@ -193,6 +193,8 @@ def load(build_if_missing: bool = True):
         "seedidx_launch_count": (u64, [vp]),
         "seedidx_last_error": (C.c_char_p, []),
         "dbg_export_info": (C.c_int, [vp, vp]),
+        "dbg_exchange_scatter_pull_device": (C.c_int, [vp, vp, vp, u64, u64, u64, u64, i32, vp, C.c_uint32, vp, vp]),
+        "dbg_insert_pull_device": (C.c_int, [vp, vp, i32, C.c_uint32, vp, C.c_uint32, u64, vp]),
         "dbg_finish_export": (C.c_int, [vp, vp, vp, u64, C.POINTER(dbg_stats), vp, vp]),
         "dbg_host_expand_nodes": (u64, [vp, u64, vp, vp, i32]),
     }

@@ -1355,6 +1355,106 @@ extern "C" int dbg_exchange_scatter_opt_device(dbg_ctx *c, const char *d_bases, 
     return DBG_OK;
 }
 
+// PULL exchange, source side: ONE extraction pass partitions this rank's occurrences by (owner, table slice of the owner) into
+// its own send buffer d_send (bucket = owner * n_slices + slice, a fixed region of `capb` tuples per bucket, space reserved
+// with atomics on d_fill); nothing crosses NVLink here.  d_fill[n_parts * n_slices] != 0: a region would have overflowed.
+extern "C" int dbg_exchange_scatter_pull_device(dbg_ctx *c, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                                uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *d_send, uint32_t capb,
+                                                uint32_t *d_fill, void *stream)
+{
+    if (!c || !d_send || !d_fill) return set_err(DBG_ERR_INVALID, "dbg_exchange_scatter_pull_device: NULL argument");
+    const uint64_t nbt64 = (uint64_t)(n_parts > 0 ? n_parts : 0) * c->n_buckets;
+    if (n_parts < 1 || nbt64 > 4096) return set_err(DBG_ERR_INVALID, "n_parts x table slices = %llu buckets (1..4096)", (unsigned long long)nbt64);
+    if (capb < INS_TILE || capb % INS_TILE) return set_err(DBG_ERR_INVALID, "capb must be a multiple of %d", INS_TILE);
+    const uint32_t nbt = (uint32_t)nbt64;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemsetAsync(d_fill, 0, ((size_t)nbt + 1) * sizeof(u32), s));
+    if (n_reads == 0 || total_bases == 0) return DBG_OK;
+    uint64_t abase = first_base & ~15ull;
+    if (((uintptr_t)(d_bases + abase) & 15) != 0) return set_err(DBG_ERR_INVALID, "device base buffer must be 16-byte aligned");
+    uint64_t n_chunks = (first_base + total_bases - abase + CB - 1) / CB;
+    if (n_chunks > 0x7fffffffull || total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
+    int rc = ensure_chunks(c, n_chunks);
+    if (rc) return rc;
+    // the batch must still fit next to nbt bucket counters in shared memory
+    uint32_t cap0 = stage_cap(c, c->wide);
+    const size_t tb = c->wide ? 32 : 16;
+    while (cap0 > (uint32_t)BLOCK * G && cap0 * tb + cap0 * 6 + (size_t)nbt * 12 > 98 * 1024) cap0 /= 2;
+    if (cap0 == 0 || cap0 * tb + cap0 * 6 + (size_t)nbt * 12 > 150 * 1024) return set_err(DBG_ERR_STATE, "staged scatter not possible with %u buckets", nbt);
+    if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
+    CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+    c->undo_reads = n_reads;
+    EvPair ev;
+    rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    k_chunk_first<<<(unsigned)((n_reads + 1 + 255) / 256), 256, 0, s>>>((const u64 *)d_offs, n_reads, abase, n_chunks, c->d_chunk_first);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    BuildArgs a;
+    a.bases = d_bases; a.offs = (const u64 *)d_offs; a.n_reads = n_reads; a.abase = abase; a.end_base = first_base + total_bases;
+    a.chunk_first = c->d_chunk_first; a.read_index0 = first_read_index; a.K = c->prm.K; a.R = c->prm.max_read_len;
+    a.stage_words = stage_words_for(c->prm.max_read_len); a.count_stats = 1; a.seed = c->prm.payload_mode == 1;
+    const uint64_t div = (c->P + n_parts - 1) / n_parts;
+    auto fill_sink = [&](auto &st) {
+        st.t = view_of(c); st.shift = c->part_shift; st.n_buckets = nbt; st.cap = cap0; st.matrix = nullptr; st.tuples = (u64 *)d_send;
+        st.fill = d_fill; st.capb = capb; st.flag = d_fill + nbt; st.filled = 0;
+        st.div = div; st.div_M = (uint64_t)((((unsigned __int128)1) << 64) / div); st.dst_ptrs = nullptr; st.region_off = 0; st.nb_local = c->n_buckets;
+    };
+    if (c->wide) { StagedScatterSink<true, true> st; fill_sink(st); rc = launch_build<true>(c, a, st, n_chunks, s, 0, StageBuf<true>::bytes(cap0, nbt)); }
+    else { StagedScatterSink<false, true> st; fill_sink(st); rc = launch_build<false>(c, a, st, n_chunks, s, 0, StageBuf<false>::bytes(cap0, nbt)); }
+    if (rc) return rc;
+    c->reads_total += n_reads;
+    ev.slot = 7;
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
+// PULL exchange, owner side: insert this shard's buckets slice by slice, reading the n_src sources' regions over NVLink
+// (d_src_ptrs[q] = base of source q's send buffer: a peer mapping, or the local buffer for q == this rank; d_fills =
+// the all-gathered fill counters, source q's at d_fills + q * fill_stride).
+extern "C" int dbg_insert_pull_device(dbg_ctx *c, void *const *d_src_ptrs, int32_t n_src, uint32_t capb, const uint32_t *d_fills,
+                                      uint32_t fill_stride, uint64_t n_tuples_upper, void *stream)
+{
+    if (!c || !d_src_ptrs || !d_fills) return set_err(DBG_ERR_INVALID, "dbg_insert_pull_device: NULL argument");
+    if (c->finalized) return set_err(DBG_ERR_STATE, "insert after finalize");
+    if (n_src < 1 || n_src > 64 || capb < INS_TILE || capb % INS_TILE) return set_err(DBG_ERR_INVALID, "dbg_insert_pull_device: bad geometry");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    c->guard_total += n_tuples_upper;
+    PullSrc ps;
+    ps.ptrs = (const u64 *const *)d_src_ptrs; ps.fills = d_fills; ps.n_src = (u32)n_src; ps.fill_stride = fill_stride;
+    ps.region0 = (u32)c->prm.shard_rank * c->n_buckets; ps.capb = capb;
+    if (c->n_shards <= 1) ps.region0 = 0;
+    const uint64_t tiles = (uint64_t)(capb / INS_TILE) * n_src * c->n_buckets;
+    const uint64_t persistent = (uint64_t)c->n_sms * INS_CTAS;
+    const unsigned grid = (unsigned)(tiles < persistent ? tiles : persistent);
+    EvPair ev, ei;
+    int rc = ev_begin(c, s, &ev);
+    if (rc) return rc;
+    rc = ev_begin(c, s, &ei);
+    if (rc) return rc;
+    ei.slot = 6;
+    CU_TRY(cudaMemsetAsync(c->d_counters + 7, 0, sizeof(u64), s));
+    if (c->wide) {
+        if (c->track) k_insert_tuples_pull<true, true><<<grid, INS_BLOCK, 0, s>>>(ps, view_of(c), c->n_buckets, c->part_shift, c->d_counters + 7);
+        else k_insert_tuples_pull<true, false><<<grid, INS_BLOCK, 0, s>>>(ps, view_of(c), c->n_buckets, c->part_shift, c->d_counters + 7);
+    } else {
+        if (c->track) k_insert_tuples_pull<false, true><<<grid, INS_BLOCK, 0, s>>>(ps, view_of(c), c->n_buckets, c->part_shift, c->d_counters + 7);
+        else k_insert_tuples_pull<false, false><<<grid, INS_BLOCK, 0, s>>>(ps, view_of(c), c->n_buckets, c->part_shift, c->d_counters + 7);
+    }
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    c->part_blocks++;
+    CU_TRY(cudaEventRecord(ei.b, s));
+    c->build_ev.push_back(ei);
+    CU_TRY(cudaEventRecord(ev.b, s));
+    c->build_ev.push_back(ev);
+    return DBG_OK;
+}
+
 // an optimistic scatter overflowed: take back what it added to this context's side counters (reads, occurrences, k-mer-0
 // lanes), so that the exact exchange can redo the block
 extern "C" int dbg_exchange_scatter_undo(dbg_ctx *c, void *stream)

@@ -453,6 +453,9 @@ struct StagedScatterSink {
     u64 div = 0, div_M = 0;
     u64 *const *dst_ptrs = nullptr;
     u64 region_off = 0;
+    // PULL exchange (OPT only, dst_ptrs == nullptr): buckets = (owner, table slice of the owner) = owner * nb_local + slice, all
+    // stored into this source's LOCAL send buffer `tuples`; the owners read their regions over NVLink (k_insert_tuples_pull)
+    u32 nb_local = 0;
     StageBuf<WIDE> sb;
     u32 filled;
 
@@ -483,8 +486,11 @@ struct StagedScatterSink {
                 } else {
                     u64 hh = WIDE ? hash_code_wide(o[g].klo, o[g].khi) : hash_code(o[g].klo);
                     const u64 home = mod_P(hh, t.P, t.M);
-                    if (OPT && div) { u32 b = (u32)__umul64hi(home, div_M); if ((u64)(b + 1) * div <= home) b++; bkt[g] = b; }
-                    else bkt[g] = (u32)((home - t.lo) >> shift);
+                    if (OPT && div) {
+                        u32 b = (u32)__umul64hi(home, div_M); if ((u64)(b + 1) * div <= home) b++;
+                        if (nb_local) b = b * nb_local + (u32)((home - (u64)b * div) >> shift);
+                        bkt[g] = b;
+                    } else bkt[g] = (u32)((home - t.lo) >> shift);
                     mine++;
                 }
             }
@@ -991,6 +997,76 @@ __global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples(const u64
 #pragma unroll
         for (int r = 0; r < INS_ROUNDS; r++)
             if ((klo[r] | khi[r]) != 0)      // tuples never carry the k-mer-0 key, so 0 = past the end
+                insert_one<WIDE, TRACK>(t, klo[r], khi[r], (u32)(meta[r] & 15), (u32)((meta[r] >> 4) & 15), meta[r] >> 8, n_new, n_conf);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { n_new += __shfl_xor_sync(0xffffffffu, n_new, s); n_conf += __shfl_xor_sync(0xffffffffu, n_conf, s); }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_new) atomicAdd(t.counters + CNT_NEW, (u64)n_new);
+        if (n_conf) atomicAdd(t.counters + CNT_CONFLICT, (u64)n_conf);
+    }
+}
+
+// Owner side of the PULL exchange: every source rank q partitioned its occurrences by (owner, table slice) into its own send
+// buffer (region of `capb` tuples per bucket, fills[q * fill_stride + bucket] of them used); the owner walks ITS buckets slice
+// by slice and reads the n_src regions of a slice straight from the sources' memory over NVLink peer mappings -- long
+// contiguous reads, no receive buffer, no owner-side partition pass.  Same tile scheduling, L2 prefetch of the next slice
+// and insert as k_insert_tuples.
+struct PullSrc {
+    const u64 *const *ptrs;   // [n_src] base of every source's send buffer (peer mappings; the own one is local)
+    const u32 *fills;         // all-gathered fill counters
+    u32 n_src, fill_stride;
+    u32 region0;              // first bucket of this owner in a source's buffer: rank * n_buckets
+    u32 capb;                 // tuples per region (multiple of INS_TILE)
+};
+
+template <bool WIDE, bool TRACK>
+__global__ void __launch_bounds__(INS_BLOCK, INS_CTAS) k_insert_tuples_pull(PullSrc ps, TableView t, u32 n_buckets, int shift, u64 *tile_counter)
+{
+    constexpr int TW = WIDE ? 4 : 2;
+    u32 n_new = 0, n_conf = 0;
+    const u32 tpr = ps.capb / INS_TILE;                       // tiles per region
+    const u64 tiles_per_bucket = (u64)tpr * ps.n_src;
+    const u64 n_tiles = tiles_per_bucket * n_buckets;
+    __shared__ u64 s_tile[2];
+    u64 next_tile = 0;
+    if (threadIdx.x == 0) next_tile = __ldcg(t.counters + CNT_ERROR) ? (1ULL << 40) : atomicAdd(tile_counter, 1ULL);
+    for (u32 par = 0;; par ^= 1) {
+        if (threadIdx.x == 0) s_tile[par] = next_tile;
+        __syncthreads();
+        const u64 ti = s_tile[par];
+        if (ti >= n_tiles) break;
+        if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1ULL);
+        const u32 b = (u32)(ti / tiles_per_bucket);
+        const u32 within = (u32)(ti - (u64)b * tiles_per_bucket);
+        const u32 q = within / tpr;
+        const u32 off = (within - q * tpr) * INS_TILE;
+        // this tile's share of the NEXT slice goes to L2 (by position inside the bucket's span, used or not)
+        if (b + 1 < n_buckets && ((u64)(b + 1) << shift) < t.n_local) {
+            const u64 slice_lo = (u64)(b + 1) << shift;
+            u64 slice_n = (u64)1 << shift;
+            if (slice_lo + slice_n > t.n_local) slice_n = t.n_local - slice_lo;
+            const u64 lines = slice_n * sizeof(NodeT<WIDE>) / 128;
+            const u64 l0 = lines * within / tiles_per_bucket, l1 = lines * (within + 1) / tiles_per_bucket;
+            const char *basep = reinterpret_cast<const char *>(static_cast<const NodeT<WIDE> *>(t.nodes) + slice_lo);
+            for (u64 l = l0 + threadIdx.x; l < l1; l += INS_BLOCK) asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + l * 128));
+        }
+        const u32 used = __ldg(ps.fills + (size_t)q * ps.fill_stride + ps.region0 + b);
+        if (off >= used) continue;                             // unused tail of the region (block-uniform)
+        const u64 *src = ps.ptrs[q] + ((u64)(ps.region0 + b) * ps.capb + off) * TW;
+        u64 klo[INS_ROUNDS], khi[INS_ROUNDS], meta[INS_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < INS_ROUNDS; r++) {
+            const u32 i = (u32)r * INS_BLOCK + threadIdx.x;
+            klo[r] = 0; khi[r] = 0; meta[r] = 0;
+            if (off + i < used) {
+                if (WIDE) { u64 z; ld256_cs(reinterpret_cast<const ulonglong2 *>(src) + 2 * i, klo[r], khi[r], meta[r], z); }
+                else { ulonglong2 x = __ldcs(reinterpret_cast<const ulonglong2 *>(src) + i); klo[r] = x.x; meta[r] = x.y; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < INS_ROUNDS; r++)
+            if ((klo[r] | khi[r]) != 0)
                 insert_one<WIDE, TRACK>(t, klo[r], khi[r], (u32)(meta[r] & 15), (u32)((meta[r] >> 4) & 15), meta[r] >> 8, n_new, n_conf);
     }
 #pragma unroll

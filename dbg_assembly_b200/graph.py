@@ -114,6 +114,17 @@ class DBGBuilder:
                                                     int(total_bases), int(first_read_index), int(n_parts), d_tuples_ptr,
                                                     int(capacity), d_counts_ptr, stream), "dbg_extract_tuples_device")
 
+    # ---- pull exchange ----
+    def exchange_scatter_pull_device(self, d_bases_ptr, d_offs_ptr, n_reads, first_base, total_bases, first_read_index, n_parts,
+                                     d_send_ptr, capb, d_fill_ptr, stream=None):
+        capi.check(self.L.dbg_exchange_scatter_pull_device(self.h, d_bases_ptr, d_offs_ptr, int(n_reads), int(first_base), int(total_bases),
+                                                           int(first_read_index), int(n_parts), d_send_ptr, int(capb), d_fill_ptr, stream),
+                   "dbg_exchange_scatter_pull_device")
+
+    def insert_pull_device(self, d_src_ptrs_ptr, n_src, capb, d_fills_ptr, fill_stride, n_tuples_upper, stream=None):
+        capi.check(self.L.dbg_insert_pull_device(self.h, d_src_ptrs_ptr, int(n_src), int(capb), d_fills_ptr, int(fill_stride),
+                                                 int(n_tuples_upper), stream), "dbg_insert_pull_device")
+
     # ---- fused exchange over peer memory ----
     def peer_alloc(self, nbytes):
         """-> (device pointer, 64-byte IPC handle) of a cudaMalloc'ed receive buffer on this context's device"""

@@ -101,7 +101,7 @@ class LocalShards:
     tests run on a single device, and what a single-process front end would run on several."""
 
     def __init__(self, n, K, max_read_len, init_slots, load_factor=0.7, devices=None, track_order=True, force_wide=False,
-                 by_slice=False, optimistic=False, cap_pair=None):
+                 by_slice=False, optimistic=False, cap_pair=None, pull=False):
         import torch
         from .graph import DBGBuilder
         self.n = n
@@ -114,6 +114,7 @@ class LocalShards:
         self.P_request, self.load_factor = init_slots, load_factor
         self.blobs = None
         self.optimistic, self.cap_pair = optimistic, cap_pair
+        self.pull = pull           # PULL exchange: sources partition by (owner, slice) locally, owners read the regions (cap_pair = capb)
         self.overflows = 0
 
     def close(self):
@@ -154,11 +155,53 @@ class LocalShards:
                 torch.cuda.synchronize(self.devices[q])
         return allf[:, :n].sum(dim=0).tolist()
 
+    def _add_blocks_pull(self, blocks):
+        """one round of the PULL exchange (dbg_exchange_scatter_pull_device / dbg_insert_pull_device); None = a region would
+        have overflowed, nothing was inserted and the side counters were restored"""
+        torch, n = self.torch, self.n
+        nbl = self.b[0].partition_info()[0]
+        nbt = n * nbl
+        biggest = max([blk[4] for blk in blocks if blk is not None] + [1])
+        capb = self.cap_pair or int(biggest / nbt * 1.25 + 6 * (biggest / nbt) ** 0.5) + 512
+        capb = (capb + 511) // 512 * 512
+        send = [torch.zeros(nbt * capb * (self.tb // 8), dtype=torch.int64, device=torch.device("cuda", self.devices[r])) for r in range(n)]
+        fills = []
+        for r, blk in enumerate(blocks):
+            fill = torch.zeros(nbt + 1, dtype=torch.int32, device=torch.device("cuda", self.devices[r]))
+            if blk is not None:
+                db, do, nr, fb, tbases, fri = blk
+                self.b[r].exchange_scatter_pull_device(db.data_ptr(), do.data_ptr(), nr, fb, tbases, fri, n, send[r].data_ptr(), capb, fill.data_ptr())
+                torch.cuda.synchronize(self.devices[r])
+            fills.append(fill.cpu())
+        allf = torch.stack(fills)                                       # [source][bucket | flag]
+        if int(allf[:, nbt].sum()) != 0:
+            self.overflows += 1
+            for r, blk in enumerate(blocks):
+                if blk is not None:
+                    self.b[r].exchange_scatter_undo()
+                    torch.cuda.synchronize(self.devices[r])
+            return None
+        got = []
+        for q in range(n):
+            dev = torch.device("cuda", self.devices[q])
+            d_src = torch.tensor([t.data_ptr() for t in send], dtype=torch.int64, device=dev)
+            d_fills = allf.to(dev).contiguous()
+            total = int(allf[:, q * nbl:(q + 1) * nbl].sum())
+            if total:
+                self.b[q].insert_pull_device(d_src.data_ptr(), n, capb, d_fills.data_ptr(), nbt + 1, total)
+                torch.cuda.synchronize(self.devices[q])
+            got.append(total)
+        return got
+
     def add_blocks(self, blocks):
         """blocks[r] = (d_bases tensor, d_offs tensor, n_reads, first_base, total_bases, first_read_index): the reads rank r
         contributes to this round (None = nothing).  One exchange round: count on every rank, offsets, scatter, insert."""
         torch, n = self.torch, self.n
-        if self.optimistic:
+        if self.pull:
+            got = self._add_blocks_pull(blocks)
+            if got is not None:
+                return got
+        elif self.optimistic:
             got = self._add_blocks_opt(blocks)
             if got is not None:
                 return got
@@ -326,7 +369,7 @@ class ShardedBuilder:
     """The per-rank driver.  `reads` are this rank's own contiguous block of the global read sequence."""
 
     def __init__(self, K, max_read_len, init_slots, load_factor=0.7, device=0, track_order=True, group=None,
-                 slack=None, exchange="peer", sub_blocks=4):
+                 slack=None, exchange="pull", sub_blocks=4):
         from .graph import DBGBuilder
         self.ex = Exchange(group)
         self.n, self.rank = self.ex.world, self.ex.rank
@@ -338,7 +381,8 @@ class ShardedBuilder:
         self.width = self.b.tuple_bytes // 8        # int64 words per tuple
         self._send = self._counts = None
         self.exchange_bytes = 0
-        # "peer" (default): OPTIMISTIC fused exchange -- one extraction pass stores tuples straight into fixed regions of
+        # "pull" (default): see _add_reads_pull;
+        # "peer": OPTIMISTIC fused exchange -- one extraction pass stores tuples straight into fixed regions of
         #     the owners' receive buffers over NVLink peer mappings, in sub-blocks, the scatter of sub-block k+1 overlapping
         #     the owners' partition + insert of sub-block k; a region overflow (skew) redoes that sub-block exactly;
         # "peer_exact": count pass + all-gathered exact offsets + scatter pass (no overlap);
@@ -351,10 +395,82 @@ class ShardedBuilder:
         self._recv_ptr = None
         self._recv_cap = 0
         self._peer_ptrs = None
+        # "pull": the source partitions by (owner, table slice) into its OWN send buffer (local stores only) and the owners read
+        #     their regions over NVLink from inside the bucketed insert: no receive buffer, no owner-side partition pass
+        self._send_ptr = None
+        self._send_cap = 0
+        self._src_ptrs = None
 
     def close(self):
         self._release_peers()
+        self._release_send()
         self.b.close()
+
+    # ---- pull exchange: send buffers readable by every peer ----
+    def _release_send(self):
+        if self._src_ptrs is not None:
+            for q, p in enumerate(self._src_ptrs):
+                if q != self.rank and p:
+                    self.b.peer_close(p)
+            self._src_ptrs = None
+        if self._send_ptr:
+            self.b.peer_free(self._send_ptr)
+            self._send_ptr = None
+            self._send_cap = 0
+
+    def _ensure_send(self, cap_tuples):
+        """(re)allocate the send buffers (every rank the same size) and map every peer's; collective"""
+        if cap_tuples <= self._send_cap:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.ex.group)
+        self._release_send()
+        self._send_ptr, handle = self.b.peer_alloc(cap_tuples * self.width * 8)
+        self._send_cap = cap_tuples
+        handles = [None] * self.n
+        dist.all_gather_object(handles, handle, group=self.ex.group)
+        self._src_ptrs = [self._send_ptr if q == self.rank else self.b.peer_open(handles[q]) for q in range(self.n)]
+        self._d_src = torch.tensor(self._src_ptrs, dtype=torch.int64, device=self.device)
+        dist.barrier(group=self.ex.group)
+
+    def _add_reads_pull(self, d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ=None):
+        from .graph import torch_stream_handle
+        stream = torch_stream_handle(self.device)
+        n, dev = self.n, self.device
+        nbl = self.b.partition_info()[0]
+        nbt = n * nbl
+        if nbt > 4096:
+            return self._add_reads_peer_opt(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ)
+        if n_occ is None:
+            lens = (d_offs[1:n_reads + 1] - d_offs[:n_reads]).clamp(max=int(self.max_read_len))
+            n_occ = int((lens - (self.K - 1)).clamp(min=0).sum().item())
+        # region size: the expected tuples of an (owner, slice) bucket + 25 % + 6 sigma, in whole insert tiles; the ranks agree
+        # on the largest.  A region that is too small is detected and the block redone exactly.
+        mean = n_occ / nbt
+        capb = int(mean * 1.25 + 6.0 * mean ** 0.5 + 512)
+        want = torch.tensor([capb], dtype=torch.int64, device=dev)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=self.ex.group)
+        capb = (int(want.item()) + 511) // 512 * 512
+        self._ensure_send(nbt * capb)
+        fill = torch.zeros(nbt + 1, dtype=torch.int32, device=dev)
+        allfill = torch.empty(n * (nbt + 1), dtype=torch.int32, device=dev)
+        self.b.exchange_scatter_pull_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, first_base, total_bases, first_read_index,
+                                            n, self._send_ptr, capb, fill.data_ptr(), stream=stream)
+        # the all-gather of the fill counters is also the barrier: every rank's regions are complete when it returns
+        dist.all_gather_into_tensor(allfill, fill, group=self.ex.group)
+        counts = allfill.view(n, nbt + 1).cpu()
+        self.sub_blocks_used = 1
+        if bool(counts[:, nbt].any()):
+            self.opt_fallbacks += 1
+            self.b.exchange_scatter_undo(stream=stream)
+            torch.cuda.synchronize(dev)
+            return self._add_reads_peer(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index)
+        mine = counts[:, self.rank * nbl:(self.rank + 1) * nbl]
+        recv_total = int(mine.sum())
+        self.exchange_bytes += int(counts[self.rank, :nbt].sum() - counts[self.rank, self.rank * nbl:(self.rank + 1) * nbl].sum()) * self.width * 8
+        self.b.insert_pull_device(self._d_src.data_ptr(), n, capb, allfill.data_ptr(), nbt + 1, recv_total, stream=stream)
+        self._keep = (fill, allfill)
+        return recv_total
 
     # ---- peer receive buffers ----
     def _release_peers(self):
@@ -524,6 +640,8 @@ class ShardedBuilder:
                          first_read_index, n_occ_upper=None):
         """one block of this rank's reads, device resident (an occurrence starts at a distinct base, so
         total_bases bounds the tuple count)"""
+        if self.exchange == "pull":
+            return self._add_reads_pull(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ_upper)
         if self.exchange == "peer":
             return self._add_reads_peer_opt(d_bases, d_offs, n_reads, first_base, total_bases, first_read_index, n_occ_upper)
         if self.exchange in ("peer_exact", "peer_sliced"):

@@ -155,6 +155,18 @@ int  dbg_insert_sliced_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, co
 int  dbg_exchange_scatter_opt_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
                                      uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
                                      uint64_t region_off, uint32_t cap_pair, uint32_t *d_fill, void *stream);
+/* PULL exchange: the source partitions its occurrences by (owner, table slice of the owner) into its OWN send buffer
+ * (bucket = owner * n_slices + slice, n_slices from dbg_partition_info; region of `capb` tuples per bucket, capb a multiple of
+ * 512; d_fill has n_parts * n_slices + 1 counters, the last one the overflow flag) -- one extraction pass, local stores only.
+ * After the fill counters have been all-gathered, every owner inserts its buckets slice by slice and READS the sources'
+ * regions over NVLink peer mappings (d_src_ptrs[q]; d_fills + q * fill_stride = source q's counters): long contiguous reads,
+ * no receive buffer and no owner-side partition pass.  n_tuples_upper: an upper bound of what this owner receives
+ * (long-probe budget only). */
+int  dbg_exchange_scatter_pull_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
+                                      uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *d_send, uint32_t capb,
+                                      uint32_t *d_fill, void *stream);
+int  dbg_insert_pull_device(dbg_ctx *ctx, void *const *d_src_ptrs, int32_t n_src, uint32_t capb, const uint32_t *d_fills,
+                            uint32_t fill_stride, uint64_t n_tuples_upper, void *stream);
 int  dbg_exchange_scatter_undo(dbg_ctx *ctx, void *stream);     /* after an overflow: restore the side counters of the scatter */
 int  dbg_insert_tuple_regions_device(dbg_ctx *ctx, const void *d_base, uint32_t n_regions, uint64_t stride_tuples,
                                      const uint64_t *counts, void *stream);

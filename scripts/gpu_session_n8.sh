@@ -9,7 +9,7 @@ import json
 for f in ["r2_n8_bench.json","r2_n8_bench_C5s.json"]:
     try:
         d=json.loads(open("gpurun_out/"+f).read().strip().splitlines()[-1]); r=d["roofline"]
-        print(f, "ms", round(d["ms_per_step"],2), "G/s", round(d["value"]/1e9,2), "insert", round(r["kernel_ms_per_step"],2), "build", round(r["build_kernels_ms_per_step"],2), "layout", round(r["layout_ms_per_step"],2), "S", d.get("sub_blocks_used"), "nvlink", d.get("nvlink",{}).get("gbs_out"), "scat", d.get("nvlink",{}).get("scatter_kernel_ms_per_step"), "fb", d.get("optimistic_exchange_fallbacks"), "e2e", d["e2e"]["ms_per_step"] if d.get("e2e") else d.get("e2e_error"))
+        print(f, "ms", round(d["ms_per_step"],2), "G/s", round(d["value"]/1e9,2), "insert", round(r["kernel_ms_per_step"],2), "build", round(r["build_kernels_ms_per_step"],2), "layout", round(r["layout_ms_per_step"],2), "S", d.get("sub_blocks_used"), "nvlink", d.get("nvlink",{}).get("gbs_out") or d.get("nvlink",{}).get("gbs_in"), "scat", d.get("nvlink",{}).get("scatter_kernel_ms_per_step"), "fb", d.get("optimistic_exchange_fallbacks"), "e2e", d["e2e"]["ms_per_step"] if d.get("e2e") else d.get("e2e_error"))
     except Exception as e: print(f, "ERR", e)
 PY
 tail -n 4 gpurun_out/r2_n8_*.err | cut -c1-300

@@ -2,7 +2,7 @@
 device inside pytest, tests/test_gpu_sharded_layout.py).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multigpu_check.py [--reads 200000] [--K 31] [--exchange peer|peer_exact|peer_sliced|nccl] [--front-end]
+        tests/multigpu_check.py [--reads 200000] [--K 31] [--exchange pull|peer|peer_exact|peer_sliced|nccl] [--front-end]
 
 Every rank extracts + exchanges + inserts its block of C2-shaped synthetic reads (ShardedBuilder, two calls so that the
 exchange repeats), the boundary clusters are handed around the ring, every rank lays out its slice and exports it into
@@ -62,7 +62,7 @@ def main():
     ap.add_argument("--reads", type=int, default=200_000)
     ap.add_argument("--K", type=int, default=31)
     ap.add_argument("--slots", type=int, default=12_000_000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_exact", "peer_sliced", "nccl"])
+    ap.add_argument("--exchange", default="peer", choices=["pull", "peer", "peer_exact", "peer_sliced", "nccl"])
     ap.add_argument("--front-end", action="store_true")
     a = ap.parse_args()
     import dbg_assembly_b200 as dbg

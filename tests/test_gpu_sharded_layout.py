@@ -56,7 +56,7 @@ def deal_blocks(torch, bases, offs, n, rounds=1):
 
 
 def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, rounds=1, load=0.7, optimistic=False, cap_pair=None,
-                info=None):
+                info=None, pull=False):
     import torch
     from dbg_assembly_b200.sharded import LocalShards
     bases = np.concatenate([f[0] for f in files]) if files else np.zeros(0, np.uint8)
@@ -64,7 +64,8 @@ def run_sharded(dbg, files, K, R, P_req, n, by_slice=False, force_wide=False, ro
     for b, o in files:
         offs.append(o[1:] + offs[-1][-1])
     offs = np.concatenate(offs)
-    ls = LocalShards(n, K, R, P_req, load_factor=load, force_wide=force_wide, by_slice=by_slice, optimistic=optimistic, cap_pair=cap_pair)
+    ls = LocalShards(n, K, R, P_req, load_factor=load, force_wide=force_wide, by_slice=by_slice, optimistic=optimistic, cap_pair=cap_pair,
+                     pull=pull)
     try:
         rds, keep = deal_blocks(torch, bases, offs, n, rounds)
         for blocks in rds:
@@ -96,27 +97,35 @@ def check_against_oracle(o, arr, nul, wide):
 
 
 @pytest.mark.parametrize("n", [2, 3, 8])
-@pytest.mark.parametrize("mode", ["optimistic", "optimistic_overflow", "exact"])
+@pytest.mark.parametrize("mode", ["optimistic", "optimistic_overflow", "exact", "pull", "pull_overflow"])
 @pytest.mark.parametrize("K,wide", [(31, False), (31, True), (63, True)])
 def test_sharded_build_merges_into_the_reference_table(dbg, oracle_mod, monkeypatch, n, mode, K, wide):
     """exchange modes: optimistic = ONE extraction pass into fixed per-source regions (dbg_exchange_scatter_opt_device +
     dbg_insert_tuple_regions_device; the default of the multi-GPU driver); optimistic_overflow = regions forced too small:
     the side counters are rolled back and the round is redone exactly; exact = count + offsets + scatter
-    (dbg_exchange_count/scatter_device, PeerStagedSink).  (The experimental (owner x slice) bucket mode, exchange=
+    (dbg_exchange_count/scatter_device, PeerStagedSink); pull = sources partition by (owner, table slice) into their own send
+    buffers and the owners read their regions from there inside the bucketed insert (dbg_exchange_scatter_pull_device +
+    dbg_insert_pull_device: no receive buffer, no owner-side partition); pull_overflow = a low-complexity read repeated 40
+    times floods two buckets, the round is redone exactly.  (The experimental (owner x slice) bucket mode, exchange=
     "peer_sliced", is not part of this harness: it was measured slower in round 1 and is kept for experiments only.)"""
     monkeypatch.setenv("DBG_B200_PART_SHIFT", "10")        # many table slices per shard at test size
     reads = random_reads(171 + n, 5000, 40, 150, genome_len=25000) + [b"A" * 70] * 30 + [b"T" * 64] * 7
+    if mode == "pull_overflow":
+        reads = reads[:2000] + [b"AC" * 75] * 40 + reads[2000:] + [b"GT" * 70] * 40
     bases, offs = reads_to_arrays(reads)
     P_req = 400_000
     o = oracle_build(oracle_mod, [(bases, offs)], K, 150, P_req, wide=wide)
     info = {}
     arr, nul, counts, fb = run_sharded(dbg, [(bases, offs)], K, 150, P_req, n, by_slice=mode == "exact_sliced", force_wide=wide and K <= 31,
                                        rounds=2, optimistic=mode.startswith("optimistic"), cap_pair=512 if mode == "optimistic_overflow" else None,
-                                       info=info)
+                                       info=info, pull=mode.startswith("pull"))
     assert not fb, "the windowed layout must handle an ordinary table"
     assert counts + 1 == o.count
     assert info["occurrences"] == o.occurrences and info["reads"] == len(reads)
-    assert info["overflows"] == (2 if mode == "optimistic_overflow" else 0)
+    if mode == "pull_overflow":
+        assert info["overflows"] >= 1
+    else:
+        assert info["overflows"] == (2 if mode == "optimistic_overflow" else 0)
     check_against_oracle(o, arr, nul, wide)
     o.close()
 
