@@ -200,6 +200,13 @@ struct dbg_ctx {
     std::vector<EvPair> build_ev;
     std::vector<cudaEvent_t> ev_all, ev_free_list;   // every timing event this context ever created / the idle ones
     float ms[8];
+    // dbg_reset clears the table on a side stream and returns; the first KERNEL of the next build waits for it (table_ready), so
+    // the 6.4-GB memset of C2 runs beside the host->device copy of the first reads instead of in front of it
+    cudaStream_t clear_stream = nullptr;
+    cudaEvent_t ev_clear = nullptr;
+    bool clear_pending = false;
+    EvPair clear_ev{nullptr, nullptr, 0};
+    bool clear_timed = false;
     LayoutInfo *d_layout_info2 = nullptr;      // dbg_finish_export: the wrap-around region found after the grouped layout
     LayoutRegion *d_regions2 = nullptr;
     LayoutRegion *h_regions = nullptr;         // pinned copy of the region list (patch copies)
@@ -271,6 +278,8 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     cudaFree(c->d_chunk_first); cudaFree(c->d_nodes_alloc); cudaFree(c->d_counters); cudaFree(c->d_polyA);
     cudaFree(c->d_tail); cudaFree(c->d_tail_nodes); cudaFree(c->d_nul_slice);
     cudaFree(c->d_offs_stage); cudaFree(c->d_boffs); cudaFree(c->d_roffs); cudaFree(c->d_tuples); cudaFree(c->d_matrix); cudaFree(c->d_tile_sums);
+    if (c->clear_stream) cudaStreamDestroy(c->clear_stream);
+    if (c->ev_clear) cudaEventDestroy(c->ev_clear);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_fill); cudaFree(c->d_snap); if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -279,19 +288,60 @@ extern "C" void dbg_destroy(dbg_ctx *c)
     delete c;
 }
 
-static int clear_table(dbg_ctx *c)
+// the table clear was started on the side stream by dbg_reset: `s` -- the stream about to touch the table -- waits for it
+static int table_ready(dbg_ctx *c, cudaStream_t s)
 {
+    if (!c->clear_pending) return DBG_OK;
+    CU_TRY(cudaStreamWaitEvent(s, c->ev_clear, 0));
+    if (s != c->stream) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_clear, 0));      // later table work on the context's stream is ordered too
+    c->clear_pending = false;
+    return DBG_OK;
+}
+
+static int clear_table(dbg_ctx *c, bool async = false)
+{
+    if (async && getenv("DBG_B200_SYNC_CLEAR")) async = false;
+    if (c->clear_timed) {          // the previous clear's time was never collected (reset twice in a row)
+        if (cudaEventSynchronize(c->clear_ev.b) == cudaSuccess) ev_put(c, c->clear_ev);
+        c->clear_timed = false;
+    }
+    if (!c->clear_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->clear_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_clear, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = async ? c->clear_stream : c->stream;
     EvPair e;
-    int rc = ev_begin(c, c->stream, &e);
+    int rc = ev_begin(c, cs, &e);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(c->d_nodes_alloc, 0, (c->porch + c->n_local) * build_node_bytes(c), c->stream));
+    CU_TRY(cudaMemsetAsync(c->d_nodes_alloc, 0, (c->porch + c->n_local) * build_node_bytes(c), cs));
+    CU_TRY(cudaEventRecord(e.b, cs));
+    // the side counters are read and written by the extraction kernels: they are cleared on the context's own stream
     CU_TRY(cudaMemsetAsync(c->d_counters, 0, CNT_N * sizeof(u64), c->stream));
     CU_TRY(cudaMemsetAsync(c->d_polyA, 0, 8 * sizeof(u64), c->stream));
-    CU_TRY(cudaEventRecord(e.b, c->stream));
+    if (async) {
+        CU_TRY(cudaEventRecord(c->ev_clear, cs));
+        c->clear_pending = true;
+        c->clear_ev = e; c->clear_timed = true;      // elapsed time collected by collect_clear_time (dbg_finalize / dbg_get_timings)
+        c->ms[0] = 0;
+        return DBG_OK;
+    }
     CU_TRY(cudaEventSynchronize(e.b));
     CU_TRY(cudaEventElapsedTime(&c->ms[0], e.a, e.b));
     ev_put(c, e);
+    c->clear_pending = false;
     return DBG_OK;
+}
+
+static void collect_clear_time(dbg_ctx *c)
+{
+    if (!c->clear_timed) return;
+    if (cudaEventSynchronize(c->clear_ev.b) == cudaSuccess) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->clear_ev.a, c->clear_ev.b) == cudaSuccess) c->ms[0] = t;
+    }
+    cudaGetLastError();
+    ev_put(c, c->clear_ev);
+    c->clear_timed = false;
 }
 
 extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
@@ -357,6 +407,10 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     // one bucket = a table slice of 16 MB (2^19 nodes of 32 B, 2^18 of 64 B): the slice in use, the one being
     // prefetched and the tuple stream fit the 126 MB L2 with room to spare
     c->part_shift = c->wide ? 18 : 19;
+    // 8 or more shards: 32-MB slices (measured neutral for the insert: 7.62 vs 7.58 ms on C2), so that the (owner, slice)
+    // buckets of the pull exchange stay below 2048 -- the source-side partition holds its reservations in registers and keeps
+    // three CTAs per SM up to there
+    if (n_shards >= 8) c->part_shift++;
     if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
     // slice geometry from the (rank-independent) shard size, so that every rank of a sharded build agrees on it
     // (the last shard may be smaller: its trailing slices just stay empty)
@@ -402,7 +456,7 @@ extern "C" int dbg_reset(dbg_ctx *c)
     for (int i = 0; i < 4; i++) c->path_counts[i] = 0;
     c->links_cutoff = INT32_MIN;
     for (int i = 1; i < 8; i++) c->ms[i] = 0;
-    return clear_table(c);
+    return clear_table(c, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -514,6 +568,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
             CU_TRY(cudaGetLastError());
             c->launches++;
             c->path_counts[2]++;
+            if ((rc = table_ready(c, s))) return rc;       // the scatter above did not touch the table; the insert does
             EvPair ev;
             rc = ev_begin(c, s, &ev);
             if (rc) return rc;
@@ -556,6 +611,7 @@ static int run_partitioned(dbg_ctx *c, BuildArgs a, uint64_t n_chunks, uint64_t 
         rc = launch_build<WIDE>(c, a, ss, n_chunks, s, nb);
     }
     if (rc) return rc;
+    if ((rc = table_ready(c, s))) return rc;
     EvPair ev;                       // the insert kernel alone (ms[6]): the roofline's dominant kernel
     rc = ev_begin(c, s, &ev);
     if (rc) return rc;
@@ -689,6 +745,10 @@ static int build_device(dbg_ctx *c, const char *d_bases, const u64 *d_offs, uint
     if (rc) return rc;
     bool part = n_parts == 0 && want_partition(c, total_bases);
     if (part && (ensure_tuples(c, total_bases) != DBG_OK || ensure_matrix(c, n_chunks) != DBG_OK)) part = false;
+    // kernels wait for the table clear that dbg_reset started on the side stream.  (It may only overlap COPIES: running the
+    // 6.4-GB memset next to the extraction / partition kernel was measured -- the memset takes the DRAM write bandwidth the
+    // partition's scattered stores need and the step got slower, 17.5 vs 17.3 ms on C2.)
+    if ((rc = table_ready(c, s))) return rc;
     if (n_parts > 0) {
         if (total_bases > bucket_stride) return set_err(DBG_ERR_BUFFER, "tuple capacity %llu < %llu (bases in the block)", (unsigned long long)bucket_stride, (unsigned long long)total_bases);
         if (total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
@@ -854,6 +914,7 @@ static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs,
         sub_ev.push_back(e);
         CU_TRY(cudaEventRecord(e, c->copy_stream));
         CU_TRY(cudaStreamWaitEvent(s, e, 0));
+        if ((rc = table_ready(c, s))) return rc;       // (first sub-block: the table clear of dbg_reset ran beside its copy)
         if (nbases) {
             const uint64_t first_base = c->batch_bases, abase = first_base & ~15ull;
             const uint64_t n_chunks = (first_base + nbases - abase + CB - 1) / CB;
@@ -886,6 +947,7 @@ static int submit_pipelined(dbg_ctx *c, const char *bases, const uint64_t *offs,
         c->launches++;
         c->path_counts[2]++;
         c->part_blocks++;
+        if ((rc = table_ready(c, s))) return rc;
         int grc = 1;
         if (fx) {
             // last block of the build and the caller waits for the image: insert, lay out and copy slice group by slice group
@@ -1234,6 +1296,7 @@ extern "C" int dbg_insert_tuples_device(dbg_ctx *c, const void *d_tuples, uint64
     c->guard_total += n;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    { int trc = table_ready(c, s); if (trc) return trc; }
     // enough tuples per table slice: put them in slice order first, then insert through L2-resident slices
     bool part = want_partition(c, n) && 2 * (size_t)c->n_buckets * sizeof(u32) <= 48 * 1024;
     // room for the fixed bucket regions of the optimistic partition: 1/8 slack plus a tile per bucket
@@ -1282,6 +1345,7 @@ extern "C" int dbg_insert_sliced_device(dbg_ctx *c, const void *d_tuples, uint64
     c->guard_total += n;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    { int trc = table_ready(c, s); if (trc) return trc; }
     CU_TRY(cudaMemcpyAsync(c->d_boffs, d_slice_offs, ((size_t)c->n_buckets + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     EvPair ev;
     int rc = ev_begin(c, s, &ev);
@@ -1423,6 +1487,7 @@ extern "C" int dbg_insert_pull_device(dbg_ctx *c, void *const *d_src_ptrs, int32
     if (n_src < 1 || n_src > 64 || capb < INS_TILE || capb % INS_TILE) return set_err(DBG_ERR_INVALID, "dbg_insert_pull_device: bad geometry");
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    { int trc = table_ready(c, s); if (trc) return trc; }
     c->guard_total += n_tuples_upper;
     PullSrc ps;
     ps.ptrs = (const u64 *const *)d_src_ptrs; ps.fills = d_fills; ps.n_src = (u32)n_src; ps.fill_stride = fill_stride;
@@ -1483,6 +1548,7 @@ extern "C" int dbg_insert_tuple_regions_device(dbg_ctx *c, const void *d_base, u
     c->guard_total += n;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    { int trc = table_ready(c, s); if (trc) return trc; }
     bool part = want_partition(c, n) && c->optimistic;
     const uint64_t want_cap = n + n / 8 + (uint64_t)c->n_buckets * INS_TILE;
     if (part && ensure_tuples(c, want_cap) != DBG_OK) part = false;
@@ -1918,6 +1984,8 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
     u64 cnt[CNT_N];
     int rc = read_counters(c, cnt);
     if (rc) return rc;
+    if ((rc = table_ready(c, c->stream))) return rc;
+    collect_clear_time(c);
     if (!c->finalized) {
         // build time = sum over blocks
         for (auto &e : c->build_ev) { float t = 0; CU_TRY(cudaEventElapsedTime(&t, e.a, e.b)); c->ms[e.slot] += t; ev_put(c, e); }
@@ -1970,6 +2038,7 @@ extern "C" int dbg_finalize(dbg_ctx *c, dbg_stats *stats)
 extern "C" int dbg_shard_tail_export(dbg_ctx *c, void *blob, uint64_t cap_bytes, uint64_t *n_bytes)
 {
     if (!c || !n_bytes) return set_err(DBG_ERR_INVALID, "NULL argument");
+    { cudaSetDevice(c->device); int trc = table_ready(c, c->stream); if (trc) return trc; }
     if (c->n_shards <= 1) return set_err(DBG_ERR_STATE, "dbg_shard_tail_export: unsharded context");
     if (c->finalized) return set_err(DBG_ERR_STATE, "dbg_shard_tail_export after finalize");
     CU_TRY(cudaSetDevice(c->device));
@@ -2019,6 +2088,7 @@ extern "C" int dbg_shard_tail_export(dbg_ctx *c, void *blob, uint64_t cap_bytes,
 extern "C" int dbg_shard_tail_import(dbg_ctx *c, const void *blob, uint64_t n_bytes)
 {
     if (!c || !blob) return set_err(DBG_ERR_INVALID, "NULL argument");
+    { cudaSetDevice(c->device); int trc = table_ready(c, c->stream); if (trc) return trc; }
     if (c->n_shards <= 1) return set_err(DBG_ERR_STATE, "dbg_shard_tail_import: unsharded context");
     if (!c->tail_exported) return set_err(DBG_ERR_STATE, "dbg_shard_tail_import before dbg_shard_tail_export (the own tail is fixed first)");
     if (c->tail_imported) return set_err(DBG_ERR_STATE, "tail already imported");
@@ -2173,6 +2243,8 @@ extern "C" int dbg_device_image(dbg_ctx *c, void **d_array, void **d_nul_flag)
 extern "C" int dbg_device_build_table(dbg_ctx *c, void **d_nodes, uint64_t *n_local, uint64_t **d_polyA)
 {
     if (!c) return set_err(DBG_ERR_INVALID, "NULL ctx");
+    { cudaSetDevice(c->device); int trc = table_ready(c, c->stream); if (trc) return trc; }
+    CU_TRY(cudaStreamSynchronize(c->stream));
     if (d_nodes) *d_nodes = c->d_nodes;
     if (n_local) *n_local = c->n_local;
     if (d_polyA) *d_polyA = (uint64_t *)c->d_polyA;
@@ -2357,6 +2429,7 @@ extern "C" int dbg_dump_shard(dbg_ctx *c, uint64_t *kmers_lo, uint64_t *kmers_hi
                               uint64_t *first_ordinal, uint64_t *n)
 {
     if (!c || !n) return set_err(DBG_ERR_INVALID, "NULL argument");
+    { cudaSetDevice(c->device); int trc = table_ready(c, c->stream); if (trc) return trc; }
     CU_TRY(cudaSetDevice(c->device));
     u64 cnt[CNT_N];
     int rc = read_counters(c, cnt);
@@ -2393,6 +2466,7 @@ extern "C" int dbg_dump_shard(dbg_ctx *c, uint64_t *kmers_lo, uint64_t *kmers_hi
 extern "C" int dbg_get_timings(dbg_ctx *c, float ms[8])
 {
     if (!c || !ms) return set_err(DBG_ERR_INVALID, "NULL argument");
+    collect_clear_time(c);
     for (int i = 0; i < 8; i++) ms[i] = c->ms[i];
     return DBG_OK;
 }

@@ -356,18 +356,31 @@ struct StageBuf {
         const u32 t = threadIdx.x, nthr = blockDim.x;
         const u32 n = misc[0];
         // OPT: reserve this batch's run in every touched bucket's region.  The atomics are issued first and their
-        // results are picked up after the scan below, so the round trips hide behind it (nb <= 4 * nthr; larger
-        // bucket counts take the results at once, chunk by chunk)
-        u32 rr[4] = {0, 0, 0, 0};
-        if (OPT) {
-            for (u32 c0 = 0; c0 < nb; c0 += 4 * nthr) {
+        // results are picked up after the scan below, so the round trips hide behind it (nb <= 8 * nthr: up to 2048
+        // buckets, the (owner, slice) buckets of the pull exchange on 8 GPUs included; larger bucket counts take the
+        // results at once, chunk by chunk)
+        constexpr int RRN = 8;       // reservations a thread holds in registers across the scan: nb <= 8 * nthr buckets
+        u32 rr[RRN];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const u32 b = c0 + j * nthr + t;
+        for (int j = 0; j < RRN; j++) rr[j] = 0;
+        const bool held = nb <= RRN * nthr;
+        if (OPT) {
+            if (held) {
+#pragma unroll
+                for (int j = 0; j < RRN; j++) {
+                    if (j * nthr >= nb) break;                 // block-uniform: 382 buckets (one GPU) take two rounds, not eight
+                    const u32 b = j * nthr + t;
                     const u32 cnt = b < nb ? bh[b] : 0u;
-                    rr[j] = cnt ? atomicAdd(&fill[b], cnt) : 0u;
+                    if (cnt) rr[j] = atomicAdd(&fill[b], cnt);
                 }
-                if (nb > 4 * nthr) {
+            } else {
+                for (u32 c0 = 0; c0 < nb; c0 += 4 * nthr) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const u32 b = c0 + j * nthr + t;
+                        const u32 cnt = b < nb ? bh[b] : 0u;
+                        rr[j] = cnt ? atomicAdd(&fill[b], cnt) : 0u;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const u32 b = c0 + j * nthr + t;
@@ -390,9 +403,10 @@ struct StageBuf {
         u32 run = incl - sum;
         for (u32 w = 0; w < (t >> 5); w++) run += misc[1 + w];
         for (u32 b = b0; b < b1; b++) { boff[b] = run; run += bh[b]; }
-        if (OPT && nb <= 4 * nthr) {
+        if (OPT && held) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < RRN; j++) {
+                if (j * nthr >= nb) break;
                 const u32 b = j * nthr + t;
                 const u32 cnt = b < nb ? bh[b] : 0u;
                 if (cnt) { if (rr[j] + cnt > capb) { *flag = 1u; base[b] = 0xffffffffu; } else base[b] = (dst_ptrs ? 0u : b * capb) + rr[j]; }
