@@ -399,7 +399,11 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     c->opt_capb = getenv("DBG_B200_OPT_CAPB") ? atoi(getenv("DBG_B200_OPT_CAPB")) : 0;
     c->stage_cap = getenv("DBG_B200_STAGE_CAP") ? atoi(getenv("DBG_B200_STAGE_CAP")) : -1;
     c->peer_unstaged = getenv("DBG_B200_PEER_UNSTAGED") ? atoi(getenv("DBG_B200_PEER_UNSTAGED")) : 0;
-    c->layout_v = getenv("DBG_B200_LAYOUT_V") && atoi(getenv("DBG_B200_LAYOUT_V")) == 1 ? 1 : 2;
+    // version 2 of the cluster-local layout pass for 32-B nodes (C2: 4.61 -> 3.67 ms); 64-B nodes keep version 1, which
+    // measured faster there (C3, K=63, table load 0.37: 13.3 vs 17.5 ms -- three 16-B quarters per staged slot and fewer
+    // occupied slots per warp-owned word pair)
+    c->layout_v = c->wide ? 1 : 2;
+    if (const char *e = getenv("DBG_B200_LAYOUT_V")) { int v = atoi(e); if (v == 1 || v == 2) c->layout_v = v; }
     c->layout_mode = 0;
     if (const char *e = getenv("DBG_B200_LAYOUT")) c->layout_mode = strcmp(e, "global") == 0 ? 1 : 0;
     c->part_mode = 2;

@@ -102,6 +102,20 @@ def test_golden_tables_global_layout_method(dbg, name, monkeypatch):
         assert np.array_equal(d[k], g[k]), k
 
 
+@pytest.mark.parametrize("version", ["1", "2"])
+@pytest.mark.parametrize("force_wide", [False, True])
+@pytest.mark.parametrize("name", ["ragged_k31", "saturate_k21", "contig_k31", "even_k16_two_files"])
+def test_both_versions_of_the_cluster_layout_pass(dbg, name, force_wide, version, monkeypatch):
+    """k_layout_clusters (version 1, the default for 64-B nodes) and k_layout_clusters2 (version 2, the default for 32-B
+    nodes) on both node widths: the reference's slot layout either way"""
+    monkeypatch.setenv("DBG_B200_LAYOUT_V", version)
+    g = load_golden(name)
+    st, arr, nul = gpu_build(dbg, g["files"], g["K"], g["R"], g["init_slots"], g["load"], force_wide=force_wide)
+    d = image_to_dump(arr, nul, g["size"])
+    for k in ("slot", "kmer", "l", "r"):
+        assert np.array_equal(d[k], g[k]), k
+
+
 def test_dense_table_long_clusters_and_wraparound(dbg, oracle_mod):
     """load factor 0.97: clusters of hundreds of slots (region path / global fallback) and a probe chain that
     runs over the end of the table into the first slots"""
