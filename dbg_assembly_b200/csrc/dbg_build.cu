@@ -411,10 +411,12 @@ extern "C" int dbg_create(dbg_ctx **out, const dbg_params *p)
     // one bucket = a table slice of 16 MB (2^19 nodes of 32 B, 2^18 of 64 B): the slice in use, the one being
     // prefetched and the tuple stream fit the 126 MB L2 with room to spare
     c->part_shift = c->wide ? 18 : 19;
-    // 8 or more shards: 32-MB slices (measured neutral for the insert: 7.62 vs 7.58 ms on C2), so that the (owner, slice)
-    // buckets of the pull exchange stay below 2048 -- the source-side partition holds its reservations in registers and keeps
-    // three CTAs per SM up to there
-    if (n_shards >= 8) c->part_shift++;
+    // sharded tables: 32-MB slices (measured neutral for the insert: 7.62 vs 7.58 ms on C2, 7.82 with 64-MB slices), which
+    // halves the (owner, slice) buckets of the pull exchange -- 382 on 2 GPUs, 764 on 4, 1528 on 8: up to 2048 the source-side
+    // partition holds its reservations in registers and keeps three CTAs per SM, and its store runs get longer
+    // (64-B nodes too: C3 on 2 GPUs has 2 x 2289 slices of 16 MB -- beyond the 4096 buckets of the pull exchange, i.e. the
+    // push exchange with its owner-side partition pass, 68.3 ms per step -- and 2 x 1145 slices of 32 MB: pull, 59.3 ms)
+    if (n_shards >= 2) c->part_shift++;
     if (const char *e = getenv("DBG_B200_PART_SHIFT")) { int v = atoi(e); if (v >= 4 && v <= 40) c->part_shift = v; }
     // slice geometry from the (rank-independent) shard size, so that every rank of a sharded build agrees on it
     // (the last shard may be smaller: its trailing slices just stay empty)
@@ -1389,6 +1391,7 @@ extern "C" int dbg_exchange_scatter_opt_device(dbg_ctx *c, const char *d_bases, 
     if (cap0 == 0) return set_err(DBG_ERR_STATE, "staged scatter disabled (DBG_B200_STAGE_CAP=0)");
     // the scatter pass counts reads / occurrences / k-mer-0 lanes as it goes: keep what dbg_exchange_scatter_undo restores
     if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
+    if ((rc = table_ready(c, s))) return rc;        // (the extraction kernel must not run beside the table clear: see build_device)
     CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     c->undo_reads = n_reads;
@@ -1445,12 +1448,13 @@ extern "C" int dbg_exchange_scatter_pull_device(dbg_ctx *c, const char *d_bases,
     if (n_chunks > 0x7fffffffull || total_bases >= (1ull << 32)) return set_err(DBG_ERR_INVALID, "block too large for the exchange: split it (< 2^32 bases)");
     int rc = ensure_chunks(c, n_chunks);
     if (rc) return rc;
-    // the batch must still fit next to nbt bucket counters in shared memory
+    // the batch must fit next to nbt bucket counters in shared memory with three CTAs per SM resident
     uint32_t cap0 = stage_cap(c, c->wide);
     const size_t tb = c->wide ? 32 : 16;
-    while (cap0 > (uint32_t)BLOCK * G && cap0 * tb + cap0 * 6 + (size_t)nbt * 12 > 98 * 1024) cap0 /= 2;
+    while (cap0 > (uint32_t)BLOCK * G && cap0 * tb + cap0 * 6 + (size_t)nbt * 12 > 68 * 1024) cap0 /= 2;
     if (cap0 == 0 || cap0 * tb + cap0 * 6 + (size_t)nbt * 12 > 150 * 1024) return set_err(DBG_ERR_STATE, "staged scatter not possible with %u buckets", nbt);
     if (ensure_opt_buffers(c) != DBG_OK) return DBG_ERR_CUDA;
+    if ((rc = table_ready(c, s))) return rc;        // (the partition kernel must not run beside the table clear: see build_device)
     CU_TRY(cudaMemcpyAsync(c->d_snap, c->d_counters, CNT_N * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     CU_TRY(cudaMemcpyAsync(c->d_snap + CNT_N, c->d_polyA, 8 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
     c->undo_reads = n_reads;
