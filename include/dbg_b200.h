@@ -155,7 +155,9 @@ int  dbg_insert_sliced_device(dbg_ctx *ctx, const void *d_tuples, uint64_t n, co
 int  dbg_exchange_scatter_opt_device(dbg_ctx *ctx, const char *d_bases, const uint64_t *d_offs, uint64_t n_reads, uint64_t first_base,
                                      uint64_t total_bases, uint64_t first_read_index, int32_t n_parts, void *const *d_dst_ptrs,
                                      uint64_t region_off, uint32_t cap_pair, uint32_t *d_fill, void *stream);
-/* PULL exchange: the source partitions its occurrences by (owner, table slice of the owner) into its OWN send buffer
+/* PULL exchange (owner = slot range of hash_code(kmer) % P: the reference's `kmer % threadNum` owner-computes split of
+ * thread_updatekmers, DBGgraph.cpp:148, lifted to GPUs): the source partitions its occurrences by (owner, table slice of
+ * the owner) into its OWN send buffer
  * (bucket = owner * n_slices + slice, n_slices from dbg_partition_info; region of `capb` tuples per bucket, capb a multiple of
  * 512; d_fill has n_parts * n_slices + 1 counters, the last one the overflow flag) -- one extraction pass, local stores only.
  * After the fill counters have been all-gathered, every owner inserts its buckets slice by slice and READS the sources'
@@ -233,7 +235,9 @@ int  dbg_get_stats(dbg_ctx *ctx, dbg_stats *stats);
 /* The KmerSet the reference's traversal consumes (kmerSet.h:88-99): array[P] in reference slot
  * layout (16-B nodes, or 32-B nodes on the wide path) and nul_flag[P/8+1], MSB first. */
 int  dbg_export_kmerset(dbg_ctx *ctx, void *array, uint8_t *nul_flag);
-/* build_debruijn_graph's tail in ONE call, for a front end that holds the LAST block of reads in host memory:
+/* build_debruijn_graph's tail (DBGgraph.cpp:383-430: the last parse_one_reads_file block, add_node_to_kmerset(PolyA), and the
+ * hand-over of `kset` to build_contig_sequence, main.cpp:204-207) in ONE call, for a front end that holds the LAST block of
+ * reads in host memory:
  *   dbg_submit_reads(bases, offs, n_reads) + dbg_finalize(stats) + dbg_export_kmerset(array, nul_flag)
  * -- same results, but pipelined where the block is large enough for the partitioned build: the copy of the reads, the
  * extraction, and then insert / reference layout / copy of the image run slice group by slice group, so the image is on
